@@ -1,0 +1,177 @@
+"""
+Seeded synthetic inputs shared by bench.py, the parity tests and tests/golden/make_golden.py.
+
+All generators use numpy.random.default_rng(seed) (PCG64) and int32/float32 arrays, so the CPU checker and the
+CUDA path see byte-identical inputs.  Pure NumPy; no device code.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# UCSC hg38.chrom.sizes, primary assembly (chr1..22, X, Y)
+HG38 = [
+    ("chr1", 248956422), ("chr2", 242193529), ("chr3", 198295559), ("chr4", 190214555), ("chr5", 181538259),
+    ("chr6", 170805979), ("chr7", 159345973), ("chr8", 145138636), ("chr9", 138394717), ("chr10", 133797422),
+    ("chr11", 135086622), ("chr12", 133275309), ("chr13", 114364328), ("chr14", 107043718), ("chr15", 101991189),
+    ("chr16", 90338345), ("chr17", 83257441), ("chr18", 80373285), ("chr19", 58617616), ("chr20", 64444167),
+    ("chr21", 46709983), ("chr22", 50818468), ("chrX", 156040895), ("chrY", 57227415),
+]
+HG38_NAMES = [c for c, _ in HG38]
+HG38_LENS = np.array([n for _, n in HG38], np.int64)
+
+
+def uniform_intervals(rng, n, G, max_len=2000):
+    """start ~ U[0, G-max_len), len ~ U{1..max_len}; returns int32 (start, end)."""
+    s = rng.integers(0, max(1, G - max_len), n, dtype=np.int64)
+    ln = rng.integers(1, max_len + 1, n, dtype=np.int64)
+    return s.astype(np.int32), (s + ln).astype(np.int32)
+
+
+# ---- C1: 10k vs 10k on one chromosome ---------------------------------------------------------------------------
+def c1_intervals(n=10_000, nq=10_000, G=1_000_000):
+    s, e = uniform_intervals(np.random.default_rng(1001), n, G)
+    qs, qe = uniform_intervals(np.random.default_rng(1002), nq, G)
+    return s, e, qs, qe
+
+
+def edge_sets(k=8, n=400, nq=300):
+    """Zero-length, inverted, duplicate and negative-coordinate intervals; reversed and empty queries."""
+    rng = np.random.default_rng(1003)
+    out = []
+    for _ in range(k):
+        G = int(rng.integers(5, 61))
+        s = rng.integers(-3, G + 1, n)
+        e = s + rng.integers(-2, 6, n)
+        qs = rng.integers(-5, G + 6, nq)
+        qe = qs + rng.integers(-3, 12, nq)
+        out.append(tuple(a.astype(np.int32) for a in (s, e, qs, qe)))
+    return out
+
+
+def neighbor_case(seed):
+    rng = np.random.default_rng(1100 + seed)
+    n = int(rng.integers(1, 300))
+    G = int(rng.integers(20, 5000))
+    s = rng.integers(0, G, n)
+    e = s + rng.integers(0, 40, n)
+    queries = [(int(rng.integers(-5, G + 50)), int(rng.integers(1, 6)), int(rng.choice([0, 1, 7, 60, 2500])))
+               for _ in range(40)]
+    return s.astype(np.int32), e.astype(np.int32), queries
+
+
+# ---- C2 / C4: hg38-shaped genome-wide interval sets ---------------------------------------------------------------
+def genome_intervals(n, seed, max_len=2000, chrom_lens=HG38_LENS):
+    """-> list over chromosomes of (start int32[], end int32[]); chromosome ~ multinomial(length)."""
+    rng = np.random.default_rng(seed)
+    counts = rng.multinomial(n, chrom_lens / chrom_lens.sum())
+    out = []
+    for L, c in zip(chrom_lens.tolist(), counts.tolist()):
+        out.append(uniform_intervals(rng, c, L, max_len))
+    return out
+
+
+# ---- bitsets ------------------------------------------------------------------------------------------------------
+def bitset_case(seed):
+    """-> size, granularity, ops, probes.  ops are tuples understood by apply_bitset_op."""
+    rng = np.random.default_rng(1200 + seed)
+    size = int(rng.integers(1, 5000))
+    gran = int(rng.choice([1, 2, 3, 7, 10, 64, 1024]))
+    ops = []
+    for _ in range(int(rng.integers(1, 30))):
+        k = int(rng.integers(0, 2))
+        op = int(rng.integers(0, 6))
+        if op == 0:
+            s = int(rng.integers(0, size))
+            c = int(rng.integers(0, min(size - s, max(1, size // 3)) + 1))
+            ops.append(("set_range", k, s, c))
+        elif op == 1:
+            ops.append(("set", k, int(rng.integers(0, size))))
+        elif op == 2:
+            ops.append(("clear", k, int(rng.integers(0, size))))
+        elif op == 3:
+            ops.append(("invert", k))
+        elif op == 4:
+            ops.append(("iand", k))
+        else:
+            ops.append(("ior", k))
+    probes = []
+    for _ in range(60):
+        s = int(rng.integers(0, size))
+        probes.append((s, int(rng.integers(0, size - s + 1))))
+    return size, gran, ops, probes
+
+
+def apply_bitset_op(b, op):
+    """b = [bitset0, bitset1] of any class exposing the BinnedBitSet API."""
+    name, k = op[0], op[1]
+    if name == "set_range":
+        b[k].set_range(op[2], op[3])
+    elif name == "set":
+        b[k].set(op[2])
+    elif name == "clear":
+        b[k].clear(op[2])
+    elif name == "invert":
+        b[k].invert()
+    elif name == "iand":
+        b[k].iand(b[1 - k])
+    elif name == "ior":
+        b[k].ior(b[1 - k])
+    else:
+        raise ValueError(name)
+
+
+def c3_case(size, nranges, seed, nq=2000, max_len=2000):
+    """Two range lists (start,count) for operands A and B plus nq count_range probes (start,count)."""
+    ra = np.random.default_rng(3000 + seed)
+    rb = np.random.default_rng(3100 + seed)
+    rq = np.random.default_rng(3200 + seed)
+
+    def ranges(r, n):
+        s = r.integers(0, size - max_len, n)
+        c = r.integers(1, max_len + 1, n)
+        return s.astype(np.int32), c.astype(np.int32)
+    return ranges(ra, nranges), ranges(rb, nranges), ranges(rq, nq)
+
+
+# ---- aggregate_scores_in_intervals ---------------------------------------------------------------------------------
+def aggregate_scores(rng, n):
+    """float32 N(0,1) with 1 % exact zeros and 1 % NaN."""
+    v = rng.normal(0.0, 1.0, n).astype(np.float32)
+    u = rng.random(n)
+    v[u < 0.01] = 0.0
+    v[(u >= 0.01) & (u < 0.02)] = np.nan
+    return v
+
+
+def aggregate_case(seed, n=3000, nw=400):
+    """-> origin, scores float32[n] (position origin+i), ws, we (absolute coords), mask_runs or None."""
+    rng = np.random.default_rng(5000 + seed)
+    origin = int(rng.integers(0, 1000))
+    v = aggregate_scores(rng, n)
+    if seed % 3 == 1:                       # large magnitudes: exercises float32 rounding order
+        v[rng.integers(0, n, 20)] = np.float32(16777216.0)
+    if seed % 3 == 2:
+        v *= np.float32(1e-3)
+    ws = rng.integers(max(0, origin - 30), origin + n + 10, nw)
+    we = ws + rng.integers(0, 60, nw)
+    mask_runs = None
+    if seed % 2 == 1:
+        ms = np.sort(rng.integers(origin, origin + n - 20, 40))
+        mask_runs = [(int(a), int(a + rng.integers(1, 20))) for a in ms]
+    return origin, v, ws.astype(np.int32), we.astype(np.int32), mask_runs
+
+
+def genome_scores(n_total, nw_total, seed, chrom_lens=HG38_LENS, mask_density=0.0):
+    """C5: per chromosome (origin, scores float32[], ws int32[], we int32[]); windows len ~ U{1..40}."""
+    rng = np.random.default_rng(seed)
+    frac = chrom_lens / chrom_lens.sum()
+    ns = rng.multinomial(n_total, frac)
+    nws = rng.multinomial(nw_total, frac)
+    out = []
+    for L, n, nw in zip(chrom_lens.tolist(), ns.tolist(), nws.tolist()):
+        origin = int(rng.integers(0, max(1, L - n)))
+        v = aggregate_scores(rng, n)
+        ws = rng.integers(origin, max(origin + 1, origin + n - 40), nw, dtype=np.int64)
+        we = ws + rng.integers(1, 41, nw, dtype=np.int64)
+        out.append((origin, v, ws.astype(np.int32), we.astype(np.int32)))
+    return out
