@@ -1,0 +1,57 @@
+"""
+Device form of the inner loop of ``scripts/aggregate_scores_in_intervals.py`` (:107-134).
+
+``ScoreTrack`` is the dense float32 score array of one chromosome (the role of ``BinnedArray``,
+lib/bx/binned_array.py:72-136: NaN where no score was set); ``aggregate`` reduces it over BED windows with the
+script's exact semantics: positions are visited left to right, a score is skipped when it is 0.0 (Python
+truthiness, :115), masked (:117-119) or NaN (:122); the running total is float32 (NumPy >= 2 scalar rules), and
+avg = total / count in float32.  Windows with no counted base yield count 0 and NaN avg/min/max (the script prints
+"nan").
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_i32, check, ptr
+from .bitset import _DeviceBits
+
+
+class ScoreTrack:
+    def __init__(self, scores, origin=0):
+        """scores[i] is the score of position origin + i (float32; NaN = unset)."""
+        v = np.ascontiguousarray(scores, np.float32)
+        self.n, self.origin = len(v), int(origin)
+        self._h = C.c_void_p()
+        check(_lib.lib().bxg_scores_create(ptr(v), len(v), self.origin, _lib.HOST, C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib._lib is not None:
+            _lib._lib.bxg_scores_free(h)
+            self._h = None
+
+    def aggregate(self, starts, ends, mask=None):
+        """-> dict(sum, avg, count, min, max) arrays, one entry per window [start, end)."""
+        ws, we = as_i32(starts), as_i32(ends)
+        nw = len(ws)
+        out = dict(sum=np.empty(nw, np.float32), avg=np.empty(nw, np.float32), count=np.empty(nw, np.int32),
+                   min=np.empty(nw, np.float32), max=np.empty(nw, np.float32))
+        mh = None
+        if mask is not None:
+            if not isinstance(mask, _DeviceBits):
+                raise TypeError("mask must be a bx_python_b200.bitset BitSet / BinnedBitSet")
+            mask._flush()
+            mh = mask._h
+        check(_lib.lib().bxg_aggregate(self._h, mh, ptr(ws), ptr(we), nw, _lib.HOST, ptr(out["sum"]), ptr(out["avg"]),
+                                      ptr(out["count"]), ptr(out["min"]), ptr(out["max"])))
+        return out
+
+
+def format_line(res, w):
+    """The three columns the script prints for window w (:126-134)."""
+    if res["count"][w] == 0:
+        return ["nan", "nan", "nan"]
+    return [str(np.float32(res[k][w])) for k in ("avg", "min", "max")]

@@ -1,0 +1,317 @@
+"""
+Drop-in for ``bx.bitset`` (``/root/reference/lib/bx/bitset.pyx``): ``BitSet``, ``BinnedBitSet``, ``MAX``.
+
+Same class / method names, argument meaning and exceptions (messages copied in spirit from bitset.pyx:78-100,
+177-192); every bit operation runs in CUDA kernels of libbxb200.so (csrc/bits.cu).  Scalar mutators are queued on
+the host and flushed as one batched kernel before the next read, because a kernel launch per ``set_range`` call
+would cost more than the reference's C call; bulk callers should use the array methods (``set_ranges``,
+``count_ranges``, ``runs``, ``and_count`` ...).
+
+``strict=True`` (default) reproduces the reference's ALL_ONE-sentinel ``count_range`` arithmetic
+(src/binBits.c:155,161) bit for bit; ``strict=False`` returns the true popcount.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_i32, check, ptr
+
+MAX_INT = 2147483647
+MAX = 512 * 1024 * 1024
+
+
+class _Pending:
+    """Host-side queue of scalar mutations, flushed in order (consecutive ops of one kind become one launch)."""
+
+    __slots__ = ("kind", "a", "b")
+
+    def __init__(self):
+        self.kind, self.a, self.b = None, [], []
+
+
+class _DeviceBits:
+    _kind = "BitSet"
+
+    def _create(self, size, granularity):
+        self._h = C.c_void_p()
+        check(_lib.lib().bxg_bits_create(int(size), int(granularity), C.byref(self._h)))
+        s, bs, nb = C.c_int32(), C.c_int32(), C.c_int32()
+        check(_lib.lib().bxg_bits_geometry(self._h, C.byref(s), C.byref(bs), C.byref(nb)))
+        self._size, self._bin_size, self._nbins = s.value, bs.value, nb.value
+        self._pend = _Pending()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib._lib is not None:
+            _lib._lib.bxg_bits_free(h)
+            self._h = None
+
+    # ---- queue -----------------------------------------------------------------------------------------------
+    def _queue(self, kind, a, b=None):
+        p = self._pend
+        if p.kind is not None and p.kind != kind:
+            self._flush()
+        p.kind = kind
+        p.a.append(a)
+        if b is not None:
+            p.b.append(b)
+        if len(p.a) >= 1 << 20:
+            self._flush()
+
+    def _flush(self):
+        p = self._pend
+        if p.kind is None:
+            return
+        L = _lib.lib()
+        a = np.asarray(p.a, np.int32)
+        if p.kind == "R":
+            b = np.asarray(p.b, np.int32)
+            check(L.bxg_bits_set_ranges(self._h, ptr(a), ptr(b), len(a), _lib.HOST))
+        else:
+            check(L.bxg_bits_set_bits(self._h, ptr(a), len(a), 1 if p.kind == "S" else 0, _lib.HOST))
+        _lib.sync()          # the staged host arrays must outlive the async copy
+        p.kind, p.a, p.b = None, [], []
+
+    # ---- checks (bitset.pyx:78-100 / 177-192) -----------------------------------------------------------------
+    def _check_index(self, index):
+        if index < 0:
+            raise IndexError("BitSet index (%d) must be non-negative." % index)
+        if index >= self._size:
+            raise IndexError("%d is larger than the size of this BitSet (%d)." % (index, self._size))
+
+    def _check_range_count(self, start, count):
+        self._check_index(start)
+        if count < 0:
+            raise IndexError("Count (%d) must be non-negative." % count)
+        if start + count > self._size:
+            if self._kind == "BinnedBitSet":
+                raise IndexError("End (%d) is larger than the size of this BinnedBitSet (%d)." % (start + count, self._size))
+            raise IndexError("End %d is larger than the size of this BitSet (%d)." % (start + count, self._size))
+
+    def _check_arrays(self, start, count):
+        """Vectorised form of _check_range_count for the batched entry points: first offender raises."""
+        if len(start) == 0:
+            return
+        s64, c64 = start.astype(np.int64), count.astype(np.int64)
+        bad = (s64 < 0) | (s64 >= self._size) | (c64 < 0) | (s64 + c64 > self._size)
+        if bad.any():
+            k = int(np.argmax(bad))
+            self._check_range_count(int(start[k]), int(count[k]))
+
+    def _check_same(self, other):
+        if not isinstance(other, type(self)):
+            raise TypeError("Argument 'other' has incorrect type (expected %s, got %s)" % (type(self).__name__, type(other).__name__))
+        if self._size != other._size:
+            raise ValueError("BitSets must have the same size")
+
+    # ---- shared API -------------------------------------------------------------------------------------------
+    @property
+    def size(self):
+        return self._size
+
+    def set(self, index):
+        self._check_index(index)
+        self._queue("S", int(index))
+
+    def clear(self, index):
+        self._check_index(index)
+        self._queue("C", int(index))
+
+    def set_range(self, start, count):
+        start, count = int(start), int(count)
+        self._check_range_count(start, count)
+        self._queue("R", start, count)
+
+    def _get(self, index):
+        self._check_index(index)
+        return int(self.get_many(np.array([index], np.int32))[0])
+
+    def __getitem__(self, index):
+        return self._get(index)
+
+    def invert(self):
+        self._flush()
+        check(_lib.lib().bxg_bits_not(self._h))
+
+    def _binop(self, other, fn):
+        self._check_same(other)
+        self._flush()
+        other._flush()
+        check(fn(self._h, other._h))
+
+    def iand(self, other):
+        self._binop(other, _lib.lib().bxg_bits_and)
+
+    def ior(self, other):
+        self._binop(other, _lib.lib().bxg_bits_or)
+
+    # ---- batched API (no reference equivalent; these are what bulk callers should use) -------------------------
+    def set_ranges(self, starts, counts):
+        """set_range for arrays of (start, count)."""
+        s, c = as_i32(starts), as_i32(counts)
+        self._check_arrays(s, c)
+        self._flush()
+        check(_lib.lib().bxg_bits_set_ranges(self._h, ptr(s), ptr(c), len(s), _lib.HOST))
+        _lib.sync()
+
+    def count_ranges(self, starts, counts, strict=True):
+        """count_range for arrays of (start, count) -> int32 array."""
+        s, c = as_i32(starts), as_i32(counts)
+        self._check_arrays(s, c)
+        self._flush()
+        out = np.empty(len(s), np.int32)
+        check(_lib.lib().bxg_bits_count_ranges(self._h, ptr(s), ptr(c), len(s), ptr(out), 1 if strict else 0, _lib.HOST))
+        return out
+
+    def get_many(self, positions):
+        p = as_i32(positions)
+        self._flush()
+        out = np.empty(len(p), np.uint8)
+        check(_lib.lib().bxg_bits_read(self._h, ptr(p), len(p), ptr(out), _lib.HOST))
+        return out
+
+    def count_all(self):
+        """True popcount of the whole bitmap."""
+        self._flush()
+        n = C.c_int64()
+        check(_lib.lib().bxg_bits_count_all(self._h, C.byref(n)))
+        return n.value
+
+    def and_count(self, other):
+        """self &= other and return the number of set bits of the result (one fused kernel)."""
+        self._check_same(other)
+        self._flush()
+        other._flush()
+        n = C.c_int64()
+        check(_lib.lib().bxg_bits_and_count(self._h, other._h, C.byref(n)))
+        return n.value
+
+    def runs(self):
+        """All maximal runs of set bits as (starts, ends) int32 arrays -- the next_set/next_clear idiom of
+        scripts/bed_intersect_basewise.py:30-38 / lib/bx/bitset_utils.py:34-43 in one call."""
+        self._flush()
+        n = C.c_int64()
+        check(_lib.lib().bxg_bits_runs_count(self._h, C.byref(n)))
+        rs, re = np.empty(n.value, np.int32), np.empty(n.value, np.int32)
+        check(_lib.lib().bxg_bits_runs_fetch(self._h, ptr(rs), ptr(re), n.value))
+        return rs, re
+
+    def _next(self, start, end, val):
+        self._flush()
+        out = C.c_int32()
+        check(_lib.lib().bxg_bits_next(self._h, int(start), int(end), val, C.byref(out)))
+        return out.value
+
+    def to_words(self):
+        """LSB-first uint64 words of the bitmap (test / interchange helper)."""
+        self._flush()
+        w = np.empty((self._size + 63) // 64, np.uint64)
+        check(_lib.lib().bxg_bits_export_words(self._h, ptr(w)))
+        return w
+
+    def from_words(self, words):
+        w = np.ascontiguousarray(words, np.uint64)
+        if len(w) != (self._size + 63) // 64:
+            raise ValueError("word count does not match size")
+        self._flush()
+        check(_lib.lib().bxg_bits_import_words(self._h, ptr(w)))
+
+
+class BitSet(_DeviceBits):
+    """bx.bitset.BitSet (bitset.pyx:107-173) on the device."""
+
+    _kind = "BitSet"
+
+    def __init__(self, bitCount):
+        if bitCount > MAX_INT:
+            raise ValueError("%d is larger than the maximum BitSet size of %d." % (bitCount, MAX_INT))
+        self._create(bitCount, 0)
+
+    def get(self, index):
+        return self._get(index)
+
+    def clone(self):
+        other = BitSet(self._size)
+        other.ior(self)
+        return other
+
+    def count_range(self, start=0, count=None):
+        if count is None:
+            count = self._size - start
+        self._check_range_count(start, count)
+        return int(self.count_ranges(np.array([start], np.int32), np.array([count], np.int32))[0])
+
+    def _check_range(self, start, end):
+        self._check_index(start)
+        if end < start:
+            raise IndexError("Range end (%d) must be greater than range start(%d)." % (end, start))
+        if end > self._size:
+            raise IndexError("End %d is larger than the size of this BitSet (%d)." % (end, self._size))
+
+    def next_set(self, start, end=None):
+        if end is None:
+            end = self._size
+        self._check_range(start, end)
+        return self._next(start, end, 1)
+
+    def next_clear(self, start, end=None):
+        if end is None:
+            end = self._size
+        self._check_range(start, end)
+        return self._next(start, end, 0)
+
+    def ixor(self, other):
+        self._binop(other, _lib.lib().bxg_bits_xor)
+
+    def __iand__(self, other):
+        self.iand(other)
+        return self
+
+    def __ior__(self, other):
+        self.ior(other)
+        return self
+
+    def __invert__(self):
+        self.invert()
+        return self
+
+
+class BinnedBitSet(_DeviceBits):
+    """bx.bitset.BinnedBitSet (bitset.pyx:198-241 over src/binBits.c) on the device."""
+
+    _kind = "BinnedBitSet"
+
+    def __init__(self, size=MAX, granularity=1024, strict=True):
+        if size > MAX_INT:
+            raise ValueError("%d is larger than the maximum BinnedBitSet size of %d." % (size, MAX_INT))
+        self._strict = bool(strict)
+        self._create(size, granularity)
+
+    @property
+    def bin_size(self):
+        return self._bin_size
+
+    def count_range(self, start, count):
+        self._check_range_count(start, count)
+        return int(self.count_ranges(np.array([start], np.int32), np.array([count], np.int32), self._strict)[0])
+
+    def count_ranges(self, starts, counts, strict=None):
+        return super().count_ranges(starts, counts, self._strict if strict is None else strict)
+
+    def next_set(self, start):
+        self._check_index(start)
+        return self._next(start, self._size, 1)
+
+    def next_clear(self, start):
+        self._check_index(start)
+        return self._next(start, self._size, 0)
+
+    def bin_states(self):
+        """uint8 per bin: 0 ALL_ZERO sentinel, 1 ALL_ONE sentinel, 2 allocated (src/binBits.c:5-6)."""
+        self._flush()
+        out = np.empty(self._nbins, np.uint8)
+        check(_lib.lib().bxg_bits_states(self._h, ptr(out)))
+        return out

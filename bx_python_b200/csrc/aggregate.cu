@@ -1,0 +1,123 @@
+// aggregate.cu -- the per-base inner loop of scripts/aggregate_scores_in_intervals.py:107-134 as one kernel.
+//
+// One thread per window walks its positions left to right (the float32 sum is order-dependent and must match the
+// reference's sequential `total += score`), skipping score == 0.0 (:115 truthiness), masked bases (:117-119) and NaN
+// (:122).  Scores are a dense float32 array (NaN = unset, lib/bx/binned_array.py:73,89-94); the mask is a dense
+// LSB-first bitmap (bits.cu).
+#include <math.h>
+
+#include "common.cuh"
+
+using namespace bxg;
+
+struct bxg_bits;
+const uint64_t *bxg_bits_words_internal(const bxg_bits *b);
+int32_t bxg_bits_size_internal(const bxg_bits *b);
+
+struct bxg_scores {
+    float *v = nullptr;
+    int64_t n = 0;
+    int32_t origin = 0;
+    bool owned = true;
+};
+
+__global__ void __launch_bounds__(256)
+k_aggregate(const float *__restrict__ v, int64_t n, int64_t origin, const uint64_t *__restrict__ mask, int64_t mask_size,
+            const int32_t *__restrict__ ws, const int32_t *__restrict__ we, int64_t nw,
+            float *__restrict__ sum, float *__restrict__ avg, int32_t *__restrict__ cnt, float *__restrict__ mn,
+            float *__restrict__ mx) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += stride) {
+        int64_t a = (int64_t)__ldg(ws + w) - origin, b = (int64_t)__ldg(we + w) - origin;
+        const int64_t shift = origin;
+        if (a < 0) a = 0;                 // positions without a score read as NaN -> skipped
+        if (b > n) b = n;
+        float total = 0.0f, lo = 100000000.0f, hi = -100000000.0f;   // script sentinels (:112-113), exact in float32
+        int32_t c = 0;
+        for (int64_t i = a; i < b; i++) {
+            float s = __ldg(v + i);
+            if (s == 0.0f || s != s) continue;
+            if (mask) {
+                int64_t p = i + shift;
+                if (p < mask_size && ((__ldg((const unsigned long long *)mask + (p >> 6)) >> (p & 63)) & 1ull)) continue;
+            }
+            total = __fadd_rn(total, s);  // strict left-to-right float32 (no fma contraction possible, but be explicit)
+            c++;
+            hi = s > hi ? s : hi;
+            lo = s < lo ? s : lo;
+        }
+        cnt[w] = c;
+        sum[w] = total;
+        if (c > 0) {
+            avg[w] = __fdiv_rn(total, (float)c);
+            mn[w] = lo;
+            mx[w] = hi;
+        } else {
+            const float qnan = __int_as_float(0x7fc00000);
+            avg[w] = qnan;
+            mn[w] = qnan;
+            mx[w] = qnan;
+        }
+    }
+}
+
+extern "C" {
+
+int bxg_scores_create(const float *scores, int64_t n, int32_t origin, int loc, bxg_scores_t **out) {
+    BXG_TRY(ensure_init());
+    if (!out || n < 0) return set_error(BXG_ERR_ARG, "bad arguments");
+    bxg_scores *s = new bxg_scores();
+    s->n = n;
+    s->origin = origin;
+    BXG_CUDA(cudaMalloc(&s->v, (size_t)(n > 0 ? n : 1) * 4));
+    if (n)
+        BXG_CUDA(cudaMemcpyAsync(s->v, scores, (size_t)n * 4,
+                                 loc == BXG_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx().stream));
+    if (loc == BXG_HOST) BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    *out = s;
+    return BXG_OK;
+}
+
+int bxg_scores_free(bxg_scores_t *s) {
+    if (!s) return BXG_OK;
+    cudaStreamSynchronize(ctx().stream);
+    cudaFree(s->v);
+    delete s;
+    return BXG_OK;
+}
+
+int bxg_aggregate(const bxg_scores_t *s, const bxg_bits_t *mask, const int32_t *ws, const int32_t *we, int64_t nw,
+                  int loc, float *sum, float *avg, int32_t *count, float *mn, float *mx) {
+    if (!s) return set_error(BXG_ERR_ARG, "null scores handle");
+    if (nw <= 0) return BXG_OK;
+    Context &c = ctx();
+    const void *dws, *dwe;
+    BXG_TRY(stage_in(0, ws, (size_t)nw * 4, loc, &dws));
+    BXG_TRY(stage_in(1, we, (size_t)nw * 4, loc, &dwe));
+    float *dsum = sum, *davg = avg, *dmn = mn, *dmx = mx;
+    int32_t *dcnt = count;
+    if (loc == BXG_HOST) {
+        void *o;
+        BXG_TRY(scratch(2, (size_t)nw * 20, &o));
+        dsum = (float *)o;
+        davg = dsum + nw;
+        dmn = davg + nw;
+        dmx = dmn + nw;
+        dcnt = (int32_t *)(dmx + nw);
+    }
+    BXG_LAUNCH(k_aggregate, grid_for(cdiv(nw, 256), 8), 256, 0, s->v, s->n, (int64_t)s->origin,
+               bxg_bits_words_internal((const bxg_bits *)mask), (int64_t)bxg_bits_size_internal((const bxg_bits *)mask),
+               (const int32_t *)dws, (const int32_t *)dwe, nw, dsum, davg, dcnt, dmn, dmx);
+    if (loc == BXG_HOST) {
+        cudaStream_t st = c.stream;
+        BXG_CUDA(cudaMemcpyAsync(sum, dsum, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        BXG_CUDA(cudaMemcpyAsync(avg, davg, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        BXG_CUDA(cudaMemcpyAsync(mn, dmn, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        BXG_CUDA(cudaMemcpyAsync(mx, dmx, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        BXG_CUDA(cudaMemcpyAsync(count, dcnt, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        BXG_CUDA(cudaStreamSynchronize(st));
+    }
+    return BXG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,721 @@
+// bits.cu -- BinnedBitSet / BitSet kernels: uint64 bit-parallel set algebra, popcount, rank table, run extraction.
+//
+// HBM layout (DESIGN.md "bitsets"): dense LSB-first uint64 words over [0,size) -- tail bits of the last word and the
+// padding words up to a 32-byte multiple are kept zero -- plus uint8 state[nbins] tracking the reference's lazy-bin
+// state machine (src/binBits.c:5-6; transitions :67-128,:230-317).  All word kernels are state-oblivious; the state
+// only feeds the strict count_range correction (binBits.c:155,161).
+#include <cub/cub.cuh>
+#include <math.h>
+
+#include "common.cuh"
+
+using namespace bxg;
+
+enum : uint8_t { BZ = 0, BO = 1, BA = 2 };
+
+struct bxg_bits {
+    int32_t size = 0, bin_size = 0, nbins = 0, flat = 0;
+    int64_t nwords = 0;        // ceil(size/64)
+    int64_t nwords_alloc = 0;  // nwords rounded up to a multiple of 4 (32 B)
+    uint64_t *words = nullptr;
+    uint8_t *state = nullptr;
+    uint32_t *rank = nullptr;  // exclusive prefix popcount per word, nwords_alloc+1 entries (lazy)
+    bool rank_valid = false;
+    int32_t *run_s = nullptr, *run_e = nullptr;  // run extraction output (device)
+    int64_t run_cap = 0, nruns = -1;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum -> one atomicAdd per CTA (warp __popcll partials, shuffle tree, smem across warps)
+__device__ __forceinline__ void block_accumulate(unsigned long long v, unsigned long long *out) {
+    __shared__ unsigned long long s_part[32];
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_part[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        v = lane < nw ? s_part[lane] : 0ull;
+        v = warp_sum(v);
+        if (lane == 0 && v) atomicAdd(out, v);
+    }
+}
+
+__device__ __forceinline__ ulonglong2 ld_stream(const ulonglong2 *p) {   // read-once operand: non-coherent, no L1 allocate
+    ulonglong2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ ulonglong2 ld_rw(const ulonglong2 *p) {       // in-place operand: coherent path, evict-first
+    ulonglong2 r;
+    asm volatile("ld.global.cs.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(ulonglong2 *p, ulonglong2 v) {
+    asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// a op= b (and / or / xor), optional fused popcount; also applies the per-bin sentinel algebra to state[]
+// ------------------------------------------------------------------------------------------------------------------
+enum { OP_AND = 0, OP_OR = 1, OP_XOR = 2 };
+
+template <int OP>
+__device__ __forceinline__ unsigned long long apply(unsigned long long a, unsigned long long b) {
+    return OP == OP_AND ? (a & b) : OP == OP_OR ? (a | b) : (a ^ b);
+}
+
+// binBits.c:230-296 restated on the state byte
+template <int OP>
+__device__ __forceinline__ uint8_t state_op(uint8_t a, uint8_t b) {
+    if (OP == OP_AND) {
+        if (a == BZ) return BZ;
+        if (b == BZ) return BZ;
+        if (b == BO) return a;
+        return BA;                       // a in {O,A}, b == A : clone or byte-and
+    } else if (OP == OP_OR) {
+        if (a == BO) return BO;
+        if (b == BO) return BO;
+        if (b == BZ) return a;
+        return BA;
+    }
+    return BA;
+}
+
+constexpr int BINOP_THREADS = 256;
+constexpr int BINOP_UNROLL = 4;
+
+template <int OP, bool COUNT>
+__global__ void __launch_bounds__(BINOP_THREADS)
+k_binop(ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b, int64_t nvec,
+        uint8_t *__restrict__ sa, const uint8_t *__restrict__ sb, int nbins, unsigned long long *count) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long pc = 0;
+    int64_t i = tid;
+    for (; i + (BINOP_UNROLL - 1) * stride < nvec; i += BINOP_UNROLL * stride) {
+        ulonglong2 va[BINOP_UNROLL], vb[BINOP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BINOP_UNROLL; u++) {
+            va[u] = ld_rw(a + i + u * stride);
+            vb[u] = ld_stream(b + i + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < BINOP_UNROLL; u++) {
+            va[u].x = apply<OP>(va[u].x, vb[u].x);
+            va[u].y = apply<OP>(va[u].y, vb[u].y);
+            if (COUNT) pc += __popcll(va[u].x) + __popcll(va[u].y);
+            st_stream(a + i + u * stride, va[u]);
+        }
+    }
+    for (; i < nvec; i += stride) {
+        ulonglong2 va = ld_rw(a + i), vb = ld_stream(b + i);
+        va.x = apply<OP>(va.x, vb.x);
+        va.y = apply<OP>(va.y, vb.y);
+        if (COUNT) pc += __popcll(va.x) + __popcll(va.y);
+        st_stream(a + i, va);
+    }
+    if (sa != nullptr)
+        for (int64_t k = tid; k < nbins; k += stride) sa[k] = state_op<OP>(sa[k], sb[k]);
+    if (COUNT) block_accumulate(pc, count);
+}
+
+// a = ~a over [0,size); tail bits stay zero; state: Z <-> O (binBits.c:298-317)
+__global__ void __launch_bounds__(BINOP_THREADS)
+k_not(ulonglong2 *__restrict__ a, int64_t nvec, int64_t nwords, uint64_t tail_mask, uint8_t *__restrict__ sa, int nbins) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        ulonglong2 v = ld_rw(a + i);
+        v.x = ~v.x;
+        v.y = ~v.y;
+        int64_t w = 2 * i;
+        if (w + 1 >= nwords - 1) {     // touches the last real word or padding
+            if (w == nwords - 1) v.x &= tail_mask; else if (w >= nwords) v.x = 0;
+            if (w + 1 == nwords - 1) v.y &= tail_mask; else if (w + 1 >= nwords) v.y = 0;
+        }
+        st_stream(a + i, v);
+    }
+    if (sa != nullptr)
+        for (int64_t k = tid; k < nbins; k += stride) {
+            uint8_t s = sa[k];
+            sa[k] = s == BZ ? BO : s == BO ? BZ : BA;
+        }
+}
+
+__global__ void __launch_bounds__(BINOP_THREADS)
+k_popcount(const ulonglong2 *__restrict__ a, int64_t nvec, unsigned long long *count) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long pc = 0;
+    int64_t i = tid;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        ulonglong2 v0 = ld_stream(a + i), v1 = ld_stream(a + i + stride), v2 = ld_stream(a + i + 2 * stride),
+                   v3 = ld_stream(a + i + 3 * stride);
+        pc += __popcll(v0.x) + __popcll(v0.y) + __popcll(v1.x) + __popcll(v1.y) + __popcll(v2.x) + __popcll(v2.y) +
+              __popcll(v3.x) + __popcll(v3.y);
+    }
+    for (; i < nvec; i += stride) {
+        ulonglong2 v = ld_stream(a + i);
+        pc += __popcll(v.x) + __popcll(v.y);
+    }
+    block_accumulate(pc, count);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// set_range x n  (binBits.c:98-128): one lane per range for the two edge words (64-bit atomicOr), the whole warp
+// sweeps each lane's interior words with coalesced stores of ~0.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_set_ranges(uint64_t *__restrict__ words, uint8_t *__restrict__ state, int bin_size, int flat,
+             const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp0 * 32; base < n; base += nwarps * 32) {
+        int64_t i = base + lane;
+        int64_t mb = 0, me = 0;
+        if (i < n) {
+            int32_t s = __ldg(start + i), c = __ldg(count + i);
+            if (c > 0) {
+                int32_t last = s + c - 1;
+                int64_t w0 = s >> 6, w1 = last >> 6;
+                unsigned long long m0 = ~0ull << (s & 63), m1 = ~0ull >> (63 - (last & 63));
+                if (w0 == w1) {
+                    atomicOr((unsigned long long *)words + w0, m0 & m1);
+                } else {
+                    atomicOr((unsigned long long *)words + w0, m0);
+                    atomicOr((unsigned long long *)words + w1, m1);
+                }
+                if (!flat) {
+                    int b1 = last / bin_size;
+                    for (int b = s / bin_size; b <= b1; b++)
+                        if (state[b] == BZ) state[b] = BA;     // benign race: every writer stores BA
+                }
+                mb = w0 + 1;
+                me = w1;
+            }
+        }
+        unsigned has = __ballot_sync(0xffffffffu, me > mb);
+        while (has) {
+            int src = __ffs(has) - 1;
+            has &= has - 1;
+            int64_t b = __shfl_sync(0xffffffffu, mb, src), e = __shfl_sync(0xffffffffu, me, src);
+            for (int64_t w = b + lane; w < e; w += 32) words[w] = ~0ull;
+        }
+    }
+}
+
+// set / clear single bits (binBits.c:67-96)
+__global__ void k_set_bits(uint64_t *__restrict__ words, uint8_t *__restrict__ state, int bin_size, int flat,
+                           const int32_t *__restrict__ pos, int64_t n, int value) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t p = pos[i];
+        unsigned long long m = 1ull << (p & 63);
+        if (value) {
+            atomicOr((unsigned long long *)words + (p >> 6), m);
+            if (!flat && state[p / bin_size] == BZ) state[p / bin_size] = BA;
+        } else {
+            atomicAnd((unsigned long long *)words + (p >> 6), ~m);
+            if (!flat && state[p / bin_size] == BO) state[p / bin_size] = BA;
+        }
+    }
+}
+
+__global__ void k_read_bits(const uint64_t *__restrict__ words, const int32_t *__restrict__ pos, int64_t n,
+                            uint8_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t p = pos[i];
+        out[i] = (uint8_t)((words[p >> 6] >> (p & 63)) & 1ull);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// count_range x n  (binBits.c:130-178): rank table lookup, O(1) per query
+// ------------------------------------------------------------------------------------------------------------------
+struct PopcWord {
+    const uint64_t *w;
+    int64_t n;
+    __device__ __forceinline__ uint32_t operator()(int64_t i) const { return i < n ? (uint32_t)__popcll(w[i]) : 0u; }
+};
+
+__device__ __forceinline__ uint32_t rank_at(const uint64_t *__restrict__ words, const uint32_t *__restrict__ rank, uint32_t p) {
+    uint32_t w = p >> 6, r = __ldg(rank + w), b = p & 63;
+    if (b) r += (uint32_t)__popcll(__ldg((const unsigned long long *)words + w) & ((1ull << b) - 1ull));
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_count_ranges(const uint64_t *__restrict__ words, const uint32_t *__restrict__ rank, const uint8_t *__restrict__ state,
+               int bin_size, int strict, const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n,
+               int32_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t s = __ldg(start + i), c = __ldg(count + i), r = 0;
+        if (c > 0) {
+            r = (int32_t)(rank_at(words, rank, (uint32_t)s + (uint32_t)c) - rank_at(words, rank, (uint32_t)s));
+            // binBits.c:155,161: an ALL_ONE *sentinel* first bin contributes (k - offset) instead of k
+            if (strict && state[s / bin_size] == BO) r -= s % bin_size;
+        }
+        out[i] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// next_set / next_clear  (binBits.c:180-228, bits.c:143-190): first p in [start,end) with bit == val, else end
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_next(const uint64_t *__restrict__ words, int64_t start, int64_t end, int val, unsigned long long *result) {
+    const int64_t w0 = start >> 6, w1 = (end - 1) >> 6;   // end > start guaranteed by the caller
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = w0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w <= w1; w += stride) {
+        if ((unsigned long long)(w << 6) >= *(volatile unsigned long long *)result) break;   // someone found an earlier one
+        unsigned long long x = words[w];
+        if (!val) x = ~x;
+        if (w == w0) x &= ~0ull << (start & 63);
+        if (w == w1 && (end & 63)) x &= (1ull << (end & 63)) - 1ull;
+        if (x) atomicMin(result, (unsigned long long)((w << 6) + __ffsll((long long)x) - 1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// run extraction: transition bits t = w ^ (w<<1 | carry); transitions alternate run start / run end.
+// pass A counts transitions per CTA tile, a device scan turns them into offsets, pass B writes positions in order.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int RUN_THREADS = 256;
+constexpr int RUN_WPT = 4;                       // words per thread (32 B contiguous)
+constexpr int RUN_TILE = RUN_THREADS * RUN_WPT;  // words per CTA
+
+__device__ __forceinline__ void load_transitions(const uint64_t *__restrict__ words, int64_t nwords_alloc, int64_t w,
+                                                 unsigned long long t[RUN_WPT]) {
+    unsigned long long v[RUN_WPT];
+    unsigned long long prev = 0;
+    if (w < nwords_alloc) {
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(words + w);
+        ulonglong2 a = __ldg(p), b = __ldg(p + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        if (w > 0) prev = __ldg((const unsigned long long *)words + w - 1);
+    } else {
+        v[0] = v[1] = v[2] = v[3] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < RUN_WPT; k++) {
+        t[k] = v[k] ^ ((v[k] << 1) | (prev >> 63));
+        prev = v[k];
+    }
+}
+
+__global__ void __launch_bounds__(RUN_THREADS)
+k_runs_count(const uint64_t *__restrict__ words, int64_t nwords_alloc, uint32_t *__restrict__ tile_count) {
+    typedef cub::BlockReduce<uint32_t, RUN_THREADS> BR;
+    __shared__ typename BR::TempStorage tmp;
+    int64_t w = ((int64_t)blockIdx.x * RUN_THREADS + threadIdx.x) * RUN_WPT;
+    unsigned long long t[RUN_WPT];
+    load_transitions(words, nwords_alloc, w, t);
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < RUN_WPT; k++) c += __popcll(t[k]);
+    uint32_t tot = BR(tmp).Sum(c);
+    if (threadIdx.x == 0) tile_count[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(RUN_THREADS)
+k_runs_fill(const uint64_t *__restrict__ words, int64_t nwords_alloc, const uint32_t *__restrict__ tile_offset,
+            int32_t *__restrict__ run_s, int32_t *__restrict__ run_e) {
+    typedef cub::BlockScan<uint32_t, RUN_THREADS> BS;
+    __shared__ typename BS::TempStorage tmp;
+    int64_t w = ((int64_t)blockIdx.x * RUN_THREADS + threadIdx.x) * RUN_WPT;
+    unsigned long long t[RUN_WPT];
+    load_transitions(words, nwords_alloc, w, t);
+    uint32_t c = 0, off;
+#pragma unroll
+    for (int k = 0; k < RUN_WPT; k++) c += __popcll(t[k]);
+    BS(tmp).ExclusiveSum(c, off);
+    off += tile_offset[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < RUN_WPT; k++) {
+        unsigned long long x = t[k];
+        while (x) {
+            int b = __ffsll((long long)x) - 1;
+            x &= x - 1;
+            int32_t p = (int32_t)(((w + k) << 6) + b);
+            if (off & 1) run_e[off >> 1] = p; else run_s[off >> 1] = p;
+            off++;
+        }
+    }
+}
+
+__global__ void k_fill_u8(uint8_t *p, int64_t n, uint8_t v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+__global__ void k_mask_tail(uint64_t *words, int64_t nwords, int64_t nwords_alloc, uint64_t tail_mask) {
+    int64_t i = nwords - 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == nwords - 1) words[i] &= tail_mask; else if (i < nwords_alloc) words[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ------------------------------------------------------------------------------------------------------------------
+static inline uint64_t tail_mask_of(int32_t size) { return (size & 63) ? ((1ull << (size & 63)) - 1ull) : ~0ull; }
+static inline int stream_grid(int64_t nvec, int unroll) {
+    return grid_for(cdiv(nvec, (int64_t)BINOP_THREADS * unroll), 8);
+}
+
+static int check_pair(const bxg_bits *a, const bxg_bits *b) {
+    if (!a || !b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (a->size != b->size) return set_error(BXG_ERR_MISMATCH, "BitSets must have the same size");
+    if (a->flat != b->flat || a->bin_size != b->bin_size)
+        return set_error(BXG_ERR_MISMATCH, "bitsets have different bin geometry (%d vs %d)", a->bin_size, b->bin_size);
+    return BXG_OK;
+}
+
+static void invalidate(bxg_bits *b) {
+    b->rank_valid = false;
+    b->nruns = -1;
+}
+
+template <int OP, bool COUNT>
+static int binop(bxg_bits *a, const bxg_bits *b, unsigned long long *d_count) {
+    int64_t nvec = a->nwords_alloc / 2;
+    BXG_LAUNCH((k_binop<OP, COUNT>), stream_grid(nvec, BINOP_UNROLL), BINOP_THREADS, 0,
+               (ulonglong2 *)a->words, (const ulonglong2 *)b->words, nvec,
+               a->flat ? nullptr : a->state, b->state, a->nbins, d_count);
+    invalidate(a);
+    return BXG_OK;
+}
+
+extern "C" {
+
+int bxg_bits_create(int32_t size, int32_t granularity, bxg_bits_t **out) {
+    BXG_TRY(ensure_init());
+    if (!out) return set_error(BXG_ERR_ARG, "out is null");
+    if (size <= 0) return set_error(BXG_ERR_ARG, "bitset size must be in [1, 2^31-1], got %d", size);
+    if (granularity < 0) return set_error(BXG_ERR_ARG, "granularity must be >= 0");
+    bxg_bits *b = new bxg_bits();
+    b->size = size;
+    if (granularity == 0) {
+        b->flat = 1;
+        b->bin_size = size;
+        b->nbins = 1;
+    } else {
+        // binBits.c:8-17 -- float32 division, double ceil
+        b->bin_size = (int32_t)ceil(size / (float)granularity);
+        b->nbins = (int32_t)ceil(size / (float)b->bin_size);
+        // the reference would index past its bins array if float rounding made nbins*bin_size < size (UB there);
+        // keep our state[] large enough for every position instead
+        int64_t need = ((int64_t)size + b->bin_size - 1) / b->bin_size;
+        if (need > b->nbins) b->nbins = (int32_t)need;
+    }
+    b->nwords = ((int64_t)size + 63) >> 6;
+    b->nwords_alloc = (b->nwords + 3) & ~3ll;
+    Context &c = ctx();
+    cudaError_t e = cudaMalloc(&b->words, (size_t)b->nwords_alloc * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&b->state, (size_t)b->nbins);
+    if (e != cudaSuccess) {
+        cudaFree(b->words);
+        delete b;
+        return set_error(BXG_ERR_CUDA, "cudaMalloc(bitset %d bits) failed: %s", size, cudaGetErrorString(e));
+    }
+    BXG_CUDA(cudaMemsetAsync(b->words, 0, (size_t)b->nwords_alloc * 8, c.stream));
+    BXG_CUDA(cudaMemsetAsync(b->state, BZ, (size_t)b->nbins, c.stream));
+    *out = b;
+    return BXG_OK;
+}
+
+int bxg_bits_free(bxg_bits_t *b) {
+    if (!b) return BXG_OK;
+    cudaStreamSynchronize(ctx().stream);
+    cudaFree(b->words);
+    cudaFree(b->state);
+    cudaFree(b->rank);
+    cudaFree(b->run_s);
+    cudaFree(b->run_e);
+    delete b;
+    return BXG_OK;
+}
+
+int bxg_bits_geometry(const bxg_bits_t *b, int32_t *size, int32_t *bin_size, int32_t *nbins) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (size) *size = b->size;
+    if (bin_size) *bin_size = b->bin_size;
+    if (nbins) *nbins = b->nbins;
+    return BXG_OK;
+}
+
+int bxg_bits_clone(const bxg_bits_t *b, bxg_bits_t **out) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    bxg_bits *n = new bxg_bits();
+    n->size = b->size; n->bin_size = b->bin_size; n->nbins = b->nbins; n->flat = b->flat;
+    n->nwords = b->nwords; n->nwords_alloc = b->nwords_alloc;
+    BXG_CUDA(cudaMalloc(&n->words, (size_t)n->nwords_alloc * 8));
+    BXG_CUDA(cudaMalloc(&n->state, (size_t)n->nbins));
+    BXG_CUDA(cudaMemcpyAsync(n->words, b->words, (size_t)n->nwords_alloc * 8, cudaMemcpyDeviceToDevice, ctx().stream));
+    BXG_CUDA(cudaMemcpyAsync(n->state, b->state, (size_t)n->nbins, cudaMemcpyDeviceToDevice, ctx().stream));
+    *out = n;
+    return BXG_OK;
+}
+
+int bxg_bits_set_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *count, int64_t n, int loc) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (n <= 0) return BXG_OK;
+    const void *ds, *dc;
+    BXG_TRY(stage_in(0, start, (size_t)n * 4, loc, &ds));
+    BXG_TRY(stage_in(1, count, (size_t)n * 4, loc, &dc));
+    BXG_LAUNCH(k_set_ranges, grid_for(cdiv(n, 256), 8), 256, 0, b->words, b->state, b->bin_size, b->flat,
+               (const int32_t *)ds, (const int32_t *)dc, n);
+    invalidate(b);
+    if (loc == BXG_HOST) BXG_CUDA(cudaStreamSynchronize(ctx().stream));   // caller may reuse its arrays on return
+    return BXG_OK;
+}
+
+int bxg_bits_set_bits(bxg_bits_t *b, const int32_t *pos, int64_t n, int value, int loc) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (n <= 0) return BXG_OK;
+    const void *dp;
+    BXG_TRY(stage_in(0, pos, (size_t)n * 4, loc, &dp));
+    BXG_LAUNCH(k_set_bits, grid_for(cdiv(n, 256), 8), 256, 0, b->words, b->state, b->bin_size, b->flat,
+               (const int32_t *)dp, n, value);
+    invalidate(b);
+    if (loc == BXG_HOST) BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    return BXG_OK;
+}
+
+int bxg_bits_read(const bxg_bits_t *b, const int32_t *pos, int64_t n, uint8_t *out, int loc) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (n <= 0) return BXG_OK;
+    const void *dp;
+    BXG_TRY(stage_in(0, pos, (size_t)n * 4, loc, &dp));
+    uint8_t *dout = out;
+    if (loc == BXG_HOST) {
+        void *t;
+        BXG_TRY(scratch(1, (size_t)n, &t));
+        dout = (uint8_t *)t;
+    }
+    BXG_LAUNCH(k_read_bits, grid_for(cdiv(n, 256), 8), 256, 0, b->words, (const int32_t *)dp, n, dout);
+    if (loc == BXG_HOST) {
+        BXG_CUDA(cudaMemcpyAsync(out, dout, (size_t)n, cudaMemcpyDeviceToHost, ctx().stream));
+        BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
+    return BXG_OK;
+}
+
+int bxg_bits_and(bxg_bits_t *a, const bxg_bits_t *b) {
+    BXG_TRY(check_pair(a, b));
+    if (a == b) return BXG_OK;              // x & x == x, states unchanged
+    return binop<OP_AND, false>(a, b, nullptr);
+}
+int bxg_bits_or(bxg_bits_t *a, const bxg_bits_t *b) {
+    BXG_TRY(check_pair(a, b));
+    if (a == b) return BXG_OK;
+    return binop<OP_OR, false>(a, b, nullptr);
+}
+int bxg_bits_xor(bxg_bits_t *a, const bxg_bits_t *b) {
+    BXG_TRY(check_pair(a, b));
+    if (a == b) {                           // x ^ x == 0 (the in-place kernel must not alias its read-only operand)
+        BXG_CUDA(cudaMemsetAsync(a->words, 0, (size_t)a->nwords_alloc * 8, ctx().stream));
+        invalidate(a);
+        return BXG_OK;
+    }
+    return binop<OP_XOR, false>(a, b, nullptr);
+}
+
+int bxg_bits_not(bxg_bits_t *a) {
+    if (!a) return set_error(BXG_ERR_ARG, "null bitset handle");
+    int64_t nvec = a->nwords_alloc / 2;
+    BXG_LAUNCH(k_not, stream_grid(nvec, 1), BINOP_THREADS, 0, (ulonglong2 *)a->words, nvec, a->nwords,
+               tail_mask_of(a->size), a->flat ? nullptr : a->state, a->nbins);
+    invalidate(a);
+    return BXG_OK;
+}
+
+static int fetch_counter(int64_t *out) {
+    Context &c = ctx();
+    BXG_CUDA(cudaMemcpyAsync(c.mailbox, c.d_mailbox, 8, cudaMemcpyDeviceToHost, c.stream));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    *out = c.mailbox[0];
+    return BXG_OK;
+}
+
+int bxg_bits_and_count(bxg_bits_t *a, const bxg_bits_t *b, int64_t *count) {
+    BXG_TRY(check_pair(a, b));
+    if (a == b) return bxg_bits_count_all(a, count);
+    Context &c = ctx();
+    BXG_CUDA(cudaMemsetAsync(c.d_mailbox, 0, 8, c.stream));
+    BXG_TRY((binop<OP_AND, true>(a, b, (unsigned long long *)c.d_mailbox)));
+    if (count) BXG_TRY(fetch_counter(count));
+    return BXG_OK;
+}
+
+int bxg_bits_count_all(const bxg_bits_t *b, int64_t *count) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    Context &c = ctx();
+    int64_t nvec = b->nwords_alloc / 2;
+    BXG_CUDA(cudaMemsetAsync(c.d_mailbox, 0, 8, c.stream));
+    BXG_LAUNCH(k_popcount, stream_grid(nvec, 4), BINOP_THREADS, 0, (const ulonglong2 *)b->words, nvec,
+               (unsigned long long *)c.d_mailbox);
+    return fetch_counter(count);
+}
+
+static int build_rank(bxg_bits *b) {
+    if (b->rank_valid) return BXG_OK;
+    Context &c = ctx();
+    int64_t n = b->nwords_alloc + 1;
+    if (!b->rank) BXG_CUDA(cudaMalloc(&b->rank, (size_t)n * 4));
+    cub::CountingInputIterator<int64_t> idx(0);
+    cub::TransformInputIterator<uint32_t, PopcWord, cub::CountingInputIterator<int64_t>> it(idx, PopcWord{b->words, b->nwords_alloc});
+    size_t tmp_bytes = 0;
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, b->rank, n, c.stream));
+    void *tmp;
+    BXG_TRY(scratch(7, tmp_bytes, &tmp));
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, b->rank, n, c.stream));
+    c.launches += 2;   // CUB's single-pass scan: init + scan kernels
+    b->rank_valid = true;
+    return BXG_OK;
+}
+
+int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *count, int64_t n, int32_t *out,
+                          int strict, int loc) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (n <= 0) return BXG_OK;
+    BXG_TRY(build_rank(b));
+    const void *ds, *dc;
+    BXG_TRY(stage_in(0, start, (size_t)n * 4, loc, &ds));
+    BXG_TRY(stage_in(1, count, (size_t)n * 4, loc, &dc));
+    int32_t *dout = out;
+    if (loc == BXG_HOST) {
+        void *t;
+        BXG_TRY(scratch(2, (size_t)n * 4, &t));
+        dout = (int32_t *)t;
+    }
+    BXG_LAUNCH(k_count_ranges, grid_for(cdiv(n, 256), 8), 256, 0, b->words, b->rank, b->state, b->bin_size,
+               (strict && !b->flat) ? 1 : 0, (const int32_t *)ds, (const int32_t *)dc, n, dout);
+    if (loc == BXG_HOST) {
+        BXG_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx().stream));
+        BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
+    return BXG_OK;
+}
+
+int bxg_bits_next(const bxg_bits_t *b, int32_t start, int32_t end, int val, int32_t *out) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (start < 0 || end > b->size || end < start) return set_error(BXG_ERR_ARG, "next: bad range [%d,%d)", start, end);
+    if (end == start) {
+        *out = end;
+        return BXG_OK;
+    }
+    Context &c = ctx();
+    c.mailbox[1] = end;
+    BXG_CUDA(cudaMemcpyAsync(c.d_mailbox + 1, c.mailbox + 1, 8, cudaMemcpyHostToDevice, c.stream));
+    int64_t nw = ((int64_t)(end - 1) >> 6) - (start >> 6) + 1;
+    BXG_LAUNCH(k_next, grid_for(cdiv(nw, 256), 4), 256, 0, b->words, (int64_t)start, (int64_t)end, val,
+               (unsigned long long *)(c.d_mailbox + 1));
+    BXG_CUDA(cudaMemcpyAsync(c.mailbox + 1, c.d_mailbox + 1, 8, cudaMemcpyDeviceToHost, c.stream));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    *out = (int32_t)c.mailbox[1];
+    return BXG_OK;
+}
+
+int bxg_bits_runs_count(bxg_bits_t *b, int64_t *nruns) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (b->nruns >= 0) {
+        *nruns = b->nruns;
+        return BXG_OK;
+    }
+    Context &c = ctx();
+    int64_t ntiles = cdiv(b->nwords_alloc, RUN_TILE);
+    void *d_cnt, *d_off, *tmp;
+    BXG_TRY(scratch(0, (size_t)(ntiles + 1) * 4, &d_cnt));
+    BXG_TRY(scratch(1, (size_t)(ntiles + 1) * 4, &d_off));
+    BXG_CUDA(cudaMemsetAsync((uint32_t *)d_cnt + ntiles, 0, 4, c.stream));
+    BXG_LAUNCH(k_runs_count, (int)ntiles, RUN_THREADS, 0, b->words, b->nwords_alloc, (uint32_t *)d_cnt);
+    size_t tmp_bytes = 0;
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (uint32_t *)d_cnt, (uint32_t *)d_off, ntiles + 1, c.stream));
+    BXG_TRY(scratch(7, tmp_bytes, &tmp));
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (uint32_t *)d_cnt, (uint32_t *)d_off, ntiles + 1, c.stream));
+    c.launches += 2;
+    uint32_t *m32 = (uint32_t *)(c.mailbox + 2);
+    BXG_CUDA(cudaMemcpyAsync(m32, (uint32_t *)d_off + ntiles, 4, cudaMemcpyDeviceToHost, c.stream));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    int64_t ntrans = *m32;
+    int64_t nr = (ntrans + 1) / 2;
+    if (nr > b->run_cap) {
+        cudaFree(b->run_s);
+        cudaFree(b->run_e);
+        b->run_s = b->run_e = nullptr;
+        b->run_cap = nr + nr / 4 + 16;
+        BXG_CUDA(cudaMalloc(&b->run_s, (size_t)b->run_cap * 4));
+        BXG_CUDA(cudaMalloc(&b->run_e, (size_t)b->run_cap * 4));
+    }
+    if (nr > 0) {
+        BXG_LAUNCH(k_runs_fill, (int)ntiles, RUN_THREADS, 0, b->words, b->nwords_alloc, (const uint32_t *)d_off,
+                   b->run_s, b->run_e);
+        if (ntrans & 1) {   // last run reaches `size` exactly on a word boundary: no closing transition exists
+            int32_t sz = b->size;
+            BXG_CUDA(cudaMemcpyAsync(b->run_e + (nr - 1), &sz, 4, cudaMemcpyHostToDevice, c.stream));
+            BXG_CUDA(cudaStreamSynchronize(c.stream));
+        }
+    }
+    b->nruns = nr;
+    *nruns = nr;
+    return BXG_OK;
+}
+
+int bxg_bits_runs_fetch(bxg_bits_t *b, int32_t *starts, int32_t *ends, int64_t nruns) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (b->nruns < 0) return set_error(BXG_ERR_STATE, "bxg_bits_runs_count must be called first");
+    if (nruns != b->nruns) return set_error(BXG_ERR_ARG, "nruns mismatch (%lld vs %lld)", (long long)nruns, (long long)b->nruns);
+    if (nruns == 0) return BXG_OK;
+    BXG_CUDA(cudaMemcpyAsync(starts, b->run_s, (size_t)nruns * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    BXG_CUDA(cudaMemcpyAsync(ends, b->run_e, (size_t)nruns * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    return BXG_OK;
+}
+
+int bxg_bits_states(const bxg_bits_t *b, uint8_t *out) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    BXG_CUDA(cudaMemcpyAsync(out, b->state, (size_t)b->nbins, cudaMemcpyDeviceToHost, ctx().stream));
+    BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    return BXG_OK;
+}
+
+int bxg_bits_export_words(const bxg_bits_t *b, uint64_t *out) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    BXG_CUDA(cudaMemcpyAsync(out, b->words, (size_t)b->nwords * 8, cudaMemcpyDeviceToHost, ctx().stream));
+    BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    return BXG_OK;
+}
+
+int bxg_bits_import_words(bxg_bits_t *b, const uint64_t *in) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    Context &c = ctx();
+    BXG_CUDA(cudaMemcpyAsync(b->words, in, (size_t)b->nwords * 8, cudaMemcpyHostToDevice, c.stream));
+    BXG_LAUNCH(k_mask_tail, 1, 32, 0, b->words, b->nwords, b->nwords_alloc, tail_mask_of(b->size));
+    BXG_LAUNCH(k_fill_u8, grid_for(cdiv(b->nbins, 256), 1), 256, 0, b->state, (int64_t)b->nbins, (uint8_t)BA);
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    invalidate(b);
+    return BXG_OK;
+}
+
+int bxg_bits_device_words(const bxg_bits_t *b, const uint64_t **dptr, int64_t *nwords) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (dptr) *dptr = b->words;
+    if (nwords) *nwords = b->nwords;
+    return BXG_OK;
+}
+
+}  // extern "C"
+
+// used by aggregate.cu
+const uint64_t *bxg_bits_words_internal(const bxg_bits *b) { return b ? b->words : nullptr; }
+int32_t bxg_bits_size_internal(const bxg_bits *b) { return b ? b->size : 0; }

@@ -1,0 +1,68 @@
+// common.cuh -- shared runtime pieces of libbxb200.so (context, error channel, scratch, launch accounting).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bxb200.h"
+
+namespace bxg {
+
+struct Context {
+    int device = -1;
+    int sm_count = 0;
+    int64_t l2_bytes = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    // grow-only device scratch (CUB temp storage, staged host arrays, partials)
+    void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // small pinned host mailbox for scalar results
+    int64_t *mailbox = nullptr;     // 64 x int64, pinned
+    int64_t *d_mailbox = nullptr;   // 64 x int64, device
+    void *l2_flush_buf = nullptr;
+    size_t l2_flush_bytes = 0;
+};
+
+Context &ctx();
+int set_error(int code, const char *fmt, ...);
+int ensure_init();
+// returns device scratch slot `slot` with at least `bytes` capacity (contents not preserved on growth)
+int scratch(int slot, size_t bytes, void **out);
+
+#define BXG_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return bxg::set_error(BXG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                                  __FILE__, __LINE__);                                              \
+    } while (0)
+
+#define BXG_TRY(call)             \
+    do {                          \
+        int r__ = (call);         \
+        if (r__ != BXG_OK) return r__; \
+    } while (0)
+
+// every kernel launch of the library goes through this so bench.py can report gpu_launches
+#define BXG_LAUNCH(kernel, grid, block, smem, ...)                                   \
+    do {                                                                             \
+        kernel<<<(grid), (block), (smem), bxg::ctx().stream>>>(__VA_ARGS__);         \
+        bxg::ctx().launches++;                                                       \
+        BXG_CUDA(cudaGetLastError());                                                \
+    } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// grid size for a grid-stride kernel: enough CTAs to cover `work_items / per_cta`, capped at `waves` full waves
+static inline int grid_for(int64_t ctas_needed, int ctas_per_sm) {
+    int64_t cap = (int64_t)ctx().sm_count * ctas_per_sm;
+    if (ctas_needed < 1) ctas_needed = 1;
+    return (int)(ctas_needed < cap ? ctas_needed : cap);
+}
+
+// Stage a caller array onto the device if it lives on the host; returns the device pointer to use.
+int stage_in(int slot, const void *src, size_t bytes, int loc, const void **dptr);
+
+}  // namespace bxg

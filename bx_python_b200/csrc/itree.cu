@@ -1,0 +1,614 @@
+// itree.cu -- device interval index: radix-sorted implicit layout + batched find (count / scan / fill).
+//
+// Replaces IntervalNode.insert / _intersect of /root/reference/lib/bx/intervals/intersection.pyx:103-138,180-189.
+// The reference treap's in-order sequence is the total order (start, end>start, +/-insertion index) (DESIGN.md
+// "interval index"); find() is a filter over that sequence:  end > qs && start < qe.  So the index is
+//   S[], E[], I[]  : starts, ends, item ids in that order (per tree, trees concatenated; toff[] delimits them)
+//   PM[]           : per-tree running max of E  -> first possible hit   lo = first k with PM[k] >  qs
+//                                                   end of candidates   hi = first k with S[k]  >= qe
+//   M[l][]         : 32-ary max-of-E hierarchy  -> skip runs of non-hits inside [lo,hi) in O(log) steps
+//   spS[], spPM[]  : every `stride`-th element of S / PM; staged to shared memory by one 1-D TMA bulk copy per CTA
+// and find is: count pass (searches + scan of [lo,hi)), exclusive scan to int64 CSR offsets, fill pass.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+using namespace bxg;
+
+constexpr int MAX_LEVELS = 6;          // 32^7 > 2^31
+constexpr int MAX_SPLIT = 4096;        // splitter entries per array (16 KB each in shared memory)
+constexpr int SMEM_TREES = 256;        // toff entries cached in shared memory
+constexpr int FIND_THREADS = 256;
+
+struct IndexView {
+    const int32_t *S, *E, *I, *PM;
+    const int32_t *M[MAX_LEVELS];
+    const int64_t *toff;
+    const int32_t *spS, *spPM;   // contiguous: spS[nsplit_pad] then spPM[nsplit_pad]
+    uint32_t n;
+    int32_t ntrees, nlev, nsplit, nsplit_pad, shift;   // stride = 1 << shift
+};
+
+struct bxg_itree {
+    int64_t n = 0;
+    int32_t ntrees = 0;
+    bool built = false;
+    int32_t *S = nullptr, *E = nullptr, *I = nullptr, *PM = nullptr;
+    int32_t *M[MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t mlen[MAX_LEVELS] = {0, 0, 0, 0, 0, 0};
+    int nlev = 0;
+    int64_t *toff = nullptr;
+    int32_t *split = nullptr;
+    int nsplit = 0, nsplit_pad = 0, shift = 0;
+    // query-side buffers (grow-only)
+    int32_t *d_cnt = nullptr, *d_lo = nullptr, *d_hi = nullptr;
+    int64_t *d_off = nullptr;
+    int32_t *d_hits = nullptr;
+    int64_t q_cap = 0, hits_cap = 0;
+    int64_t nq = -1, total = 0;
+    // the staged query arrays of the last find (device pointers valid until the next call)
+    IndexView view() const {
+        IndexView v;
+        v.S = S; v.E = E; v.I = I; v.PM = PM;
+        for (int l = 0; l < MAX_LEVELS; l++) v.M[l] = M[l];
+        v.toff = toff; v.spS = split; v.spPM = split + nsplit_pad;
+        v.n = (uint32_t)n; v.ntrees = ntrees; v.nlev = nlev; v.nsplit = nsplit; v.nsplit_pad = nsplit_pad; v.shift = shift;
+        return v;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// build kernels
+// ------------------------------------------------------------------------------------------------------------------
+// key = (start biased to unsigned) : (end > start) : (proper ? index : 2^31-1-index)   -- intersection.pyx:110-116
+__global__ void k_make_keys(const int32_t *__restrict__ tree, const int32_t *__restrict__ start,
+                            const int32_t *__restrict__ end, int64_t n, int32_t ntrees,
+                            uint64_t *__restrict__ keys, int32_t *__restrict__ vals, int *bad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t s = start[i], e = end[i];
+        uint64_t c = e > s ? 1u : 0u;
+        uint64_t tb = c ? (uint64_t)i : (uint64_t)(0x7fffffff - i);
+        keys[i] = ((uint64_t)((uint32_t)s ^ 0x80000000u) << 32) | (c << 31) | tb;
+        vals[i] = (int32_t)i;
+        if (tree && (tree[i] < 0 || tree[i] >= ntrees)) *bad = 1;
+    }
+}
+
+__global__ void k_gather_tree(const int32_t *__restrict__ tree, const int32_t *__restrict__ vals, int64_t n,
+                              uint32_t *__restrict__ tk) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) tk[i] = (uint32_t)tree[vals[i]];
+}
+
+// S,E in sorted order; TE = (tree : biased end) for the segmented running max
+__global__ void k_gather_items(const int32_t *__restrict__ tree, const int32_t *__restrict__ start,
+                               const int32_t *__restrict__ end, const int32_t *__restrict__ I, int64_t n,
+                               int32_t *__restrict__ S, int32_t *__restrict__ E, uint64_t *__restrict__ TE) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        int32_t i = I[k];
+        int32_t e = end[i];
+        S[k] = start[i];
+        E[k] = e;
+        uint64_t t = tree ? (uint64_t)(uint32_t)tree[i] : 0ull;
+        TE[k] = (t << 32) | (uint64_t)((uint32_t)e ^ 0x80000000u);
+    }
+}
+
+// toff[t] = first sorted position whose tree id >= t   (TE is sorted by tree id in its high word)
+__global__ void k_tree_offsets(const uint64_t *__restrict__ TE, int64_t n, int32_t ntrees, int64_t *__restrict__ toff) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntrees) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)(TE[mid] >> 32) < t) lo = mid + 1; else hi = mid;
+    }
+    toff[t] = lo;
+}
+
+__global__ void k_unpack_pm(const uint64_t *__restrict__ TEmax, int64_t n, int32_t *__restrict__ PM) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+        PM[k] = (int32_t)((uint32_t)TEmax[k] ^ 0x80000000u);
+}
+
+// one warp per 32-entry block: out[b] = max(in[32b .. 32b+31])
+__global__ void k_block_max(const int32_t *__restrict__ in, int64_t n, int32_t *__restrict__ out, int64_t nout) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nout; b += nwarps) {
+        int64_t k = b * 32 + lane;
+        int32_t v = k < n ? in[k] : INT32_MIN;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) out[b] = v;
+    }
+}
+
+__global__ void k_sample(const int32_t *__restrict__ S, const int32_t *__restrict__ PM, int64_t n, int shift, int nsplit,
+                         int nsplit_pad, int32_t *__restrict__ split) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nsplit_pad) return;
+    int64_t p = (int64_t)k << shift;
+    split[k] = (k < nsplit && p < n) ? S[p] : INT32_MAX;
+    split[nsplit_pad + k] = (k < nsplit && p < n) ? PM[p] : INT32_MAX;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// find
+// ------------------------------------------------------------------------------------------------------------------
+struct SmemIndex {
+    const int32_t *spS, *spPM;   // shared
+    const int64_t *toff;         // shared (ntrees <= SMEM_TREES) or global
+};
+
+// first position p in [seg_lo, seg_hi) where !(A[p] < key)  (LESS_EQ: !(A[p] <= key)), else seg_hi.
+// `sp` = every 2^shift-th element of A, resident in shared memory.
+template <bool LESS_EQ>
+__device__ __forceinline__ uint32_t seg_search(const int32_t *__restrict__ A, const int32_t *sp, int shift,
+                                               uint32_t seg_lo, uint32_t seg_hi, int32_t key) {
+    auto before = [&](int32_t v) { return LESS_EQ ? (v <= key) : (v < key); };
+    uint32_t lo = seg_lo, hi = seg_hi;
+    if (lo >= hi) return hi;
+    // splitters whose sampled position lies inside the segment: k in [k0, k1)
+    uint32_t k0 = (seg_lo + (1u << shift) - 1) >> shift, k1 = ((seg_hi - 1) >> shift) + 1;
+    if (k0 < k1) {
+        uint32_t a = k0, b = k1;              // count splitters `before` key
+        while (a < b) {
+            uint32_t m = (a + b) >> 1;
+            if (before(sp[m])) a = m + 1; else b = m;
+        }
+        if (a == k0) {
+            hi = k0 << shift;                 // A[k0<<shift] is not before key
+        } else {
+            lo = ((a - 1) << shift) + 1;      // A[(a-1)<<shift] is before key
+            uint32_t h = a << shift;
+            if (a < k1 && h < hi) hi = h;
+        }
+    }
+    while (lo < hi) {
+        uint32_t m = (lo + hi) >> 1;
+        if (before(__ldg(A + m))) lo = m + 1; else hi = m;
+    }
+    return lo;
+}
+
+// Walk k over [lo,hi) visiting every k with E[k] > qs, in order; aligned all-miss blocks are skipped through the
+// max hierarchy (M[0] covers 32 items, M[l] covers 32^(l+1)).
+template <typename F>
+__device__ __forceinline__ void for_each_hit(const IndexView &ix, uint32_t lo, uint32_t hi, int32_t qs, F &&emit) {
+    uint32_t k = lo;
+    while (k < hi) {
+        if ((k & 31u) == 0 && k + 32u <= hi && __ldg(ix.M[0] + (k >> 5)) <= qs) {
+            uint32_t idx = k >> 5;
+            int lvl = 0;
+            while (lvl + 1 < ix.nlev && (idx & 31u) == 0) {
+                uint32_t up = idx >> 5;
+                uint64_t span_end = ((uint64_t)up + 1) << (5 * (lvl + 2));
+                if (span_end > hi || __ldg(ix.M[lvl + 1] + up) > qs) break;
+                idx = up;
+                lvl++;
+            }
+            k = (idx + 1u) << (5 * (lvl + 1));
+            continue;
+        }
+        if (__ldg(ix.E + k) > qs) emit(k);
+        k++;
+    }
+}
+
+__device__ __forceinline__ const SmemIndex stage_index(const IndexView &ix, unsigned char *smem_raw) {
+    // layout: [mbarrier 8 B][pad 8 B][spS nsplit_pad x 4][spPM nsplit_pad x 4][toff (ntrees+1) x 8]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    int32_t *sp = reinterpret_cast<int32_t *>(smem_raw + 16);
+    int64_t *stoff = reinterpret_cast<int64_t *>(smem_raw + 16 + (size_t)ix.nsplit_pad * 8);
+    const uint32_t bytes = (uint32_t)ix.nsplit_pad * 8u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        if (bytes) {
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(sp, ix.spS, bytes, bar);
+        }
+    }
+    const bool toff_smem = ix.ntrees <= SMEM_TREES;
+    if (toff_smem)
+        for (int t = threadIdx.x; t <= ix.ntrees; t += blockDim.x) stoff[t] = ix.toff[t];
+    __syncthreads();                       // barrier init + toff visible to every thread
+    if (bytes) mbar_wait(bar, 0);
+    SmemIndex s;
+    s.spS = sp;
+    s.spPM = sp + ix.nsplit_pad;
+    s.toff = toff_smem ? stoff : ix.toff;
+    return s;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(FIND_THREADS)
+k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, const int32_t *__restrict__ qs_, const int32_t *__restrict__ qe_,
+       int64_t nq, int32_t *__restrict__ cnt, int32_t *__restrict__ lo_, int32_t *__restrict__ hi_,
+       const int64_t *__restrict__ off, int32_t *__restrict__ hits, unsigned long long *total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemIndex sm;
+    if (!FILL) sm = stage_index(ix, smem_raw);
+    unsigned long long local = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+        const int32_t qs = __ldg(qs_ + q);
+        if (!FILL) {
+            const int32_t qe = __ldg(qe_ + q);
+            const int32_t t = qtree ? __ldg(qtree + q) : 0;
+            uint32_t lo = 0, hi = 0;
+            int32_t c = 0;
+            if (t >= 0 && t < ix.ntrees) {
+                const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
+                hi = seg_search<false>(ix.S, sm.spS, ix.shift, seg_lo, seg_hi, qe);     // start <  qe
+                lo = seg_search<true>(ix.PM, sm.spPM, ix.shift, seg_lo, seg_hi, qs);    // running max end > qs
+                if (lo > hi) lo = hi;
+                for_each_hit(ix, lo, hi, qs, [&](uint32_t) { c++; });
+            }
+            cnt[q] = c;
+            lo_[q] = (int32_t)lo;
+            hi_[q] = (int32_t)hi;
+            local += (unsigned long long)c;
+        } else {
+            const uint32_t lo = (uint32_t)lo_[q], hi = (uint32_t)hi_[q];
+            int32_t *dst = hits + off[q];
+            for_each_hit(ix, lo, hi, qs, [&](uint32_t k) { *dst++ = __ldg(ix.I + k); });
+        }
+    }
+    if (!FILL && total) {
+        // warp-aggregated: one atomic per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(total, local);
+    }
+}
+
+struct CastI64 {
+    __device__ __forceinline__ int64_t operator()(int32_t v) const { return (int64_t)v; }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+static void free_index(bxg_itree *t) {
+    cudaFree(t->S); cudaFree(t->E); cudaFree(t->I); cudaFree(t->PM); cudaFree(t->toff); cudaFree(t->split);
+    for (int l = 0; l < MAX_LEVELS; l++) { cudaFree(t->M[l]); t->M[l] = nullptr; t->mlen[l] = 0; }
+    t->S = t->E = t->I = t->PM = nullptr;
+    t->toff = nullptr;
+    t->split = nullptr;
+    t->nlev = 0;
+    t->built = false;
+}
+
+static size_t find_smem_bytes(const bxg_itree *t) {
+    return 16 + (size_t)t->nsplit_pad * 8 + (t->ntrees <= SMEM_TREES ? (size_t)(t->ntrees + 1) * 8 : 0);
+}
+
+static int ensure_query_buffers(bxg_itree *t, int64_t nq) {
+    if (nq + 1 <= t->q_cap) return BXG_OK;
+    BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    cudaFree(t->d_cnt); cudaFree(t->d_lo); cudaFree(t->d_hi); cudaFree(t->d_off);
+    t->d_cnt = t->d_lo = t->d_hi = nullptr;
+    t->d_off = nullptr;
+    int64_t cap = nq + 1 + nq / 8;
+    BXG_CUDA(cudaMalloc(&t->d_cnt, (size_t)cap * 4));
+    BXG_CUDA(cudaMalloc(&t->d_lo, (size_t)cap * 4));
+    BXG_CUDA(cudaMalloc(&t->d_hi, (size_t)cap * 4));
+    BXG_CUDA(cudaMalloc(&t->d_off, (size_t)cap * 8));
+    t->q_cap = cap;
+    return BXG_OK;
+}
+
+static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t nq,
+                        unsigned long long *d_total) {
+    size_t smem = find_smem_bytes(t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        BXG_CUDA(cudaFuncSetAttribute(k_find<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
+    int grid = grid_for(cdiv(nq, FIND_THREADS), 8);
+    BXG_LAUNCH((k_find<false>), grid, FIND_THREADS, smem, t->view(), dqt, dqs, dqe, nq, t->d_cnt, t->d_lo, t->d_hi,
+               (const int64_t *)nullptr, (int32_t *)nullptr, d_total);
+    return BXG_OK;
+}
+
+extern "C" {
+
+int bxg_itree_create(bxg_itree_t **out) {
+    BXG_TRY(ensure_init());
+    if (!out) return set_error(BXG_ERR_ARG, "out is null");
+    *out = new bxg_itree();
+    return BXG_OK;
+}
+
+int bxg_itree_free(bxg_itree_t *t) {
+    if (!t) return BXG_OK;
+    cudaStreamSynchronize(ctx().stream);
+    free_index(t);
+    cudaFree(t->d_cnt); cudaFree(t->d_lo); cudaFree(t->d_hi); cudaFree(t->d_off); cudaFree(t->d_hits);
+    delete t;
+    return BXG_OK;
+}
+
+int bxg_itree_size(const bxg_itree_t *t, int64_t *n, int32_t *ntrees) {
+    if (!t) return set_error(BXG_ERR_ARG, "null index handle");
+    if (n) *n = t->n;
+    if (ntrees) *ntrees = t->ntrees;
+    return BXG_OK;
+}
+
+int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, const int32_t *end, int64_t n,
+                    int32_t ntrees, int loc) {
+    if (!t) return set_error(BXG_ERR_ARG, "null index handle");
+    if (n < 0 || n > 0x7fffff00ll) return set_error(BXG_ERR_ARG, "item count %lld out of range", (long long)n);
+    if (ntrees < 1) return set_error(BXG_ERR_ARG, "ntrees must be >= 1");
+    Context &c = ctx();
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    free_index(t);
+    t->n = n;
+    t->ntrees = ntrees;
+    t->nq = -1;
+    BXG_CUDA(cudaMalloc(&t->toff, (size_t)(ntrees + 1) * 8));
+    BXG_CUDA(cudaMemsetAsync(t->toff, 0, (size_t)(ntrees + 1) * 8, c.stream));
+    if (n == 0) {
+        t->nsplit = t->nsplit_pad = 0;
+        t->built = true;
+        return BXG_OK;
+    }
+    const void *dt = nullptr, *ds, *de;
+    if (tree) BXG_TRY(stage_in(0, tree, (size_t)n * 4, loc, &dt));
+    BXG_TRY(stage_in(1, start, (size_t)n * 4, loc, &ds));
+    BXG_TRY(stage_in(2, end, (size_t)n * 4, loc, &de));
+    const int32_t *d_tree = (const int32_t *)dt, *d_start = (const int32_t *)ds, *d_end = (const int32_t *)de;
+
+    uint64_t *k0 = nullptr, *k1 = nullptr;
+    int32_t *v0 = nullptr, *v1 = nullptr;
+    uint32_t *tk0 = nullptr, *tk1 = nullptr;
+    auto cleanup = [&]() { cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(tk0); cudaFree(tk1); };
+#define BUILD_CUDA(call)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            cleanup();                                                                                     \
+            return set_error(BXG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                  \
+    } while (0)
+    BUILD_CUDA(cudaMalloc(&k0, (size_t)n * 8));
+    BUILD_CUDA(cudaMalloc(&k1, (size_t)n * 8));
+    BUILD_CUDA(cudaMalloc(&v0, (size_t)n * 4));
+    BUILD_CUDA(cudaMalloc(&v1, (size_t)n * 4));
+    BUILD_CUDA(cudaMemsetAsync(c.d_mailbox + 4, 0, 8, c.stream));
+    int g = grid_for(cdiv(n, 256), 8);
+    BXG_LAUNCH(k_make_keys, g, 256, 0, d_tree, d_start, d_end, n, ntrees, k0, v0, (int *)(c.d_mailbox + 4));
+
+    // sort 1: (start, end>start, tie) -- 64-bit LSD radix sort
+    size_t tmp_bytes = 0, tb2 = 0;
+    BUILD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, v0, v1, n, 0, 64, c.stream));
+    void *tmp;
+    {
+        int r = scratch(7, tmp_bytes, &tmp);
+        if (r != BXG_OK) { cleanup(); return r; }
+    }
+    BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, n, 0, 64, c.stream));
+    c.launches += 17;   // CUB onesweep: histogram + 8 x (scan, onesweep) kernels
+    int32_t *order = v1;
+    if (d_tree && ntrees > 1) {
+        // sort 2 (stable): bring each tree's items together, keeping the order of sort 1 inside a tree
+        int bits = 1;
+        while ((1ll << bits) < ntrees) bits++;
+        BUILD_CUDA(cudaMalloc(&tk0, (size_t)n * 4));
+        BUILD_CUDA(cudaMalloc(&tk1, (size_t)n * 4));
+        BXG_LAUNCH(k_gather_tree, g, 256, 0, d_tree, v1, n, tk0);
+        BUILD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, tk0, tk1, v1, v0, n, 0, bits, c.stream));
+        {
+            int r = scratch(7, tb2, &tmp);
+            if (r != BXG_OK) { cleanup(); return r; }
+        }
+        BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, tk0, tk1, v1, v0, n, 0, bits, c.stream));
+        c.launches += 1 + 2 * ((bits + 7) / 8);
+        order = v0;
+    }
+    BUILD_CUDA(cudaMalloc(&t->S, (size_t)n * 4));
+    BUILD_CUDA(cudaMalloc(&t->E, (size_t)n * 4));
+    BUILD_CUDA(cudaMalloc(&t->I, (size_t)n * 4));
+    BUILD_CUDA(cudaMalloc(&t->PM, (size_t)n * 4));
+    BUILD_CUDA(cudaMemcpyAsync(t->I, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
+    // k0/k1 are free now: reuse as TE / running max
+    BXG_LAUNCH(k_gather_items, g, 256, 0, d_tree && ntrees > 1 ? d_tree : nullptr, d_start, d_end, t->I, n, t->S, t->E, k0);
+    BXG_LAUNCH(k_tree_offsets, (ntrees + 1 + 127) / 128, 128, 0, k0, n, ntrees, t->toff);
+    BUILD_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tb2, k0, k1, cub::Max(), n, c.stream));
+    {
+        int r = scratch(7, tb2, &tmp);
+        if (r != BXG_OK) { cleanup(); return r; }
+    }
+    BUILD_CUDA(cub::DeviceScan::InclusiveScan(tmp, tb2, k0, k1, cub::Max(), n, c.stream));
+    c.launches += 2;
+    BXG_LAUNCH(k_unpack_pm, g, 256, 0, k1, n, t->PM);
+
+    // 32-ary max hierarchy over E
+    const int32_t *src = t->E;
+    int64_t len = n;
+    t->nlev = 0;
+    while (t->nlev < MAX_LEVELS) {
+        int64_t nout = cdiv(len, 32);
+        BUILD_CUDA(cudaMalloc(&t->M[t->nlev], (size_t)nout * 4));
+        BXG_LAUNCH(k_block_max, grid_for(cdiv(nout * 32, 256), 8), 256, 0, src, len, t->M[t->nlev], nout);
+        t->mlen[t->nlev] = nout;
+        src = t->M[t->nlev];
+        len = nout;
+        t->nlev++;
+        if (nout <= 1) break;
+    }
+    // splitters
+    t->shift = 0;
+    while (cdiv(n, 1ll << t->shift) > MAX_SPLIT) t->shift++;
+    t->nsplit = (int)cdiv(n, 1ll << t->shift);
+    t->nsplit_pad = (t->nsplit + 3) & ~3;
+    BUILD_CUDA(cudaMalloc(&t->split, (size_t)t->nsplit_pad * 8));
+    BXG_LAUNCH(k_sample, (t->nsplit_pad + 255) / 256, 256, 0, t->S, t->PM, n, t->shift, t->nsplit, t->nsplit_pad, t->split);
+
+    BUILD_CUDA(cudaMemcpyAsync(c.mailbox + 4, c.d_mailbox + 4, 8, cudaMemcpyDeviceToHost, c.stream));
+    BUILD_CUDA(cudaStreamSynchronize(c.stream));
+    cleanup();
+#undef BUILD_CUDA
+    if ((int)c.mailbox[4] != 0) {
+        free_index(t);
+        t->n = 0;
+        return set_error(BXG_ERR_ARG, "tree id out of range [0,%d)", ntrees);
+    }
+    t->built = true;
+    return BXG_OK;
+}
+
+int bxg_itree_order(const bxg_itree_t *t, int32_t *perm, int64_t *tree_offsets) {
+    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
+    Context &c = ctx();
+    if (perm && t->n) BXG_CUDA(cudaMemcpyAsync(perm, t->I, (size_t)t->n * 4, cudaMemcpyDeviceToHost, c.stream));
+    if (tree_offsets)
+        BXG_CUDA(cudaMemcpyAsync(tree_offsets, t->toff, (size_t)(t->ntrees + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    return BXG_OK;
+}
+
+static int stage_queries(bxg_itree *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq, int loc,
+                         const int32_t **dqt, const int32_t **dqs, const int32_t **dqe) {
+    const void *a = nullptr, *b, *d;
+    if (qtree && t->ntrees > 1) BXG_TRY(stage_in(0, qtree, (size_t)nq * 4, loc, &a));
+    BXG_TRY(stage_in(1, qs, (size_t)nq * 4, loc, &b));
+    BXG_TRY(stage_in(2, qe, (size_t)nq * 4, loc, &d));
+    *dqt = (const int32_t *)a;
+    *dqs = (const int32_t *)b;
+    *dqe = (const int32_t *)d;
+    return BXG_OK;
+}
+
+int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq, int loc,
+                   int64_t *total) {
+    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
+    if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
+    Context &c = ctx();
+    BXG_TRY(ensure_query_buffers(t, nq));
+    t->nq = nq;
+    t->total = 0;
+    if (nq == 0) {
+        BXG_CUDA(cudaMemsetAsync(t->d_off, 0, 8, c.stream));
+        if (total) *total = 0;
+        return BXG_OK;
+    }
+    const int32_t *dqt, *dqs, *dqe;
+    BXG_TRY(stage_queries(t, qtree, qs, qe, nq, loc, &dqt, &dqs, &dqe));
+    // pass A: searches + per-query hit counts
+    BXG_CUDA(cudaMemsetAsync(t->d_cnt + nq, 0, 4, c.stream));
+    BXG_TRY(launch_count(t, dqt, dqs, dqe, nq, nullptr));
+    // exclusive scan -> int64 CSR offsets (offsets[nq] = total)
+    cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(t->d_cnt, CastI64());
+    size_t tmp_bytes = 0;
+    void *tmp;
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, t->d_off, nq + 1, c.stream));
+    BXG_TRY(scratch(7, tmp_bytes, &tmp));
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, t->d_off, nq + 1, c.stream));
+    c.launches += 2;
+    BXG_CUDA(cudaMemcpyAsync(c.mailbox + 5, t->d_off + nq, 8, cudaMemcpyDeviceToHost, c.stream));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    t->total = c.mailbox[5];
+    if (t->total > t->hits_cap) {
+        cudaFree(t->d_hits);
+        t->d_hits = nullptr;
+        t->hits_cap = t->total + t->total / 8 + 1024;
+        BXG_CUDA(cudaMalloc(&t->d_hits, (size_t)t->hits_cap * 4));
+    }
+    // pass B: fill (reuses lo/hi of pass A)
+    if (t->total > 0) {
+        int grid = grid_for(cdiv(nq, FIND_THREADS), 8);
+        BXG_LAUNCH((k_find<true>), grid, FIND_THREADS, 0, t->view(), dqt, dqs, dqe, nq, t->d_cnt, t->d_lo, t->d_hi,
+                   (const int64_t *)t->d_off, t->d_hits, (unsigned long long *)nullptr);
+    }
+    if (total) *total = t->total;
+    return BXG_OK;
+}
+
+int bxg_itree_fetch(bxg_itree_t *t, int64_t *offsets, int32_t *hits) {
+    if (!t || t->nq < 0) return set_error(BXG_ERR_STATE, "bxg_itree_find must be called first");
+    Context &c = ctx();
+    if (offsets) BXG_CUDA(cudaMemcpyAsync(offsets, t->d_off, (size_t)(t->nq + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
+    if (hits && t->total) BXG_CUDA(cudaMemcpyAsync(hits, t->d_hits, (size_t)t->total * 4, cudaMemcpyDeviceToHost, c.stream));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    return BXG_OK;
+}
+
+int bxg_itree_result_dev(const bxg_itree_t *t, const int64_t **d_offsets, const int32_t **d_hits, int64_t *nq, int64_t *total) {
+    if (!t || t->nq < 0) return set_error(BXG_ERR_STATE, "bxg_itree_find must be called first");
+    if (d_offsets) *d_offsets = t->d_off;
+    if (d_hits) *d_hits = t->d_hits;
+    if (nq) *nq = t->nq;
+    if (total) *total = t->total;
+    return BXG_OK;
+}
+
+int bxg_itree_count(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq, int loc,
+                    int32_t *counts, int64_t *total) {
+    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
+    if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
+    Context &c = ctx();
+    if (nq == 0) {
+        if (total) *total = 0;
+        return BXG_OK;
+    }
+    BXG_TRY(ensure_query_buffers(t, nq));
+    t->nq = -1;
+    const int32_t *dqt, *dqs, *dqe;
+    BXG_TRY(stage_queries(t, qtree, qs, qe, nq, loc, &dqt, &dqs, &dqe));
+    BXG_CUDA(cudaMemsetAsync(c.d_mailbox + 6, 0, 8, c.stream));
+    BXG_TRY(launch_count(t, dqt, dqs, dqe, nq, (unsigned long long *)(c.d_mailbox + 6)));
+    if (counts)
+        BXG_CUDA(cudaMemcpyAsync(counts, t->d_cnt, (size_t)nq * 4,
+                                 loc == BXG_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c.stream));
+    if (total || loc == BXG_HOST) {
+        BXG_CUDA(cudaMemcpyAsync(c.mailbox + 6, c.d_mailbox + 6, 8, cudaMemcpyDeviceToHost, c.stream));
+        BXG_CUDA(cudaStreamSynchronize(c.stream));
+        if (total) *total = c.mailbox[6];
+    }
+    return BXG_OK;
+}
+
+int bxg_itree_neighbors(bxg_itree_t *t, const int32_t *, const int32_t *, const int32_t *, const int32_t *, int64_t,
+                        int, int, int64_t *) {
+    (void)t;
+    return set_error(BXG_ERR_STATE, "bxg_itree_neighbors: not implemented in this build");
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+"""
+Drop-in for ``bx.intervals.intersection`` (``/root/reference/lib/bx/intervals/intersection.pyx``):
+``Interval``, ``IntervalNode``, ``IntervalTree``, ``Intersecter``.
+
+``insert``/``add_interval`` queue (start, end, value) on the host; the first query after a mutation uploads the
+int32 arrays and builds the device index (radix sort + implicit max hierarchy, csrc/itree.cu).  ``find`` returns the
+stored objects in exactly the reference's order (in-order traversal of its treap, intersection.pyx:180-189).
+Bulk callers use ``find_batch`` / ``count_batch``; ``IntervalForest`` holds one tree per chromosome in a single
+device index so that millions of (chrom, start, end) queries are answered by one kernel launch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from .._lib import as_i32, check, ptr
+
+
+def _c_int(x):
+    """Cython `int` argument coercion (intersection.pyx:388): truncate floats, OverflowError outside int32."""
+    v = int(x)
+    if v > 0x7FFFFFFF or v < -0x80000000:
+        raise OverflowError("value too large to convert to int")
+    return v
+
+
+class Interval:
+    """intersection.pyx:274-323."""
+
+    __slots__ = ("start", "end", "value", "chrom", "strand")
+
+    def __init__(self, start, end, value=None, chrom=None, strand=None):
+        start, end = _c_int(start), _c_int(end)
+        assert start <= end, "start must be less than end"
+        self.start, self.end, self.value, self.chrom, self.strand = start, end, value, chrom, strand
+
+    def __repr__(self):
+        fstr = "Interval(%d, %d" % (self.start, self.end)
+        if self.value is not None:
+            fstr += ", value=" + str(self.value)
+        return fstr + ")"
+
+    # intersection.pyx:305-323
+    def __lt__(self, other): return self.start < other.start or self.end < other.end
+    def __eq__(self, other): return self.start == other.start and self.end == other.end
+    def __ne__(self, other): return self.start != other.start or self.end != other.end
+    def __gt__(self, other): return self.start > other.start or self.end > other.end
+    def __le__(self, other): return self == other or self < other
+    def __ge__(self, other): return self == other or self > other
+    __hash__ = None
+
+
+class IntervalNode:
+    """What ``traverse`` hands to its callback (intersection.pyx:61-101): start, end and the stored object."""
+
+    __slots__ = ("start", "end", "interval")
+
+    def __init__(self, start, end, interval):
+        self.start, self.end, self.interval = start, end, interval
+
+    def __repr__(self):
+        return "IntervalNode(%i, %i)" % (self.start, self.end)
+
+
+class _DeviceIndex:
+    """Owner of one bxg_itree handle (ntrees trees)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(_lib.lib().bxg_itree_create(C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib._lib is not None:
+            _lib._lib.bxg_itree_free(h)
+            self._h = None
+
+    def build(self, tree, start, end, ntrees):
+        check(_lib.lib().bxg_itree_build(self._h, ptr(tree), ptr(start), ptr(end), len(start), ntrees, _lib.HOST))
+
+    def find(self, qtree, qs, qe):
+        L = _lib.lib()
+        total = C.c_int64()
+        check(L.bxg_itree_find(self._h, ptr(qtree), ptr(qs), ptr(qe), len(qs), _lib.HOST, C.byref(total)))
+        off = np.empty(len(qs) + 1, np.int64)
+        hits = np.empty(total.value, np.int32)
+        check(L.bxg_itree_fetch(self._h, ptr(off), ptr(hits)))
+        return off, hits
+
+    def count(self, qtree, qs, qe):
+        out = np.empty(len(qs), np.int32)
+        check(_lib.lib().bxg_itree_count(self._h, ptr(qtree), ptr(qs), ptr(qe), len(qs), _lib.HOST, ptr(out), None))
+        return out
+
+    def order(self, n, ntrees):
+        perm = np.empty(n, np.int32)
+        toff = np.empty(ntrees + 1, np.int64)
+        check(_lib.lib().bxg_itree_order(self._h, ptr(perm), ptr(toff)))
+        return perm, toff
+
+    def neighbors(self, qtree, pos, n, max_dist, direction):
+        L = _lib.lib()
+        total = C.c_int64()
+        check(L.bxg_itree_neighbors(self._h, ptr(qtree), ptr(pos), ptr(n), ptr(max_dist), len(pos), direction,
+                                    _lib.HOST, C.byref(total)))
+        off = np.empty(len(pos) + 1, np.int64)
+        hits = np.empty(total.value, np.int32)
+        check(L.bxg_itree_fetch(self._h, ptr(off), ptr(hits)))
+        return off, hits
+
+
+class IntervalTree:
+    """intersection.pyx:325-485 -- same methods, device-resident index."""
+
+    def __init__(self):
+        self._starts, self._ends, self._values = [], [], []
+        self._index = None
+        self._dirty = False
+
+    # ---- position based interface --------------------------------------------------------------------------
+    def insert(self, start, end, value=None):
+        """Insert the interval [start,end) associated with value `value`."""
+        self._starts.append(_c_int(start))
+        self._ends.append(_c_int(end))
+        self._values.append(value)
+        self._dirty = True
+
+    add = insert
+
+    def insert_many(self, starts, ends, values=None):
+        """Array form of insert (no reference equivalent); values defaults to the running item index."""
+        s, e = as_i32(starts), as_i32(ends)
+        base = len(self._starts)
+        self._starts.extend(s.tolist())
+        self._ends.extend(e.tolist())
+        self._values.extend(values if values is not None else range(base, base + len(s)))
+        self._dirty = True
+
+    def _ensure(self):
+        if self._index is None:
+            self._index = _DeviceIndex()
+            self._dirty = True
+        if self._dirty:
+            self._s = np.asarray(self._starts, np.int32)
+            self._e = np.asarray(self._ends, np.int32)
+            self._index.build(None, self._s, self._e, 1)
+            self._dirty = False
+        return self._index
+
+    def find(self, start, end):
+        """Return a sorted list of all intervals overlapping [start,end)."""
+        if not self._starts:
+            return []
+        qs, qe = np.array([_c_int(start)], np.int32), np.array([_c_int(end)], np.int32)
+        _, hits = self._ensure().find(None, qs, qe)
+        v = self._values
+        return [v[i] for i in hits.tolist()]
+
+    def find_batch(self, starts, ends):
+        """-> (offsets int64[nq+1], hits int32[total]): item indices (insertion order) per query, reference order."""
+        qs, qe = as_i32(starts), as_i32(ends)
+        if not self._starts:
+            return np.zeros(len(qs) + 1, np.int64), np.empty(0, np.int32)
+        return self._ensure().find(None, qs, qe)
+
+    def count_batch(self, starts, ends):
+        """len(find(s, e)) for every query -> int32 array."""
+        qs, qe = as_i32(starts), as_i32(ends)
+        if not self._starts:
+            return np.zeros(len(qs), np.int32)
+        return self._ensure().count(None, qs, qe)
+
+    # ---- neighbours (intersection.pyx:192-260, 408-477) ------------------------------------------------------
+    def _neighbors(self, position, n, max_dist, direction):
+        if not self._starts:
+            return []
+        pos = np.array([_c_int(position)], np.int32)
+        _, hits = self._ensure().neighbors(None, pos, np.array([_c_int(n)], np.int32),
+                                           np.array([_c_int(max_dist)], np.int32), direction)
+        v = self._values
+        return [v[i] for i in hits.tolist()]
+
+    def before(self, position, num_intervals=1, max_dist=2500):
+        return self._neighbors(position, num_intervals, max_dist, 0)
+
+    def after(self, position, num_intervals=1, max_dist=2500):
+        return self._neighbors(position, num_intervals, max_dist, 1)
+
+    # ---- interval-like object based interface ----------------------------------------------------------------
+    def insert_interval(self, interval):
+        self.insert(interval.start, interval.end, interval)
+
+    add_interval = insert_interval
+
+    def before_interval(self, interval, num_intervals=1, max_dist=2500):
+        if not self._starts:
+            return []
+        return self.before(interval.start, num_intervals, max_dist)
+
+    def after_interval(self, interval, num_intervals=1, max_dist=2500):
+        if not self._starts:
+            return []
+        return self.after(interval.end, num_intervals, max_dist)
+
+    def upstream_of_interval(self, interval, num_intervals=1, max_dist=2500):
+        if not self._starts:
+            return []
+        if interval.strand == -1 or interval.strand == "-":
+            return self.after(interval.end, num_intervals, max_dist)
+        return self.before(interval.start, num_intervals, max_dist)
+
+    def downstream_of_interval(self, interval, num_intervals=1, max_dist=2500):
+        if not self._starts:
+            return []
+        if interval.strand == -1 or interval.strand == "-":
+            return self.before(interval.start, num_intervals, max_dist)
+        return self.after(interval.end, num_intervals, max_dist)
+
+    def traverse(self, fn):
+        """call fn for each element in the tree (in-order; fn receives an IntervalNode)."""
+        if not self._starts:
+            return None
+        perm, _ = self._ensure().order(len(self._starts), 1)
+        for i in perm.tolist():
+            fn(IntervalNode(self._starts[i], self._ends[i], self._values[i]))
+
+    def order(self):
+        """Item indices in in-order sequence (int32 array)."""
+        if not self._starts:
+            return np.empty(0, np.int32)
+        return self._ensure().order(len(self._starts), 1)[0]
+
+    def __len__(self):
+        return len(self._starts)
+
+
+# For backward compatibility (intersection.pyx:488)
+Intersecter = IntervalTree
+
+
+class IntervalForest:
+    """One IntervalTree per chromosome in a single device index -- the batched form of the reference idiom
+    ``ranges[chrom].add_interval(...)`` / ``ranges[chrom].find(start, end)``
+    (scripts/bed_count_overlapping.py:17-33).  Trees are addressed by integer id (0..ntrees-1)."""
+
+    def __init__(self, ntrees):
+        self.ntrees = int(ntrees)
+        self._index = _DeviceIndex()
+        self.n = 0
+
+    def build(self, tree_ids, starts, ends):
+        t, s, e = as_i32(tree_ids), as_i32(starts), as_i32(ends)
+        self.n = len(s)
+        self._index.build(t, s, e, self.ntrees)
+        return self
+
+    def find_batch(self, tree_ids, starts, ends):
+        """-> CSR (offsets, hits); hits are positions in the arrays passed to build()."""
+        return self._index.find(as_i32(tree_ids), as_i32(starts), as_i32(ends))
+
+    def count_batch(self, tree_ids, starts, ends):
+        return self._index.count(as_i32(tree_ids), as_i32(starts), as_i32(ends))
+
+    def order(self):
+        return self._index.order(self.n, self.ntrees)
+
+    @property
+    def handle(self):
+        return self._index._h

@@ -1,0 +1,193 @@
+/*
+ * bxb200.h -- C ABI of libbxb200.so: the B200-native (sm_100a) replacement for bx-python's interval-intersection /
+ * binned-bitset hot path.
+ *
+ * The reference has no FFI registry for this path; the boundary it offers is
+ *   (1) the C ABI that lib/bx/bitset.pyx consumes:  src/binBits.h:7-26  (struct BinBits + binBits*) and
+ *       src/kent/bits.h:13-59 (bit*), declared to Cython at lib/bx/bitset.pyx:14-69, and
+ *   (2) the extension-module API of lib/bx/intervals/intersection.pyx:61-488 (IntervalNode/IntervalTree), which has
+ *       no C layer underneath it.
+ * Each entry point below names the reference interface it replaces.  Differences by design: calls are BATCHED
+ * (arrays of positions/ranges/queries instead of one scalar per call), objects are opaque handles that own device
+ * memory, and every function returns a status (0 = ok, <0 = error; message via bxg_last_error()) because the
+ * reference C layer has no error channel at all (src/kent/common.c:3-16 exits on OOM).
+ *
+ * Conventions: plain C types only; `loc` arguments say where the caller's arrays live (BXG_HOST: host memory,
+ * pageable or pinned; BXG_DEVICE: device memory of the current device).  All work is issued on the library's own
+ * CUDA stream; functions that return data to host memory synchronise that stream before returning.
+ * Not thread-safe per handle (the reference holds the GIL for every call, lib/bx/bitset.pyx has no nogil).
+ */
+#ifndef BXB200_H
+#define BXB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BXG_HOST   0
+#define BXG_DEVICE 1
+
+#define BXG_OK            0
+#define BXG_ERR_CUDA     -1   /* CUDA runtime / no device */
+#define BXG_ERR_ARG      -2   /* invalid argument */
+#define BXG_ERR_MISMATCH -3   /* operands of different size / geometry */
+#define BXG_ERR_NCCL     -4
+#define BXG_ERR_STATE    -5   /* call sequence error (e.g. fetch before find) */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Runtime
+ * ------------------------------------------------------------------------------------------------------------------ */
+int         bxg_init(int device);                 /* bind this thread/process to `device`, create the stream       */
+int         bxg_device_count(int *n);
+int         bxg_device_info(char *name, int name_cap, int *sm_count, int64_t *total_mem, int *cc_major, int *cc_minor);
+const char *bxg_last_error(void);                 /* thread-local message of the last failing call                 */
+const char *bxg_version(void);
+int         bxg_sync(void);                       /* cudaStreamSynchronize(library stream)                          */
+int         bxg_launch_count(int64_t *n);         /* kernels launched by this library since bxg_init / last reset   */
+int         bxg_launch_count_reset(void);
+
+/* pinned host memory + raw device buffers (used by the host shim for staging and by bench.py for resident inputs) */
+int bxg_host_alloc(int64_t bytes, void **ptr);
+int bxg_host_free(void *ptr);
+int bxg_dev_alloc(int64_t bytes, void **dptr);
+int bxg_dev_free(void *dptr);
+int bxg_memcpy_h2d(void *dptr, const void *hptr, int64_t bytes);   /* async on the library stream */
+int bxg_memcpy_d2h(void *hptr, const void *dptr, int64_t bytes);   /* async; call bxg_sync() before reading */
+
+/* device timing on the library stream (CUDA events) */
+typedef struct bxg_timer bxg_timer_t;
+int bxg_timer_create(bxg_timer_t **t);
+int bxg_timer_free(bxg_timer_t *t);
+int bxg_timer_start(bxg_timer_t *t);
+int bxg_timer_stop(bxg_timer_t *t);
+int bxg_timer_elapsed_ms(bxg_timer_t *t, float *ms);               /* synchronises on the stop event */
+int bxg_l2_flush(void);                            /* overwrite a buffer larger than L2 (timing hygiene) */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Bit sets.   Replaces struct BinBits + binBits* (src/binBits.h:7-26) and Bits + bit* (src/kent/bits.h:13-59).
+ *
+ * HBM layout: one dense LSB-first uint64 bitmap of exactly `size` bits (bit p -> word p>>6, bit p&63; tail bits of the
+ * last word are kept 0), plus uint8 state[nbins] in {0=ALL_ZERO sentinel, 1=ALL_ONE sentinel, 2=allocated} that
+ * tracks the reference's lazy-bin state machine (binBits.c:5-6, transitions at :67-128, :230-317) -- observable only
+ * through count_range's ALL_ONE arithmetic (binBits.c:155,161), reproduced when strict != 0.
+ * granularity == 0 creates a flat BitSet (bits.h semantics: no bins, no sentinel states).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct bxg_bits bxg_bits_t;
+
+/* binBitsAlloc (binBits.c:8-17; float32 bin geometry) / bitAlloc (bits.c:51-56).  size in [1, 2^31-1]. */
+int bxg_bits_create(int32_t size, int32_t granularity, bxg_bits_t **out);
+int bxg_bits_free(bxg_bits_t *b);                                                   /* binBitsFree / bitFree   */
+int bxg_bits_geometry(const bxg_bits_t *b, int32_t *size, int32_t *bin_size, int32_t *nbins);
+int bxg_bits_clone(const bxg_bits_t *b, bxg_bits_t **out);                          /* bitClone (bits.c:58-66)  */
+
+/* binBitsSetRange (binBits.c:98-128) / bitSetRange (bits.c:86-109), n ranges per call; ranges must satisfy
+ * 0 <= start, 0 <= count, start+count <= size (the host shim raises the reference's IndexError first). */
+int bxg_bits_set_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *count, int64_t n, int loc);
+/* binBitsSetOne / binBitsClearOne (binBits.c:67-96), n positions per call, value 1 = set, 0 = clear */
+int bxg_bits_set_bits(bxg_bits_t *b, const int32_t *pos, int64_t n, int value, int loc);
+/* binBitsReadOne (binBits.c:49-65) for n positions */
+int bxg_bits_read(const bxg_bits_t *b, const int32_t *pos, int64_t n, uint8_t *out, int loc);
+
+/* binBitsAnd / binBitsOr / binBitsNot (binBits.c:230-317); bitAnd/bitOr/bitXor/bitNot (bits.c:222-263). In place on a. */
+int bxg_bits_and(bxg_bits_t *a, const bxg_bits_t *b);
+int bxg_bits_or(bxg_bits_t *a, const bxg_bits_t *b);
+int bxg_bits_xor(bxg_bits_t *a, const bxg_bits_t *b);      /* flat BitSet only in the reference (bitset.pyx:157-159) */
+int bxg_bits_not(bxg_bits_t *a);
+/* fused a &= b ; *count = popcount(a)   (bed_intersect_basewise.py:25-28 followed by a coverage count) */
+int bxg_bits_and_count(bxg_bits_t *a, const bxg_bits_t *b, int64_t *count);
+
+/* binBitsCountRange (binBits.c:130-178) / bitCountRange (bits.c:118-141) for n (start,count) pairs -> int32 counts.
+ * strict != 0 reproduces the reference's ALL_ONE-sentinel arithmetic; strict == 0 returns the true popcount. */
+int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *count, int64_t n,
+                          int32_t *out, int strict, int loc);
+int bxg_bits_count_all(const bxg_bits_t *b, int64_t *count);                  /* count_range(0, size)          */
+
+/* binBitsFindSet / binBitsFindClear (binBits.c:180-228) ; bitFindSet/Clear with an end bound (bits.c:143-190).
+ * first position p in [start, end) whose bit == val, else `end`; end <= size. */
+int bxg_bits_next(const bxg_bits_t *b, int32_t start, int32_t end, int val, int32_t *out);
+/* The run-extraction idiom  start=next_set(end); end=next_clear(start)  (bed_intersect_basewise.py:30-38,
+ * lib/bx/bitset_utils.py:34-43) for the whole bitmap: first call counts, second fills (host arrays). */
+int bxg_bits_runs_count(bxg_bits_t *b, int64_t *nruns);
+int bxg_bits_runs_fetch(bxg_bits_t *b, int32_t *starts, int32_t *ends, int64_t nruns);
+
+/* test / interchange helpers */
+int bxg_bits_states(const bxg_bits_t *b, uint8_t *out /* nbins */);
+int bxg_bits_export_words(const bxg_bits_t *b, uint64_t *out /* ceil(size/64) */);
+int bxg_bits_import_words(bxg_bits_t *b, const uint64_t *in /* ceil(size/64) */);   /* marks every bin allocated */
+int bxg_bits_device_words(const bxg_bits_t *b, const uint64_t **dptr, int64_t *nwords);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Interval index.   Replaces IntervalNode/IntervalTree of lib/bx/intervals/intersection.pyx.
+ *
+ * One index holds `ntrees` independent trees (one per chromosome: the reference keeps dict[chrom] -> IntervalTree,
+ * scripts/bed_count_overlapping.py:17-25); ntrees == 1 is a plain IntervalTree.  Items are identified by their
+ * position in the arrays passed to bxg_itree_build (== insertion order, which fixes the reference's tie order,
+ * intersection.pyx:110-116).
+ * HBM layout: items radix-sorted by (tree, start, end>start, +/-index) into S[], E[], I[] (= in-order traversal of the
+ * reference treap), a per-tree prefix-max of E (first possible hit), a 32-ary max-of-E hierarchy for skipping, and a
+ * sampled splitter table that the find kernels stage into shared memory with a 1-D TMA bulk copy.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct bxg_itree bxg_itree_t;
+
+int bxg_itree_create(bxg_itree_t **out);
+int bxg_itree_free(bxg_itree_t *t);
+/* IntervalTree.insert x n (intersection.pyx:388-395 -> IntervalNode.insert :103-138).  tree == NULL means all items
+ * belong to tree 0.  Rebuilds the whole index (the host shim queues inserts and builds lazily). */
+int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, const int32_t *end,
+                    int64_t n, int32_t ntrees, int loc);
+int bxg_itree_size(const bxg_itree_t *t, int64_t *n, int32_t *ntrees);
+/* in-order traversal (IntervalNode.traverse, intersection.pyx:262-268): perm[k] = item index of the k-th node;
+ * tree_offsets[ntrees+1] (may be NULL) delimits each tree's slice of perm. */
+int bxg_itree_order(const bxg_itree_t *t, int32_t *perm, int64_t *tree_offsets);
+
+/* IntervalTree.find x nq (intersection.pyx:400-406 -> _intersect :180-189): for query q every item of tree qtree[q]
+ * with  end > qs[q] && start < qe[q], in in-order sequence.  Results stay in device buffers owned by the index
+ * (CSR: int64 offsets[nq+1], int32 hits[total]) until the next find; *total receives the number of hits.
+ * qtree == NULL means tree 0 for every query. */
+int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe,
+                   int64_t nq, int loc, int64_t *total);
+int bxg_itree_fetch(bxg_itree_t *t, int64_t *offsets /* nq+1 */, int32_t *hits /* total */);   /* to host */
+int bxg_itree_result_dev(const bxg_itree_t *t, const int64_t **d_offsets, const int32_t **d_hits, int64_t *nq,
+                         int64_t *total);
+/* len(find(...)) only (scripts/bed_count_overlapping.py:27-33): int32 counts[nq] written to `counts` (host or device
+ * per loc); *total (may be NULL) receives the sum. */
+int bxg_itree_count(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe,
+                    int64_t nq, int loc, int32_t *counts, int64_t *total);
+
+/* IntervalNode.left / right (intersection.pyx:192-260) = IntervalTree.before / after (:408-426): for query q the
+ * reference-ordered list of at most n[q] neighbours of position pos[q] within max_dist[q].
+ * dir = 0: before (left), 1: after (right).  CSR result fetched like find. */
+int bxg_itree_neighbors(bxg_itree_t *t, const int32_t *qtree, const int32_t *pos, const int32_t *n,
+                        const int32_t *max_dist, int64_t nq, int dir, int loc, int64_t *total);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * aggregate_scores_in_intervals inner loop (scripts/aggregate_scores_in_intervals.py:107-134 over
+ * BinnedArray.get, lib/bx/binned_array.py:89-94).  scores: dense float32, position origin+i, NaN = unset.
+ * Per window [ws,we): strict left-to-right float32 sum of the scores that are non-zero, non-NaN and not masked;
+ * count; min; max; avg = sum/count (float32).  count==0 -> avg/min/max = NaN.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct bxg_scores bxg_scores_t;
+int bxg_scores_create(const float *scores, int64_t n, int32_t origin, int loc, bxg_scores_t **out);
+int bxg_scores_free(bxg_scores_t *s);
+int bxg_aggregate(const bxg_scores_t *s, const bxg_bits_t *mask /* or NULL */,
+                  const int32_t *ws, const int32_t *we, int64_t nw, int loc,
+                  float *sum, float *avg, int32_t *count, float *mn, float *mx);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU; chromosomes are sharded with no data-path exchange; only the final per-chromosome
+ * counters are summed (NCCL all-reduce over NVLink).  NCCL is dlopen()ed on first use.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define BXG_UNIQUE_ID_BYTES 128
+int bxg_comm_unique_id(char id[BXG_UNIQUE_ID_BYTES]);                 /* rank 0; ship to the other ranks      */
+int bxg_comm_init(const char id[BXG_UNIQUE_ID_BYTES], int nranks, int rank);
+int bxg_comm_allreduce_i64(int64_t *buf, int64_t n);                   /* in-place sum over ranks (host buffer) */
+int bxg_comm_allreduce_max_f64(double *buf, int64_t n);                /* in-place max over ranks (timings)     */
+int bxg_comm_barrier(void);
+int bxg_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BXB200_H */

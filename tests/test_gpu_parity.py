@@ -1,0 +1,467 @@
+"""
+GPU parity: the CUDA path (through the Python shim -> ctypes -> C ABI of libbxb200.so) against
+  * the committed golden vectors produced by the compiled unmodified reference (tests/golden/),
+  * the reference's own unit-test known answers and doctests,
+  * the CPU restatement (oracle/) on seeded random inputs,
+bit-exact everywhere (integer / index work) and bit-exact float32 for the aggregate path.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from bx_python_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    oracle.lib()
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def bx():
+    import bx_python_b200.bitset as bitset
+    import bx_python_b200.intervals.intersection as ix
+    from bx_python_b200 import _lib, aggregate
+    _lib.lib()   # raises if there is no device: GPU tests must never pass on a fallback
+
+    class NS:
+        pass
+    ns = NS()
+    ns.bitset, ns.ix, ns.aggregate, ns.lib = bitset, ix, aggregate, _lib
+    return ns
+
+
+def tree_of(bx, s, e):
+    t = bx.ix.IntervalTree()
+    t.insert_many(s, e)
+    return t
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# find
+# ---------------------------------------------------------------------------------------------------------------
+def test_find_c1_golden(bx):
+    g = np.load(os.path.join(G, "find.npz"))
+    s, e, qs, qe = synth.c1_intervals()
+    t = tree_of(bx, s, e)
+    off, hits = t.find_batch(qs, qe)
+    assert np.array_equal(off, g["c1_offsets"])
+    assert np.array_equal(hits, g["c1_hits"])
+    assert np.array_equal(t.order(), g["c1_order"])
+    assert np.array_equal(t.count_batch(qs, qe), np.diff(g["c1_offsets"]).astype(np.int32))
+
+
+def test_find_edge_sets_golden(bx):
+    g = np.load(os.path.join(G, "find.npz"))
+    for k, (s, e, qs, qe) in enumerate(synth.edge_sets()):
+        t = tree_of(bx, s, e)
+        off, hits = t.find_batch(qs, qe)
+        assert np.array_equal(off, g[f"edge{k}_offsets"]), k
+        assert np.array_equal(hits, g[f"edge{k}_hits"]), k
+        assert np.array_equal(t.order(), g[f"edge{k}_order"]), k
+
+
+def test_find_scalar_api_reference_answers(bx):
+    Interval, IntervalTree = bx.ix.Interval, bx.ix.IntervalTree
+    # SURVEY 8(a) addendum 2 (probed on the compiled reference)
+    t = IntervalTree()
+    for i, (a, b) in enumerate([(10, 20), (15, 12), (30, 30), (-5, 3), (20, 25)]):
+        t.insert(a, b, i)
+    assert t.find(-100, 100) == [3, 0, 1, 4, 2]
+    assert t.find(18, 11) == [0]
+    assert t.find(20, 20) == []
+    assert t.find(19, 21) == [0, 4]
+    assert t.find(30, 30) == []
+    assert t.find(29, 31) == [2]
+    assert t.find(1.5, 3) == [3]
+    with pytest.raises(OverflowError):
+        t.find(2**31, 5)
+    t2 = IntervalTree()
+    for name, (a, b) in zip("a b z0 c z1 d e y".split(), [(5, 10), (5, 7), (5, 5), (5, 20), (5, 5), (3, 6), (5, 6), (4, 4)]):
+        t2.insert(a, b, name)
+    assert t2.find(0, 100) == "d y z1 z0 a b c e".split()
+    # doctest intersection.pyx:341-361
+    it = IntervalTree()
+    it.insert(0, 10, "food")
+    it.insert(3, 7, dict(foo="bar"))
+    assert it.find(2, 5) == ["food", {"foo": "bar"}]
+    it = IntervalTree()
+    for a, b in [(0, 10), (3, 7), (3, 40), (13, 50)]:
+        it.insert_interval(Interval(a, b))
+    assert repr(it.find(30, 50)) == "[Interval(3, 40), Interval(13, 50)]"
+    assert it.find(100, 200) == []
+    # intersection_tests.py:158-186
+    iv = IntervalTree()
+    n = 0
+    for i in range(1, 1000, 80):
+        iv.insert(i, i + 10, {"value": i * i})
+        iv.add(i + 20, i + 30, {"astr": str(i * i)})
+        iv.insert_interval(Interval(i + 40, i + 50, value={"astr": str(i * i)}))
+        iv.add_interval(Interval(i + 60, i + 70, value={"astr": str(i * i)}))
+        n += 4
+    assert len(iv.find(100, 200)) == 5
+    seen = []
+    iv.traverse(seen.append)
+    assert len(seen) == n and all(node.interval for node in seen)
+    # lazily rebuilt after a mutation
+    iv.insert(150, 160, "late")
+    assert "late" in iv.find(100, 200) and len(iv.find(100, 200)) == 6
+
+
+def test_find_lotsa_reference_case(bx):
+    # intersection_tests.py:104-155: 100k zero-length intervals + 600 duplicates of (0,1)
+    mx = 1000000
+    s = [1] + list(range(0, mx, 10)) + [0] * 600
+    e = [2] + list(range(0, mx, 10)) + [1] * 600
+    t = tree_of(bx, s, e)
+    rng = np.random.default_rng(5)
+    qs = rng.integers(0, mx - 10000, 25).astype(np.int32)
+    qe = (qs + rng.integers(100, 10000, 25)).astype(np.int32)
+    off, hits = t.find_batch(qs, qe)
+    S, E = np.array(s), np.array(e)
+    for q in range(25):
+        h = hits[off[q]:off[q + 1]]
+        assert len(h) > 0
+        assert np.all(((E[h] >= qs[q]) & (E[h] <= qe[q])) | ((S[h] <= qe[q]) & (S[h] >= qs[q])))
+    off2, hits2 = t.find_batch([0], [1])
+    assert off2[1] == 600   # the 600 (0,1) duplicates; the zero-length (0,0) item does not overlap [0,1)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_find_random_vs_oracle(bx, orc, seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1, 200000))
+    nq = 50000
+    G_ = int(rng.choice([50, 5000, 1_000_000, 200_000_000]))
+    if seed % 2:
+        s = rng.integers(-3, G_, n)
+        e = s + rng.integers(-2, 6, n)
+        qs = rng.integers(-5, G_ + 5, nq)
+        qe = qs + rng.integers(-3, 12, nq)
+    else:
+        s, e = synth.uniform_intervals(rng, n, G_ + 3000, 2000)
+        qs, qe = synth.uniform_intervals(rng, nq, G_ + 3000, 2000)
+    s, e, qs, qe = (np.asarray(a, np.int32) for a in (s, e, qs, qe))
+    off, hits = tree_of(bx, s, e).find_batch(qs, qe)
+    ooff, ohits = orc.OracleIntervalTree(s, e).find(qs, qe)
+    assert np.array_equal(off, ooff) and np.array_equal(hits, ohits)
+
+
+def test_find_adversarial_long_intervals(bx, orc):
+    """A few chromosome-long intervals at the front defeat the prefix-max bound; the max hierarchy must skip."""
+    rng = np.random.default_rng(77)
+    n, nq, G_ = 300000, 20000, 50_000_000
+    s, e = synth.uniform_intervals(rng, n, G_, 500)
+    s[:3] = [0, 5, 10]
+    e[:3] = [G_, G_ - 7, G_ // 2]
+    qs, qe = synth.uniform_intervals(rng, nq, G_, 500)
+    off, hits = tree_of(bx, s, e).find_batch(qs, qe)
+    ooff, ohits = orc.OracleIntervalTree(s, e).find(qs, qe)
+    assert np.array_equal(off, ooff) and np.array_equal(hits, ohits)
+
+
+def test_forest_vs_per_tree_oracle(bx, orc):
+    """hg38-shaped: one index holding 24 trees, queries carry their chromosome id."""
+    n, nq = 400000, 400000
+    db = synth.genome_intervals(n, 2001)
+    qq = synth.genome_intervals(nq, 2002)
+    tid = np.concatenate([np.full(len(s), c, np.int32) for c, (s, e) in enumerate(db)])
+    S = np.concatenate([s for s, e in db]); E = np.concatenate([e for s, e in db])
+    qt = np.concatenate([np.full(len(s), c, np.int32) for c, (s, e) in enumerate(qq)])
+    QS = np.concatenate([s for s, e in qq]); QE = np.concatenate([e for s, e in qq])
+    # shuffle items and queries so neither arrives grouped by chromosome
+    rng = np.random.default_rng(9)
+    p = rng.permutation(len(S)); tid, S, E = tid[p], S[p], E[p]
+    pq = rng.permutation(len(QS)); qt, QS, QE = qt[pq], QS[pq], QE[pq]
+    forest = bx.ix.IntervalForest(24).build(tid, S, E)
+    off, hits = forest.find_batch(qt, QS, QE)
+    cnt = forest.count_batch(qt, QS, QE)
+    assert np.array_equal(cnt, np.diff(off).astype(np.int32))
+    for c in range(24):
+        items = np.nonzero(tid == c)[0]
+        o = orc.OracleIntervalTree(S[items], E[items])
+        qsel = np.nonzero(qt == c)[0]
+        ooff, ohits = o.find(QS[qsel], QE[qsel])
+        ohits = items[ohits].astype(np.int32)          # local -> global item ids
+        for j in range(0, len(qsel), max(1, len(qsel) // 300)):
+            q = qsel[j]
+            assert np.array_equal(hits[off[q]:off[q + 1]], ohits[ooff[j]:ooff[j + 1]])
+        assert np.array_equal(np.diff(off)[qsel], np.diff(ooff))
+    # out-of-range chromosome ids yield no hits
+    off2, hits2 = forest.find_batch([24, -1], [0, 0], [10**9, 10**9])
+    assert off2.tolist() == [0, 0, 0]
+
+
+def test_find_large_properties(bx):
+    """Size-independent checks at 2M x 2M: every hit satisfies the predicate, per-query hits are in index order,
+    counts equal an independent rank formula (valid because every synthetic interval is proper)."""
+    n = nq = 2_000_000
+    s, e = synth.uniform_intervals(np.random.default_rng(11), n, 248956422)
+    qs, qe = synth.uniform_intervals(np.random.default_rng(12), nq, 248956422)
+    t = tree_of(bx, s, e)
+    off, hits = t.find_batch(qs, qe)
+    cnt = np.diff(off)
+    q_of_hit = np.repeat(np.arange(nq), cnt)
+    assert np.all(e[hits] > qs[q_of_hit]) and np.all(s[hits] < qe[q_of_hit])
+    expected = np.searchsorted(np.sort(s), qe, "left") - np.searchsorted(np.sort(e), qs, "right")
+    assert np.array_equal(cnt, expected)
+    order = t.order()
+    rank = np.empty(n, np.int64); rank[order] = np.arange(n)
+    r = rank[hits]
+    inc = np.ones(len(hits), bool); inc[1:] = r[1:] > r[:-1]
+    inc[off[:-1][cnt > 0]] = True
+    assert inc.all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bitsets
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cls", ["flat", "binned"])
+def test_bitset_reference_unit_tests(bx, cls):
+    # lib/bx/bitset_tests.py:10-119
+    def new(size=100):
+        return bx.bitset.BitSet(size) if cls == "flat" else bx.bitset.BinnedBitSet(size, size % 11)
+
+    def bits(b):
+        return [b[i] for i in range(b.size)]
+    with pytest.raises(ValueError):
+        new(4000000000)
+    b = new()
+    with pytest.raises(IndexError):
+        b.set(-5)
+    with pytest.raises(IndexError):
+        b.set(110)
+    l = [0] * 100
+    assert bits(b) == l
+    for pos in (11, 14, 70, 16):
+        b.set(pos); l[pos] = 1
+    for pos in (14, 80, 16):
+        b.clear(pos); l[pos] = 0
+    assert bits(b) == l
+    b = new(); l = [0] * 100
+    for s, e in ((11, 14), (20, 75), (90, 99)):
+        b.set_range(s, e - s)
+        for p in range(s, e):
+            l[p] = 1
+    assert bits(b) == l
+    b = new()
+    for s, e in ((11, 14), (20, 75), (90, 100)):
+        b.set_range(s, e - s)
+    assert [b.count_range(0, 0), b.count_range(0, 20), b.count_range(25, 25), b.count_range(80, 20),
+            b.count_range(0, 100)] == [0, 3, 25, 10, 68]
+    assert [b.next_set(0), b.next_set(13), b.next_set(15)] == [11, 13, 20]
+    assert [b.next_clear(0), b.next_clear(11), b.next_clear(20), b.next_clear(92)] == [0, 14, 75, 100]
+    b1, b2 = new(), new(); b1.set_range(20, 40); b2.set_range(50, 25); b1.iand(b2)
+    assert bits(b1) == [1 if 50 <= i < 60 else 0 for i in range(100)]
+    b1, b2 = new(), new(); b1.set_range(20, 40); b2.set_range(50, 25); b1.ior(b2)
+    assert bits(b1) == [1 if 20 <= i < 75 else 0 for i in range(100)]
+    b1 = new(); b1.set_range(20, 40); b1.invert()
+    assert bits(b1) == [0 if 20 <= i < 60 else 1 for i in range(100)]
+
+
+def test_bitset_survey_probes(bx):
+    B = bx.bitset.BinnedBitSet
+    geo = {(2**29, 1024): 524288, (250000000, 1024): 244141, (248956422, 1024): 243122, (100, 1): 100,
+           (100, 3): 34, (100, 1024): 1, (1000, 10): 100, (1000, 20): 50}
+    for (size, gran), bin_size in geo.items():
+        assert B(size, gran).bin_size == bin_size
+    b = B(1000, 10)
+    for args, msg in [((-1, 5), r"BitSet index \(-1\) must be non-negative."),
+                      ((1000, 0), r"1000 is larger than the size of this BitSet \(1000\)."),
+                      ((999, 2), r"End \(1001\) is larger than the size of this BinnedBitSet \(1000\)."),
+                      ((5, -1), r"Count \(-1\) must be non-negative.")]:
+        with pytest.raises(IndexError, match=msg):
+            b.set_range(*args)
+    b.set_range(5, 0)
+    assert b.count_range(0, 0) == 0
+    with pytest.raises(IndexError):
+        b.count_range(1000, 0)
+    with pytest.raises(IndexError):
+        b.next_set(1000)
+    with pytest.raises(ValueError, match="BitSets must have the same size"):
+        b.iand(B(999, 10))
+    with pytest.raises(TypeError):
+        b.iand(bx.bitset.BitSet(1000))
+    b = B(10000, 10); b.set_range(0, 10); b.invert()
+    assert [b.count_range(1500, 100), b.count_range(1000, 1000), b.count_range(1100, 1900),
+            b.count_range(0, 10000)] == [-400, 1000, 1800, 9990]
+    assert b.count_ranges([1500], [100], strict=False).tolist() == [100]
+    b = B(95, 10); b.set_range(90, 5); b.invert()
+    assert [b[i] for i in range(88, 95)] == [1, 1, 0, 0, 0, 0, 0] and b.next_set(94) == 95
+
+
+def test_bitset_golden_sequences(bx):
+    for case in json.load(open(os.path.join(G, "bitset.json"))):
+        size, gran, ops, probes = synth.bitset_case(case["seed"])
+        b = [bx.bitset.BinnedBitSet(size, gran), bx.bitset.BinnedBitSet(size, gran)]
+        for op in ops:
+            synth.apply_bitset_op(b, op)
+        ps = np.array([s for s, _ in probes], np.int32); pc = np.array([c for _, c in probes], np.int32)
+        for k in (0, 1):
+            r = case["results"][k]
+            assert b[k].bin_size == r["bin_size"]
+            assert b[k].count_ranges(ps, pc).tolist() == r["count"], case["seed"]
+            assert b[k].get_many(ps).tolist() == r["get"]
+            assert [b[k].next_set(s) for s in ps[:12].tolist()] == r["next_set"][:12]
+            assert [b[k].next_clear(s) for s in ps[:12].tolist()] == r["next_clear"][:12]
+
+
+def test_bitset_c3_golden(bx):
+    g = np.load(os.path.join(G, "bitset_c3.npz"))
+    for tag, nr in (("dense", 4000), ("sparse", 200)):
+        size = 2_500_000
+        a, b = bx.bitset.BinnedBitSet(size), bx.bitset.BinnedBitSet(size)
+        (sa, ca), (sb, cb), (qs, qc) = synth.c3_case(size, nr, 31)
+        a.set_ranges(sa, ca); b.set_ranges(sb, cb)
+        assert a.count_range(0, size) == int(g[f"{tag}_count_a"])
+        assert a.and_count(b) == int(g[f"{tag}_count_and"])
+        assert a.count_range(0, size) == int(g[f"{tag}_count_and"])
+        assert np.array_equal(a.count_ranges(qs, qc), g[f"{tag}_counts"])
+        rs, re = a.runs()
+        assert np.array_equal(np.stack([rs, re], 1), g[f"{tag}_runs"])
+        a.invert()
+        assert np.array_equal(a.count_ranges(qs, qc), g[f"{tag}_inv_counts"])
+        assert a.count_range(0, size) == int(g[f"{tag}_inv_total"])
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_bitset_random_vs_oracle(bx, orc, seed):
+    rng = np.random.default_rng(400 + seed)
+    size = int(rng.integers(1, 200000))
+    gran = int(rng.choice([1, 3, 10, 64, 1024]))
+    b = [bx.bitset.BinnedBitSet(size, gran) for _ in range(2)]
+    o = [orc.OracleBinnedBitSet(size, gran) for _ in range(2)]
+    for _ in range(int(rng.integers(1, 12))):
+        k = int(rng.integers(0, 2)); op = int(rng.integers(0, 6))
+        if op == 0:
+            m = int(rng.integers(1, 200))
+            s = rng.integers(0, size, m); c = rng.integers(0, np.minimum(size - s, max(1, size // 50)) + 1)
+            b[k].set_ranges(s, c); o[k].set_ranges(s, c)
+        elif op == 1:
+            p = int(rng.integers(0, size)); b[k].set(p); o[k].set(p)
+        elif op == 2:
+            p = int(rng.integers(0, size)); b[k].clear(p); o[k].clear(p)
+        elif op == 3:
+            b[k].invert(); o[k].invert()
+        elif op == 4:
+            b[k].iand(b[1 - k]); o[k].iand(o[1 - k])
+        else:
+            b[k].ior(b[1 - k]); o[k].ior(o[1 - k])
+    for x, y in zip(b, o):
+        assert (x.size, x.bin_size) == (y.size, y.bin_size)
+        assert np.array_equal(x.bin_states(), y.states())
+        assert np.array_equal(x.to_words(), y.words())
+        s = rng.integers(0, size, 500); c = rng.integers(0, size - s + 1)
+        assert np.array_equal(x.count_ranges(s, c), y.count_ranges(s, c))
+        assert np.array_equal(x.get_many(s), y.read(s))
+        rs, re = x.runs(); ors, ore = y.runs()
+        assert np.array_equal(rs, ors) and np.array_equal(re, ore)
+        for p in s[:10].tolist():
+            assert x.next_set(p) == y.next_set(p) and x.next_clear(p) == y.next_clear(p)
+        assert x.count_all() == int(np.unpackbits(y.words().view(np.uint8)).sum())
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_flat_bitset_vs_oracle(bx, orc, seed):
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(1, 50000))
+    b = [bx.bitset.BitSet(n) for _ in range(2)]
+    o = [orc.OracleBitSet(n) for _ in range(2)]
+    for _ in range(20):
+        k = int(rng.integers(0, 2)); op = int(rng.integers(0, 7))
+        if op == 0:
+            s = int(rng.integers(0, n)); c = int(rng.integers(0, n - s + 1)); b[k].set_range(s, c); o[k].set_range(s, c)
+        elif op == 1:
+            p = int(rng.integers(0, n)); b[k].set(p); o[k].set(p)
+        elif op == 2:
+            p = int(rng.integers(0, n)); b[k].clear(p); o[k].clear(p)
+        elif op == 3:
+            b[k].invert(); o[k].invert()
+        elif op == 4:
+            b[k] &= b[1 - k]; o[k].iand(o[1 - k])
+        elif op == 5:
+            b[k] |= b[1 - k]; o[k].ior(o[1 - k])
+        else:
+            b[k].ixor(b[1 - k]); o[k].ixor(o[1 - k])
+    for x, y in zip(b, o):
+        for _ in range(40):
+            s = int(rng.integers(0, n)); e = int(rng.integers(s, n + 1))
+            assert x.count_range(s, e - s) == y.count_range(s, e - s)
+            assert x.next_set(s, e) == y.next_set(s, e)
+            assert x.next_clear(s, e) == y.next_clear(s, e)
+            assert x[s] == y[s]
+    c = b[0].clone()
+    assert np.array_equal(c.to_words(), b[0].to_words())
+
+
+def test_bitset_chromosome_scale_properties(bx):
+    """C3 shape at full size for one chromosome pair: De Morgan, popcount identities, run/coverage consistency."""
+    size = 250_000_000
+    (sa, ca), (sb, cb), (qs, qc) = synth.c3_case(size, 400_000, 1, nq=100_000)
+    a, b = bx.bitset.BinnedBitSet(size), bx.bitset.BinnedBitSet(size)
+    a.set_ranges(sa, ca); b.set_ranges(sb, cb)
+    na, nb = a.count_all(), b.count_all()
+    assert na == 199484802                       # probe of the compiled reference with seed 1
+    u = bx.bitset.BinnedBitSet(size); u.ior(a); u.ior(b)
+    nand = a.and_count(b)                        # a := a & b
+    assert u.count_all() == na + nb - nand       # inclusion-exclusion
+    rs, re = a.runs()
+    assert int(np.sum(re.astype(np.int64) - rs)) == nand and np.all(rs[1:] > re[:-1])
+    cnt = a.count_ranges(qs, qc)
+    assert cnt.min() >= 0 and np.all(cnt <= qc)
+    assert a.count_range(0, size) == nand
+    a.invert()
+    assert a.count_all() == size - nand
+    assert np.array_equal(a.count_ranges(qs, qc, strict=False), qc - cnt)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# aggregate
+# ---------------------------------------------------------------------------------------------------------------
+def test_aggregate_golden(bx):
+    for case in json.load(open(os.path.join(G, "aggregate.json"))):
+        origin, v, ws, we, mask_runs = synth.aggregate_case(case["seed"])
+        track = bx.aggregate.ScoreTrack(v, origin)
+        mask = None
+        if mask_runs is not None:
+            mask = bx.bitset.BinnedBitSet()
+            for a, b in mask_runs:
+                mask.set_range(a, b - a)
+        res = track.aggregate(ws, we, mask)
+        got = [bx.aggregate.format_line(res, w) for w in range(len(ws))]
+        assert got == case["lines"], case["seed"]
+
+
+def test_aggregate_survey_probe(bx):
+    v = np.array([0.1, 0.2, 0.0, 0.3, np.nan, 1e-3, 16777216, 1, 1], np.float32)
+    res = bx.aggregate.ScoreTrack(v, 0).aggregate([0, 0, 2], [4, 9, 3])
+    f = bx.aggregate.format_line
+    assert f(res, 0) == ["0.2", "0.1", "0.3"]
+    assert f(res, 1) == ["2.3967452e+06", "0.001", "1.6777216e+07"]
+    assert f(res, 2) == ["nan", "nan", "nan"]
+
+
+def test_aggregate_random_vs_oracle(bx, orc):
+    rng = np.random.default_rng(55)
+    n, nw = 2_000_000, 200_000
+    origin = 12345
+    v = synth.aggregate_scores(rng, n)
+    ws = rng.integers(origin - 50, origin + n + 20, nw).astype(np.int32)
+    we = (ws + rng.integers(0, 80, nw)).astype(np.int32)
+    mask = bx.bitset.BinnedBitSet(origin + n + 200)
+    ms = rng.integers(origin, origin + n, 5000); mc = rng.integers(1, 30, 5000)
+    mask.set_ranges(ms, mc)
+    res = bx.aggregate.ScoreTrack(v, origin).aggregate(ws, we, mask)
+    dense = np.full(origin + n, np.nan, np.float32); dense[origin:] = v
+    ores = orc.aggregate(dense, ws, we, mask.to_words())
+    for k in ("sum", "avg", "min", "max"):
+        assert np.array_equal(res[k].view(np.uint32), ores[k].view(np.uint32)), k
+    assert np.array_equal(res["count"], ores["count"])
