@@ -1,0 +1,506 @@
+#!/usr/bin/env python
+"""
+bench.py -- the hot-path benchmark (contract: one JSON line on stdout from rank 0).
+
+Workload at N GPUs (BASELINE.json configs[1], the config the metric is quoted on):
+  * database: 10 M random hg38-shaped intervals (24 chromosomes, start~U, len~U{1..2000}), one device index per rank
+    holding the chromosomes LPT-assigned to that rank;
+  * queries: N x 10 M intervals of the same law ("weak" scaling: 10 M queries per GPU), routed to the rank that owns
+    their chromosome; no data-path collective; the per-chromosome hit counters are summed with one NCCL all-reduce.
+  A "step" is one batched find() over the rank's queries: count pass, exclusive scan, fill pass -> ordered CSR hit
+  lists (bit-identical to bx.intervals.intersection order; checked against the oracle on a sample every run).
+
+  value  = queries/s with queries and results resident in HBM (CUDA events on the library stream, max over ranks)
+  e2e    = queries/s through the host API with pinned HOST buffers: H2D of (chrom,start,end), find, D2H of
+           (offsets, hits) inside the timed region
+  roofline      = the dominant find kernel: algorithmic bytes / CUDA-event time vs the measured HBM peak
+  cpu_baseline  = the reference's Cython IntervalTree (oracle/_ref) timed on this box's host cores (bounded sample)
+  extra.bitset  = BinnedBitSet AND+count over 24 chromosome-length bitmaps (BASELINE configs[2]), GB/s and HBM fraction
+
+--impl reference: the unmodified reference (oracle/_ref, compiled from /root/reference by oracle/Makefile) on all
+host cores, sharded per chromosome with multiprocessing, same metric/config; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from bx_python_b200 import synth  # noqa: E402
+from bx_python_b200.dist import Comm, env_rank, lpt_assign  # noqa: E402
+
+METRIC = "interval_overlap_queries_per_sec"
+UNIT = "queries/s"
+N_DB = 10_000_000
+NQ_PER_GPU = 10_000_000
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------------------
+def make_workload(world, n_db, nq_per_gpu):
+    """-> per-chromosome database [(s,e)] and queries [(s,e)] (numpy int32), and the chromosome -> rank shards."""
+    db = synth.genome_intervals(n_db, 2001)
+    qq = synth.genome_intervals(nq_per_gpu * world, 2002)
+    weights = [len(q[0]) + 0.25 * len(d[0]) for q, d in zip(qq, db)]
+    shards = lpt_assign(weights, world)
+    return db, qq, shards
+
+
+def flatten(per_chrom, chroms):
+    """Concatenate the selected chromosomes; tree ids are LOCAL (0..len(chroms)-1)."""
+    tid = np.concatenate([np.full(len(per_chrom[c][0]), k, np.int32) for k, c in enumerate(chroms)])
+    s = np.concatenate([per_chrom[c][0] for c in chroms])
+    e = np.concatenate([per_chrom[c][1] for c in chroms])
+    return tid, s, e
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for k, nme in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference (CPU) arm
+# ---------------------------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    """Build the reference IntervalTree for some chromosomes and time find() on a bounded query sample."""
+    chroms, db, qs_list, repeats = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    from bx.intervals.intersection import IntervalTree  # the unmodified reference, compiled by oracle/Makefile
+    t0 = time.perf_counter()
+    trees = []
+    for (s, e) in db:
+        t = IntervalTree()
+        ins = t.insert
+        for a, b in zip(s.tolist(), e.tolist()):
+            ins(a, b, None)
+        trees.append(t)
+    build = time.perf_counter() - t0
+    times, hits, nq = [], 0, 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        hits = nq = 0
+        for t, (qs, qe) in zip(trees, qs_list):
+            f = t.find
+            for a, b in zip(qs.tolist(), qe.tolist()):
+                hits += len(f(a, b))
+            nq += len(qs)
+        times.append(time.perf_counter() - t0)
+    return build, times, hits, nq
+
+
+def reference_rate(db, qq, sample_frac, workers, repeats=1, chroms=None):
+    """queries/s of the compiled reference on `workers` processes; chromosome-sharded; find time only.
+    Every chromosome keeps its FULL database (so hits/query match the GPU workload); queries are subsampled."""
+    import multiprocessing as mp
+    chroms = list(range(len(db))) if chroms is None else chroms
+    nq = {c: max(1, int(len(qq[c][0]) * sample_frac)) for c in chroms}
+    shards = lpt_assign([len(db[c][0]) + nq[c] for c in chroms], min(workers, len(chroms)))
+    jobs = []
+    for sh in shards:
+        cs = [chroms[i] for i in sh]
+        jobs.append((cs, [db[c] for c in cs], [(qq[c][0][:nq[c]], qq[c][1][:nq[c]]) for c in cs], repeats))
+    if len(jobs) == 1:
+        res = [_ref_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
+            res = pool.map(_ref_worker, jobs)
+    total_q = sum(r[3] for r in res)
+    total_hits = sum(r[2] for r in res)
+    per_step = [max(r[1][k] for r in res) for k in range(repeats)]      # slowest shard bounds each step
+    return {"rates": [total_q / t for t in per_step], "times": per_step, "queries": total_q, "hits": total_hits,
+            "build_s": max(r[0] for r in res), "workers": len(jobs)}
+
+
+def run_reference(args):
+    rank, world, _ = env_rank()
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    if not orc.ref_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return
+    db, qq, _ = make_workload(max(1, args.gpus), args.n_db, args.nq)
+    cores = os.cpu_count() or 1
+    workers = min(cores, 24)
+    frac = args.ref_sample
+    r = reference_rate(db, qq, frac, workers, repeats=args.steps + args.warmup)
+    times = r["times"][args.warmup:]
+    val = r["queries"] * len(times) / sum(times)
+    sample = (f"all 24 chromosomes at full database density ({args.n_db} intervals, built once in {r['build_s']:.1f} s, "
+              f"not timed), first {frac:.3%} of each chromosome's queries ({r['queries']} queries, {r['hits']} hits) "
+              f"per step; {r['workers']} processes (one tree per chromosome, LPT)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args, max(1, args.gpus)),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["workers"], "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores": cores,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": "find: 10M hg38-shaped intervals (24 chromosomes) vs 10M queries per GPU, ordered CSR hit lists",
+            "n_intervals": args.n_db, "n_queries": args.nq * world, "queries_per_gpu": args.nq,
+            "sharding": "per-chromosome LPT, no data-path collective; NCCL all-reduce of per-chromosome hit counts",
+            "l2_policy": "inputs larger than L2 (index 160 MB + queries 120 MB + results >300 MB per step vs 126 MB L2)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as C
+
+    rank, world, local_rank = env_rank()
+    os.environ.setdefault("BXB200_DEVICE", str(local_rank))
+    from bx_python_b200 import _lib
+    from bx_python_b200._lib import check, ptr
+    from bx_python_b200.intervals import IntervalForest
+    L = _lib.lib()
+    comm = Comm("nccl")
+    info = _lib.device_info()
+    t_gen = time.perf_counter()
+    db, qq, shards = make_workload(world, args.n_db, args.nq)
+    mine = shards[rank]
+    tid, s, e = flatten(db, mine)
+    qt, qs, qe = flatten(qq, mine)
+    # shuffle queries so they arrive in file order (not grouped by chromosome), as a BED file would deliver them
+    perm = np.random.default_rng(7 + rank).permutation(len(qs))
+    qt, qs, qe = qt[perm], qs[perm], qe[perm]
+    nq = len(qs)
+    if rank == 0:
+        log(f"device {info['name']} x{world}; rank0 owns chroms {mine}: {len(s)} intervals, {nq} queries "
+            f"(gen {time.perf_counter() - t_gen:.1f}s)")
+
+    # ---- build (not part of the step; reported) ----------------------------------------------------------------------
+    forest = IntervalForest(len(mine))
+    timer = _lib.Timer()
+    d_tid, d_s, d_e = _lib.DeviceBuffer(tid), _lib.DeviceBuffer(s), _lib.DeviceBuffer(e)
+    build_ms = []
+    for _ in range(3):
+        timer.start()
+        check(L.bxg_itree_build(forest.handle, d_tid.ptr, d_s.ptr, d_e.ptr, len(s), len(mine), _lib.DEVICE))
+        timer.stop()
+        build_ms.append(timer.elapsed_ms())
+    forest.n = len(s)
+    del d_tid, d_s, d_e
+
+    # ---- value: queries + results resident in HBM ---------------------------------------------------------------------
+    d_qt, d_qs, d_qe = _lib.DeviceBuffer(qt), _lib.DeviceBuffer(qs), _lib.DeviceBuffer(qe)
+    total = C.c_int64()
+
+    def step_dev():
+        check(L.bxg_itree_find(forest.handle, d_qt.ptr, d_qs.ptr, d_qe.ptr, nq, _lib.DEVICE, C.byref(total)))
+
+    for _ in range(args.warmup):
+        step_dev()
+    _lib.sync()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    comm.barrier()
+    _lib.sync()
+    check(L.bxg_launch_count_reset())
+    t0 = time.perf_counter()
+    timer.start()
+    for _ in range(args.steps):
+        step_dev()
+    timer.stop()
+    ms = timer.elapsed_ms()
+    _lib.sync()
+    t1 = time.perf_counter()
+    comm.barrier()
+    launches = _lib.launch_count()
+    ms_max = float(comm.allreduce_max_f64(np.array([ms]))[0])
+    hits_total = total.value
+    q_all = int(comm.allreduce_sum_i64(np.array([nq]))[0])
+    value = q_all * args.steps / (ms_max * 1e-3)
+
+    # ---- per-kernel CUDA-event times for the roofline (separate pass so event overhead is not in `value`) --------------
+    _lib.profile_enable(True)
+    for _ in range(args.steps):
+        step_dev()
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    clock_summary = None
+    if rank == 0:
+        time.sleep(0.2)
+        clocks.stop()
+        clock_summary = clocks.summary(t0, t1)
+
+    # ---- parity spot check against the oracle (every run; outside the timed regions) -----------------------------------
+    parity = None
+    if rank == 0:
+        parity = spot_check(forest, tid, s, e, qt, qs, qe, total.value)
+
+    # ---- per-chromosome hit counts, reduced over ranks with NCCL -------------------------------------------------------
+    off = np.empty(nq + 1, np.int64)
+    check(L.bxg_itree_fetch(forest.handle, ptr(off), None))
+    cnt = np.diff(off)
+    per_chrom = np.zeros(24, np.int64)
+    np.add.at(per_chrom, np.asarray(mine)[qt], cnt)
+    per_chrom = comm.allreduce_sum_i64(per_chrom)
+    hits_all = int(per_chrom.sum())
+
+    # ---- e2e: pinned host buffers in, host CSR out ---------------------------------------------------------------------
+    h_qt, h_qs, h_qe = (_lib.PinnedArray(nq, np.int32) for _ in range(3))
+    h_qt.array[:], h_qs.array[:], h_qe.array[:] = qt, qs, qe
+    h_off = _lib.PinnedArray(nq + 1, np.int64)
+    h_hits = _lib.PinnedArray(int(hits_total * 1.05) + 1024, np.int32)
+
+    def step_host():
+        check(L.bxg_itree_find(forest.handle, ptr(h_qt.array), ptr(h_qs.array), ptr(h_qe.array), nq, _lib.HOST,
+                               C.byref(total)))
+        check(L.bxg_itree_fetch(forest.handle, ptr(h_off.array), ptr(h_hits.array)))
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    comm.barrier()
+    _lib.sync()
+    e2e_steps = max(1, min(args.steps, 5))
+    tw = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    _lib.sync()
+    e2e_s = time.perf_counter() - tw
+    e2e_max = float(comm.allreduce_max_f64(np.array([e2e_s]))[0])
+    e2e_value = q_all * e2e_steps / e2e_max
+    assert np.array_equal(h_off.array, off), "host-path offsets differ from device-path offsets"
+
+    extra = {"build_ms": min(build_ms), "hits_per_step": hits_all, "hits_per_query": hits_all / q_all,
+             "per_chrom_hits_checksum": int((per_chrom * np.arange(1, 25)).sum()), "parity_spot_check": parity}
+
+    if rank != 0:
+        comm.close()
+        return
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    n_items = len(s)
+    alg = {
+        # per launch, bytes that must move (DESIGN.md "algorithmic bytes"):
+        # count pass: read (chrom,start,end) 12 B/query, write (count,lo,hi) 12 B/query, read S,PM,E once 12 B/item
+        "k_find<false>": 24 * nq + 12 * n_items,
+        # fill pass: read start,lo,hi,offset 20 B/query, read E once 4 B/item, read I + write hit 8 B/hit
+        "k_find<true>": 20 * nq + 4 * n_items + 8 * hits_total,
+    }
+    kern = {}
+    for name, (n_l, tot_ms) in prof.items():
+        key = name.replace("(", "").replace(")", "")
+        kern[key] = {"launches": n_l, "avg_ms": tot_ms / max(1, n_l)}
+    dom = max((k for k in kern if k.startswith("k_find")), key=lambda k: kern[k]["avg_ms"] * kern[k]["launches"])
+    dom_ms = kern[dom]["avg_ms"]
+    achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except (OSError, ValueError):
+        pass
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dom_ms,
+                "note": "find is latency/L2-bound, not HBM-bound (SURVEY 8d): frac is reported, not targeted"}
+    step_ms = sum(v["avg_ms"] * v["launches"] for v in kern.values()) / args.steps
+    extra["kernels"] = {k: {"avg_ms": round(v["avg_ms"], 4), "per_step": v["launches"] / args.steps,
+                            "share": round(v["avg_ms"] * v["launches"] / args.steps / step_ms, 4)} for k, v in kern.items()}
+
+    # ---- bitset AND (configs[2]) -----------------------------------------------------------------------------------------
+    if not args.no_bitset:
+        extra["bitset"] = bench_bitset(args, peak, peak_src)
+
+    # ---- CPU baseline (bounded sample, single thread = the reference's only native mode) -----------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(db, qq)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clock_summary, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(12 * nq), "d2h_bytes_per_step": int(8 * (nq + 1) + 4 * hits_total),
+                "steps": e2e_steps, "timing": "host wall clock around find()+fetch() incl. both copies, max over ranks"},
+        "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+    }
+    print(json.dumps(line))
+    comm.close()
+
+
+def spot_check(forest, tid, s, e, qt, qs, qe, total):
+    """Ordered hit lists of a query sample vs the oracle restatement; returns a short report."""
+    from bx_python_b200 import _lib
+    from bx_python_b200._lib import check, ptr
+    from oracle import oracle as orc
+    L = _lib.lib()
+    nq = len(qs)
+    off = np.empty(nq + 1, np.int64)
+    hits = np.empty(total, np.int32)
+    check(L.bxg_itree_fetch(forest.handle, ptr(off), ptr(hits)))
+    checked = 0
+    for c in (0, len(np.unique(tid)) - 1):
+        items = np.nonzero(tid == c)[0]
+        o = orc.OracleIntervalTree(s[items], e[items])
+        qsel = np.nonzero(qt == c)[0][:20000]
+        ooff, ohits = o.find(qs[qsel], qe[qsel])
+        ohits = items[ohits].astype(np.int32)
+        for j, q in enumerate(qsel):
+            if not np.array_equal(hits[off[q]:off[q + 1]], ohits[ooff[j]:ooff[j + 1]]):
+                raise AssertionError(f"parity failure: tree {c} query {q}")
+        checked += len(qsel)
+    return f"{checked} queries bit-identical to oracle (ordered hit lists)"
+
+
+def cpu_baseline(db, qq):
+    from oracle import oracle as orc
+    c = 20   # chr21: the smallest chromosome keeps the sample at a few seconds; full database density
+    if orc.ref_available():
+        r = reference_rate(db, qq, 1.0, 1, repeats=1, chroms=[c])
+        return {"value": r["rates"][0], "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"chr21 shard at full density: {len(db[c][0])} intervals (build {r['build_s']:.1f} s, not timed), "
+                          f"{r['queries']} queries, {r['hits']} hits; unmodified bx.intervals.intersection (oracle/_ref), "
+                          f"1 thread (the reference holds the GIL)"}
+    t = orc.OracleIntervalTree(db[c][0], db[c][1])
+    t0 = time.perf_counter()
+    off, _ = t.find(qq[c][0], qq[c][1])
+    dt = time.perf_counter() - t0
+    return {"value": len(qq[c][0]) / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"chr21 shard: {len(db[c][0])} intervals, {len(qq[c][0])} queries; C restatement (oracle/bx_oracle.c)"}
+
+
+def bench_bitset(args, peak, peak_src):
+    """configs[2]: AND + count over 24 chromosome-length bitmaps (hg38 lengths), 400k ranges per operand."""
+    import ctypes as C
+
+    from bx_python_b200 import _lib
+    from bx_python_b200._lib import check
+    from bx_python_b200.bitset import BinnedBitSet
+    L = _lib.lib()
+    A, B = [], []
+    words = 0
+    for c, size in enumerate(synth.HG38_LENS.tolist()):
+        (sa, ca), (sb, cb), _ = synth.c3_case(size, 400_000, c, nq=1)
+        a, b = BinnedBitSet(size), BinnedBitSet(size)
+        a.set_ranges(sa, ca)
+        b.set_ranges(sb, cb)
+        A.append(a)
+        B.append(b)
+        words += (size + 63) // 64
+    timer = _lib.Timer()
+    n = C.c_int64()
+
+    def one_pass(count):
+        for a, b in zip(A, B):
+            if count:
+                check(L.bxg_bits_and_count(a._h, b._h, None))
+            else:
+                check(L.bxg_bits_and(a._h, b._h))
+    res = {}
+    for name, count in (("and", False), ("and_count", True)):
+        for _ in range(3):
+            one_pass(count)
+        _lib.sync()
+        reps = 10
+        timer.start()
+        for _ in range(reps):
+            one_pass(count)
+        timer.stop()
+        ms = timer.elapsed_ms() / reps
+        gbs = 3 * words * 8 / (ms * 1e-3) / 1e9
+        res[name] = {"ms_per_pass": ms, "gbs": gbs, "frac": gbs / peak}
+    check(L.bxg_bits_count_all(A[0]._h, C.byref(n)))
+    res.update({"bitmaps": 48, "total_bits": int(synth.HG38_LENS.sum()), "algorithmic_bytes_per_pass": 3 * words * 8,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "bound": "hbm",
+                "l2_policy": "one pass streams 1.16 GB through 24 operand pairs (> 126 MB L2)"})
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-db", dest="n_db", type=int, default=N_DB)
+    ap.add_argument("--nq", type=int, default=NQ_PER_GPU, help="queries per GPU")
+    ap.add_argument("--ref-sample", type=float, default=0.02, help="fraction of each chromosome's queries per reference step")
+    ap.add_argument("--no-bitset", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

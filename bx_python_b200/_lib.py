@@ -41,6 +41,8 @@ SIGNATURES = {
     "bxg_timer_stop": [vp],
     "bxg_timer_elapsed_ms": [vp, C.POINTER(C.c_float)],
     "bxg_l2_flush": [],
+    "bxg_profile_enable": [cint],
+    "bxg_profile_report": [C.c_char_p, i64],
     "bxg_bits_create": [i32, i32, pvp],
     "bxg_bits_free": [vp],
     "bxg_bits_geometry": [vp, pi32, pi32, pi32],
@@ -156,6 +158,25 @@ def launch_count() -> int:
     n = i64()
     check(lib().bxg_launch_count(C.byref(n)))
     return n.value
+
+
+def profile_enable(on: bool):
+    check(lib().bxg_profile_enable(1 if on else 0))
+
+
+def profile_report() -> dict:
+    """-> {kernel: (launches, total_ms)} for every launch since profile_enable(True)."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().bxg_profile_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split("\t")
+        out[name] = (int(n), float(ms))
+    return out
+
+
+def l2_flush():
+    check(lib().bxg_l2_flush())
 
 
 def device_info() -> dict:

@@ -45,10 +45,16 @@ int scratch(int slot, size_t bytes, void **out);
         if (r__ != BXG_OK) return r__; \
     } while (0)
 
+// optional per-kernel CUDA-event timing (bxg_profile_enable / bxg_profile_report); no-ops when disabled
+void prof_begin(const char *name);
+void prof_end();
+
 // every kernel launch of the library goes through this so bench.py can report gpu_launches
 #define BXG_LAUNCH(kernel, grid, block, smem, ...)                                   \
     do {                                                                             \
+        bxg::prof_begin(#kernel);                                                    \
         kernel<<<(grid), (block), (smem), bxg::ctx().stream>>>(__VA_ARGS__);         \
+        bxg::prof_end();                                                             \
         bxg::ctx().launches++;                                                       \
         BXG_CUDA(cudaGetLastError());                                                \
     } while (0)

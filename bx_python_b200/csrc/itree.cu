@@ -540,7 +540,9 @@ int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, cons
     void *tmp;
     BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, t->d_off, nq + 1, c.stream));
     BXG_TRY(scratch(7, tmp_bytes, &tmp));
+    prof_begin("cub::DeviceScan::ExclusiveSum(offsets)");
     BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, t->d_off, nq + 1, c.stream));
+    prof_end();
     c.launches += 2;
     BXG_CUDA(cudaMemcpyAsync(c.mailbox + 5, t->d_off + nq, 8, cudaMemcpyDeviceToHost, c.stream));
     BXG_CUDA(cudaStreamSynchronize(c.stream));

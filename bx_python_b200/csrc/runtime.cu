@@ -3,6 +3,10 @@
 #include <nccl.h>
 #include <stdarg.h>
 
+#include <map>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 
 namespace bxg {
@@ -52,6 +56,37 @@ int stage_in(int slot, const void *src, size_t bytes, int loc, const void **dptr
     BXG_CUDA(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx().stream));
     *dptr = d;
     return BXG_OK;
+}
+
+// ---- per-kernel event profiler ------------------------------------------------------------------------------------
+struct ProfRec {
+    const char *name;
+    cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t prof_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void prof_begin(const char *name) {
+    if (!g_prof_on) return;
+    ProfRec r{name, prof_event(), prof_event()};
+    cudaEventRecord(r.a, ctx().stream);
+    g_prof.push_back(r);
+}
+void prof_end() {
+    if (!g_prof_on || g_prof.empty()) return;
+    cudaEventRecord(g_prof.back().b, ctx().stream);
 }
 
 }  // namespace bxg
@@ -191,6 +226,47 @@ int bxg_timer_stop(bxg_timer_t *t) {
 int bxg_timer_elapsed_ms(bxg_timer_t *t, float *ms) {
     BXG_CUDA(cudaEventSynchronize(t->b));
     BXG_CUDA(cudaEventElapsedTime(ms, t->a, t->b));
+    return BXG_OK;
+}
+
+int bxg_profile_enable(int on) {
+    BXG_TRY(ensure_init());
+    BXG_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    for (auto &r : g_prof) {
+        g_event_pool.push_back(r.a);
+        g_event_pool.push_back(r.b);
+    }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return BXG_OK;
+}
+
+// one line per kernel: "<name>\t<launches>\t<total_ms>\n"
+int bxg_profile_report(char *buf, int64_t cap) {
+    BXG_TRY(ensure_init());
+    BXG_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    std::map<std::string, std::pair<int64_t, double>> agg;
+    std::vector<std::string> order;
+    for (auto &r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+        auto it = agg.find(r.name);
+        if (it == agg.end()) {
+            order.push_back(r.name);
+            agg[r.name] = {1, (double)ms};
+        } else {
+            it->second.first++;
+            it->second.second += ms;
+        }
+    }
+    std::string out;
+    char line[512];
+    for (auto &n : order) {
+        snprintf(line, sizeof(line), "%s\t%lld\t%.6f\n", n.c_str(), (long long)agg[n].first, agg[n].second);
+        out += line;
+    }
+    if ((int64_t)out.size() + 1 > cap) return set_error(BXG_ERR_ARG, "profile buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
     return BXG_OK;
 }
 

@@ -64,6 +64,10 @@ int bxg_timer_start(bxg_timer_t *t);
 int bxg_timer_stop(bxg_timer_t *t);
 int bxg_timer_elapsed_ms(bxg_timer_t *t, float *ms);               /* synchronises on the stop event */
 int bxg_l2_flush(void);                            /* overwrite a buffer larger than L2 (timing hygiene) */
+/* per-kernel CUDA-event timing of every launch the library makes: enable(1) clears and starts recording,
+ * report() synchronises and writes "<kernel>\t<launches>\t<total_ms>\n" lines (bench.py's roofline uses it) */
+int bxg_profile_enable(int on);
+int bxg_profile_report(char *buf, int64_t cap);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Bit sets.   Replaces struct BinBits + binBits* (src/binBits.h:7-26) and Bits + bit* (src/kent/bits.h:13-59).
