@@ -55,6 +55,7 @@ SIGNATURES = {
     "bxg_bits_xor": [vp, vp],
     "bxg_bits_not": [vp],
     "bxg_bits_and_count": [vp, vp, pi64],
+    "bxg_bits_binop_batch": [cint, pvp, pvp, i32, vp],
     "bxg_bits_count_ranges": [vp, vp, vp, i64, vp, cint, cint],
     "bxg_bits_count_all": [vp, pi64],
     "bxg_bits_next": [vp, i32, i32, cint, pi32],
@@ -71,6 +72,7 @@ SIGNATURES = {
     "bxg_itree_order": [vp, vp, vp],
     "bxg_itree_find": [vp, vp, vp, vp, i64, cint, pi64],
     "bxg_itree_fetch": [vp, vp, vp],
+    "bxg_itree_find_host": [vp, vp, vp, vp, i64, pvp, pvp, pi64],
     "bxg_itree_result_dev": [vp, pvp, pvp, pi64, pi64],
     "bxg_itree_count": [vp, vp, vp, vp, i64, cint, vp, pi64],
     "bxg_itree_neighbors": [vp, vp, vp, vp, vp, i64, cint, cint, pi64],

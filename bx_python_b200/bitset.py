@@ -220,6 +220,39 @@ class _DeviceBits:
         check(_lib.lib().bxg_bits_import_words(self._h, ptr(w)))
 
 
+def _batch(op, dst, src, want_counts):
+    dst, src = list(dst), list(src)
+    if len(dst) != len(src):
+        raise ValueError("dst and src must have the same length")
+    for a, b in zip(dst, src):
+        a._check_same(b)
+        a._flush()
+        b._flush()
+    n = len(dst)
+    if n == 0:
+        return np.zeros(0, np.int64) if want_counts else None
+    ha = (C.c_void_p * n)(*[a._h for a in dst])
+    hb = (C.c_void_p * n)(*[b._h for b in src])
+    counts = np.empty(n, np.int64) if want_counts else None
+    check(_lib.lib().bxg_bits_binop_batch(op, ha, hb, n, ptr(counts)))
+    return counts
+
+
+def iand_many(dst, src):
+    """dst[i].iand(src[i]) for every pair in one kernel launch -- the genome-wide loop of
+    scripts/bed_intersect_basewise.py:25-28 (`for chrom in bits1: bits1[chrom].iand(bits2[chrom])`)."""
+    _batch(0, dst, src, False)
+
+
+def ior_many(dst, src):
+    _batch(1, dst, src, False)
+
+
+def and_count_many(dst, src):
+    """iand_many fused with a popcount of every result -> int64 array (covered bases per chromosome)."""
+    return _batch(0, dst, src, True)
+
+
 class BitSet(_DeviceBits):
     """bx.bitset.BitSet (bitset.pyx:107-173) on the device."""
 

@@ -7,6 +7,8 @@
 #include <cub/cub.cuh>
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace bxg;
@@ -126,6 +128,80 @@ k_binop(ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b, int64_t nv
     if (sa != nullptr)
         for (int64_t k = tid; k < nbins; k += stride) sa[k] = state_op<OP>(sa[k], sb[k]);
     if (COUNT) block_accumulate(pc, count);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Genome-wide form: one persistent launch applies a[p] op= b[p] to every pair p (the reference loop
+// `for chrom in bits1: bits1[chrom].iand(bits2[chrom])`, scripts/bed_intersect_basewise.py:25-28).
+// The pairs are cut into 16 KB chunks; each CTA owns one contiguous chunk range (DRAM-page friendly, and a CTA
+// flushes its popcount once per pair it touches).
+// ------------------------------------------------------------------------------------------------------------------
+struct BatchDesc {
+    ulonglong2 *a;
+    const ulonglong2 *b;
+    int64_t nvec;
+    uint8_t *sa;
+    const uint8_t *sb;
+    int64_t chunk0;      // global index of this pair's first chunk
+    int32_t nbins, flat;
+};
+constexpr int BATCH_CHUNK_VEC = 1024;   // 16 KB of a per chunk: 4 x 128-bit per thread
+constexpr int BATCH_MAX_PAIRS = 1024;
+
+template <int OP, bool COUNT>
+__global__ void __launch_bounds__(BINOP_THREADS)
+k_binop_batch(const BatchDesc *__restrict__ descs, int npairs, int64_t nchunks, int64_t chunks_per_cta,
+              unsigned long long *__restrict__ counts) {
+    __shared__ int64_t s_chunk0[BATCH_MAX_PAIRS + 1];
+    for (int p = threadIdx.x; p <= npairs; p += blockDim.x) s_chunk0[p] = p < npairs ? descs[p].chunk0 : nchunks;
+    __syncthreads();
+    int64_t c = (int64_t)blockIdx.x * chunks_per_cta;
+    const int64_t c_end = min(c + chunks_per_cta, nchunks);
+    if (c >= c_end) return;
+    int p = 0;
+    {   // pair of the first chunk: largest p with chunk0[p] <= c
+        int lo = 0, hi = npairs;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (s_chunk0[mid] <= c) lo = mid; else hi = mid;
+        }
+        p = lo;
+    }
+    unsigned long long pc = 0;
+    while (c < c_end) {
+        const BatchDesc d = descs[p];
+        const int64_t pair_end = min(s_chunk0[p + 1], c_end);
+        if (c == d.chunk0 && d.sa != nullptr)       // the CTA that owns a pair's first chunk applies the bin-state algebra
+            for (int k = threadIdx.x; k < d.nbins; k += blockDim.x) d.sa[k] = state_op<OP>(d.sa[k], d.sb[k]);
+        for (; c < pair_end; c++) {
+            const int64_t base = (c - d.chunk0) * BATCH_CHUNK_VEC + threadIdx.x;
+            ulonglong2 va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int64_t i = base + u * BINOP_THREADS;
+                if (i < d.nvec) {
+                    va[u] = ld_rw(d.a + i);
+                    vb[u] = ld_stream(d.b + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int64_t i = base + u * BINOP_THREADS;
+                if (i < d.nvec) {
+                    va[u].x = apply<OP>(va[u].x, vb[u].x);
+                    va[u].y = apply<OP>(va[u].y, vb[u].y);
+                    if (COUNT) pc += __popcll(va[u].x) + __popcll(va[u].y);
+                    st_stream(d.a + i, va[u]);
+                }
+            }
+        }
+        if (COUNT) {
+            block_accumulate(pc, counts + p);       // uniform across the CTA: every thread walks the same chunks
+            pc = 0;
+            __syncthreads();
+        }
+        p++;
+    }
 }
 
 // a = ~a over [0,size); tail bits stay zero; state: Z <-> O (binBits.c:298-317)
@@ -554,6 +630,57 @@ int bxg_bits_and_count(bxg_bits_t *a, const bxg_bits_t *b, int64_t *count) {
     BXG_CUDA(cudaMemsetAsync(c.d_mailbox, 0, 8, c.stream));
     BXG_TRY((binop<OP_AND, true>(a, b, (unsigned long long *)c.d_mailbox)));
     if (count) BXG_TRY(fetch_counter(count));
+    return BXG_OK;
+}
+
+int bxg_bits_binop_batch(int op, bxg_bits_t *const *a, const bxg_bits_t *const *b, int32_t n, int64_t *counts) {
+    BXG_TRY(ensure_init());
+    if (n <= 0) return BXG_OK;
+    if (n > BATCH_MAX_PAIRS) return set_error(BXG_ERR_ARG, "at most %d pairs per batch", BATCH_MAX_PAIRS);
+    if (op < OP_AND || op > OP_XOR) return set_error(BXG_ERR_ARG, "op must be 0 (and), 1 (or) or 2 (xor)");
+    if (counts && op != OP_AND) return set_error(BXG_ERR_ARG, "fused counts are provided for op 0 (and) only");
+    Context &c = ctx();
+    static BatchDesc h_desc[BATCH_MAX_PAIRS];
+    int64_t nchunks = 0;
+    for (int p = 0; p < n; p++) {
+        BXG_TRY(check_pair(a[p], b[p]));
+        if (a[p] == b[p]) return set_error(BXG_ERR_ARG, "pair %d aliases one bitset", p);
+        for (int q = 0; q < p; q++)
+            if (a[q] == a[p]) return set_error(BXG_ERR_ARG, "bitset appears twice as a destination (pairs %d, %d)", q, p);
+        BatchDesc &d = h_desc[p];
+        d.a = (ulonglong2 *)a[p]->words;
+        d.b = (const ulonglong2 *)b[p]->words;
+        d.nvec = a[p]->nwords_alloc / 2;
+        d.sa = a[p]->flat ? nullptr : a[p]->state;
+        d.sb = b[p]->state;
+        d.nbins = a[p]->nbins;
+        d.flat = a[p]->flat;
+        d.chunk0 = nchunks;
+        nchunks += cdiv(d.nvec, BATCH_CHUNK_VEC);
+        invalidate(a[p]);
+    }
+    void *d_desc, *d_cnt;
+    BXG_TRY(scratch(3, sizeof(BatchDesc) * (size_t)n, &d_desc));
+    BXG_TRY(scratch(4, 8 * (size_t)n, &d_cnt));
+    BXG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(BatchDesc) * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+    if (counts) BXG_CUDA(cudaMemsetAsync(d_cnt, 0, 8 * (size_t)n, c.stream));
+    // persistent grid: a whole number of CTAs per SM, each owning one contiguous chunk range
+    int grid = (int)std::min<int64_t>((int64_t)c.sm_count * 8, nchunks);
+    int64_t per_cta = cdiv(nchunks, grid);
+    grid = (int)cdiv(nchunks, per_cta);
+    const BatchDesc *dd = (const BatchDesc *)d_desc;
+    unsigned long long *dc = (unsigned long long *)d_cnt;
+    if (counts) {
+        BXG_LAUNCH((k_binop_batch<OP_AND, true>), grid, BINOP_THREADS, 0, dd, n, nchunks, per_cta, dc);
+        BXG_CUDA(cudaMemcpyAsync(counts, d_cnt, 8 * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+        BXG_CUDA(cudaStreamSynchronize(c.stream));
+    } else if (op == OP_AND) {
+        BXG_LAUNCH((k_binop_batch<OP_AND, false>), grid, BINOP_THREADS, 0, dd, n, nchunks, per_cta, dc);
+    } else if (op == OP_OR) {
+        BXG_LAUNCH((k_binop_batch<OP_OR, false>), grid, BINOP_THREADS, 0, dd, n, nchunks, per_cta, dc);
+    } else {
+        BXG_LAUNCH((k_binop_batch<OP_XOR, false>), grid, BINOP_THREADS, 0, dd, n, nchunks, per_cta, dc);
+    }
     return BXG_OK;
 }
 

@@ -11,6 +11,8 @@
 // and find is: count pass (searches + scan of [lo,hi)), exclusive scan to int64 CSR offsets, fill pass.
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace bxg;
@@ -46,6 +48,13 @@ struct bxg_itree {
     int32_t *d_hits = nullptr;
     int64_t q_cap = 0, hits_cap = 0;
     int64_t nq = -1, total = 0;
+    // pipelined host path (bxg_itree_find_host): copy-in / copy-out streams, per-chunk events, pinned result buffers
+    static constexpr int MAX_CHUNKS = 16;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[MAX_CHUNKS], ev_scan[MAX_CHUNKS], ev_fill[MAX_CHUNKS];
+    int64_t *h_off = nullptr, *h_tot = nullptr;
+    int32_t *h_hits = nullptr;
+    int64_t h_off_cap = 0, h_hits_cap = 0;
     // the staged query arrays of the last find (device pointers valid until the next call)
     IndexView view() const {
         IndexView v;
@@ -332,8 +341,9 @@ static int ensure_query_buffers(bxg_itree *t, int64_t nq) {
     return BXG_OK;
 }
 
+// pass A over queries [q0, q0+nq): searches + per-query hit counts into d_cnt/d_lo/d_hi[q0..]
 static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t nq,
-                        unsigned long long *d_total) {
+                        unsigned long long *d_total, int64_t q0 = 0) {
     size_t smem = find_smem_bytes(t);
     static bool attr_set = false;
     if (!attr_set) {
@@ -341,8 +351,39 @@ static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
         attr_set = true;
     }
     int grid = grid_for(cdiv(nq, FIND_THREADS), 8);
-    BXG_LAUNCH((k_find<false>), grid, FIND_THREADS, smem, t->view(), dqt, dqs, dqe, nq, t->d_cnt, t->d_lo, t->d_hi,
-               (const int64_t *)nullptr, (int32_t *)nullptr, d_total);
+    BXG_LAUNCH((k_find<false>), grid, FIND_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, nq,
+               t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, (const int64_t *)nullptr, (int32_t *)nullptr, d_total);
+    return BXG_OK;
+}
+
+// pass B over queries [q0, q0+nq): writes hits at the (global) CSR offsets d_off[q0..]
+static int launch_fill(bxg_itree *t, const int32_t *dqs, int64_t nq, int64_t q0 = 0) {
+    int grid = grid_for(cdiv(nq, FIND_THREADS), 8);
+    BXG_LAUNCH((k_find<true>), grid, FIND_THREADS, 0, t->view(), (const int32_t *)nullptr, dqs + q0,
+               (const int32_t *)nullptr, nq, t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, (const int64_t *)(t->d_off + q0),
+               t->d_hits, (unsigned long long *)nullptr);
+    return BXG_OK;
+}
+
+// counts of one chunk followed by a single 0, so that an exclusive scan also emits the chunk's end offset
+struct ChunkCount {
+    const int32_t *cnt;
+    int64_t n;
+    __device__ __forceinline__ int64_t operator()(int64_t i) const { return i < n ? (int64_t)cnt[i] : 0ll; }
+};
+
+static int grow_hits(bxg_itree *t, int64_t need, bool preserve) {
+    if (need <= t->hits_cap) return BXG_OK;
+    int64_t cap = need + need / 4 + 1024;
+    int32_t *nbuf = nullptr;
+    BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (t->s_out) BXG_CUDA(cudaStreamSynchronize(t->s_out));
+    BXG_CUDA(cudaMalloc(&nbuf, (size_t)cap * 4));
+    if (preserve && t->d_hits && t->hits_cap)
+        BXG_CUDA(cudaMemcpy(nbuf, t->d_hits, (size_t)t->hits_cap * 4, cudaMemcpyDeviceToDevice));
+    cudaFree(t->d_hits);
+    t->d_hits = nbuf;
+    t->hits_cap = cap;
     return BXG_OK;
 }
 
@@ -360,6 +401,20 @@ int bxg_itree_free(bxg_itree_t *t) {
     cudaStreamSynchronize(ctx().stream);
     free_index(t);
     cudaFree(t->d_cnt); cudaFree(t->d_lo); cudaFree(t->d_hi); cudaFree(t->d_off); cudaFree(t->d_hits);
+    if (t->s_in) {
+        cudaStreamSynchronize(t->s_in);
+        cudaStreamSynchronize(t->s_out);
+        for (int k = 0; k < bxg_itree::MAX_CHUNKS; k++) {
+            cudaEventDestroy(t->ev_in[k]);
+            cudaEventDestroy(t->ev_scan[k]);
+            cudaEventDestroy(t->ev_fill[k]);
+        }
+        cudaStreamDestroy(t->s_in);
+        cudaStreamDestroy(t->s_out);
+        cudaFreeHost(t->h_tot);
+    }
+    if (t->h_off) cudaFreeHost(t->h_off);
+    if (t->h_hits) cudaFreeHost(t->h_hits);
     delete t;
     return BXG_OK;
 }
@@ -547,18 +602,122 @@ int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, cons
     BXG_CUDA(cudaMemcpyAsync(c.mailbox + 5, t->d_off + nq, 8, cudaMemcpyDeviceToHost, c.stream));
     BXG_CUDA(cudaStreamSynchronize(c.stream));
     t->total = c.mailbox[5];
-    if (t->total > t->hits_cap) {
-        cudaFree(t->d_hits);
-        t->d_hits = nullptr;
-        t->hits_cap = t->total + t->total / 8 + 1024;
-        BXG_CUDA(cudaMalloc(&t->d_hits, (size_t)t->hits_cap * 4));
-    }
+    BXG_TRY(grow_hits(t, t->total, false));
     // pass B: fill (reuses lo/hi of pass A)
-    if (t->total > 0) {
-        int grid = grid_for(cdiv(nq, FIND_THREADS), 8);
-        BXG_LAUNCH((k_find<true>), grid, FIND_THREADS, 0, t->view(), dqt, dqs, dqe, nq, t->d_cnt, t->d_lo, t->d_hi,
-                   (const int64_t *)t->d_off, t->d_hits, (unsigned long long *)nullptr);
+    if (t->total > 0) BXG_TRY(launch_fill(t, dqs, nq));
+    if (total) *total = t->total;
+    return BXG_OK;
+}
+
+// Host-array find with the copies overlapped: queries are cut into chunks; chunk c+1 is uploaded (copy-in stream) and
+// counted while chunk c is filled and its hits / offsets travel back (copy-out stream).  The CSR offsets stay global:
+// each chunk's exclusive scan starts from the previous chunk's end offset, read on the device (cub::FutureValue).
+// Results land in pinned host buffers owned by the index, valid until its next find / free.
+int bxg_itree_find_host(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
+                        const int64_t **offsets, const int32_t **hits, int64_t *total) {
+    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
+    if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
+    Context &c = ctx();
+    if (!t->s_in) {
+        BXG_CUDA(cudaStreamCreateWithFlags(&t->s_in, cudaStreamNonBlocking));
+        BXG_CUDA(cudaStreamCreateWithFlags(&t->s_out, cudaStreamNonBlocking));
+        for (int k = 0; k < bxg_itree::MAX_CHUNKS; k++) {
+            BXG_CUDA(cudaEventCreateWithFlags(&t->ev_in[k], cudaEventDisableTiming));
+            BXG_CUDA(cudaEventCreateWithFlags(&t->ev_scan[k], cudaEventDisableTiming));
+            BXG_CUDA(cudaEventCreateWithFlags(&t->ev_fill[k], cudaEventDisableTiming));
+        }
+        BXG_CUDA(cudaMallocHost(&t->h_tot, (bxg_itree::MAX_CHUNKS + 1) * 8));
     }
+    BXG_TRY(ensure_query_buffers(t, nq));
+    if (nq + 1 > t->h_off_cap) {
+        BXG_CUDA(cudaStreamSynchronize(t->s_out));
+        if (t->h_off) BXG_CUDA(cudaFreeHost(t->h_off));
+        t->h_off_cap = nq + 1 + nq / 8;
+        BXG_CUDA(cudaMallocHost(&t->h_off, (size_t)t->h_off_cap * 8));
+    }
+    t->nq = nq;
+    t->total = 0;
+    t->h_off[0] = 0;
+    if (offsets) *offsets = t->h_off;
+    if (hits) *hits = t->h_hits;
+    if (total) *total = 0;
+    if (nq == 0) return BXG_OK;
+
+    const bool has_tree = qtree && t->ntrees > 1;
+    void *p0 = nullptr, *p1, *p2;
+    if (has_tree) BXG_TRY(scratch(0, (size_t)nq * 4, &p0));
+    BXG_TRY(scratch(1, (size_t)nq * 4, &p1));
+    BXG_TRY(scratch(2, (size_t)nq * 4, &p2));
+    int32_t *dqt = (int32_t *)p0, *dqs = (int32_t *)p1, *dqe = (int32_t *)p2;
+    int nchunks = (int)std::min<int64_t>(bxg_itree::MAX_CHUNKS, std::max<int64_t>(1, nq / (1 << 20)));
+    const int64_t per = cdiv(nq, nchunks);
+    nchunks = (int)cdiv(nq, per);
+    size_t tmp_bytes = 0;
+    {
+        cub::CountingInputIterator<int64_t> idx(0);
+        cub::TransformInputIterator<int64_t, ChunkCount, cub::CountingInputIterator<int64_t>> it(idx, ChunkCount{t->d_cnt, per});
+        BXG_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp_bytes, it, t->d_off, cub::Sum(),
+                                                cub::FutureValue<int64_t>(t->d_off), per + 1, c.stream));
+    }
+    void *tmp;
+    BXG_TRY(scratch(7, tmp_bytes, &tmp));
+    BXG_CUDA(cudaMemsetAsync(t->d_off, 0, 8, c.stream));
+
+    auto stage_a = [&](int k) -> int {      // upload + count + scan of chunk k
+        const int64_t q0 = k * per, n = std::min(per, nq - q0);
+        if (has_tree) BXG_CUDA(cudaMemcpyAsync(dqt + q0, qtree + q0, (size_t)n * 4, cudaMemcpyHostToDevice, t->s_in));
+        BXG_CUDA(cudaMemcpyAsync(dqs + q0, qs + q0, (size_t)n * 4, cudaMemcpyHostToDevice, t->s_in));
+        BXG_CUDA(cudaMemcpyAsync(dqe + q0, qe + q0, (size_t)n * 4, cudaMemcpyHostToDevice, t->s_in));
+        BXG_CUDA(cudaEventRecord(t->ev_in[k], t->s_in));
+        BXG_CUDA(cudaStreamWaitEvent(c.stream, t->ev_in[k], 0));
+        BXG_TRY(launch_count(t, has_tree ? dqt : nullptr, dqs, dqe, n, nullptr, q0));
+        cub::CountingInputIterator<int64_t> idx(0);
+        cub::TransformInputIterator<int64_t, ChunkCount, cub::CountingInputIterator<int64_t>> it(idx, ChunkCount{t->d_cnt + q0, n});
+        size_t tb = tmp_bytes;
+        prof_begin("cub::DeviceScan::ExclusiveScan(offsets)");
+        BXG_CUDA(cub::DeviceScan::ExclusiveScan(tmp, tb, it, t->d_off + q0, cub::Sum(),
+                                                cub::FutureValue<int64_t>(t->d_off + q0), n + 1, c.stream));
+        prof_end();
+        c.launches += 2;
+        BXG_CUDA(cudaMemcpyAsync(t->h_tot + k + 1, t->d_off + q0 + n, 8, cudaMemcpyDeviceToHost, c.stream));
+        BXG_CUDA(cudaEventRecord(t->ev_scan[k], c.stream));
+        return BXG_OK;
+    };
+    auto stage_b = [&](int k) -> int {      // fill + download of chunk k
+        const int64_t q0 = k * per, n = std::min(per, nq - q0);
+        BXG_CUDA(cudaEventSynchronize(t->ev_scan[k]));
+        const int64_t base = k ? t->h_tot[k] : 0, end = t->h_tot[k + 1];
+        BXG_TRY(grow_hits(t, end, true));
+        if (end > t->h_hits_cap) {
+            BXG_CUDA(cudaStreamSynchronize(t->s_out));
+            int64_t cap = std::max<int64_t>(end + end / 4, (int64_t)((double)end * nq / (q0 + n) * 1.05)) + 1024;
+            int32_t *nh = nullptr;
+            BXG_CUDA(cudaMallocHost(&nh, (size_t)cap * 4));
+            if (t->h_hits) {
+                if (base) memcpy(nh, t->h_hits, (size_t)base * 4);
+                BXG_CUDA(cudaFreeHost(t->h_hits));
+            }
+            t->h_hits = nh;
+            t->h_hits_cap = cap;
+        }
+        if (end > base) BXG_TRY(launch_fill(t, dqs, n, q0));
+        BXG_CUDA(cudaEventRecord(t->ev_fill[k], c.stream));
+        BXG_CUDA(cudaStreamWaitEvent(t->s_out, t->ev_fill[k], 0));
+        if (end > base)
+            BXG_CUDA(cudaMemcpyAsync(t->h_hits + base, t->d_hits + base, (size_t)(end - base) * 4, cudaMemcpyDeviceToHost, t->s_out));
+        BXG_CUDA(cudaMemcpyAsync(t->h_off + q0 + 1, t->d_off + q0 + 1, (size_t)n * 8, cudaMemcpyDeviceToHost, t->s_out));
+        return BXG_OK;
+    };
+    BXG_TRY(stage_a(0));
+    for (int k = 0; k < nchunks; k++) {
+        if (k + 1 < nchunks) BXG_TRY(stage_a(k + 1));
+        BXG_TRY(stage_b(k));
+    }
+    BXG_CUDA(cudaStreamSynchronize(t->s_out));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    t->total = t->h_tot[nchunks];
+    if (offsets) *offsets = t->h_off;
+    if (hits) *hits = t->h_hits;
     if (total) *total = t->total;
     return BXG_OK;
 }

@@ -80,13 +80,19 @@ class _DeviceIndex:
     def build(self, tree, start, end, ntrees):
         check(_lib.lib().bxg_itree_build(self._h, ptr(tree), ptr(start), ptr(end), len(start), ntrees, _lib.HOST))
 
-    def find(self, qtree, qs, qe):
+    def find(self, qtree, qs, qe, copy=True):
+        """Batched find over host arrays (copies overlapped with the kernels, bxg_itree_find_host).
+        copy=False returns views of the index's pinned result buffers, valid until its next find."""
         L = _lib.lib()
         total = C.c_int64()
-        check(L.bxg_itree_find(self._h, ptr(qtree), ptr(qs), ptr(qe), len(qs), _lib.HOST, C.byref(total)))
-        off = np.empty(len(qs) + 1, np.int64)
-        hits = np.empty(total.value, np.int32)
-        check(L.bxg_itree_fetch(self._h, ptr(off), ptr(hits)))
+        p_off, p_hits = C.c_void_p(), C.c_void_p()
+        check(L.bxg_itree_find_host(self._h, ptr(qtree), ptr(qs), ptr(qe), len(qs), C.byref(p_off), C.byref(p_hits),
+                                    C.byref(total)))
+        nq, n = len(qs), total.value
+        off = np.frombuffer((C.c_int64 * (nq + 1)).from_address(p_off.value), np.int64)
+        hits = (np.frombuffer((C.c_int32 * n).from_address(p_hits.value), np.int32) if n else np.empty(0, np.int32))
+        if copy:
+            return off.copy(), hits.copy()
         return off, hits
 
     def count(self, qtree, qs, qe):
@@ -256,9 +262,10 @@ class IntervalForest:
         self._index.build(t, s, e, self.ntrees)
         return self
 
-    def find_batch(self, tree_ids, starts, ends):
-        """-> CSR (offsets, hits); hits are positions in the arrays passed to build()."""
-        return self._index.find(as_i32(tree_ids), as_i32(starts), as_i32(ends))
+    def find_batch(self, tree_ids, starts, ends, copy=True):
+        """-> CSR (offsets, hits); hits are positions in the arrays passed to build().
+        copy=False returns zero-copy views of pinned buffers that the next find_batch overwrites."""
+        return self._index.find(as_i32(tree_ids), as_i32(starts), as_i32(ends), copy=copy)
 
     def count_batch(self, tree_ids, starts, ends):
         return self._index.count(as_i32(tree_ids), as_i32(starts), as_i32(ends))

@@ -101,6 +101,10 @@ int bxg_bits_xor(bxg_bits_t *a, const bxg_bits_t *b);      /* flat BitSet only i
 int bxg_bits_not(bxg_bits_t *a);
 /* fused a &= b ; *count = popcount(a)   (bed_intersect_basewise.py:25-28 followed by a coverage count) */
 int bxg_bits_and_count(bxg_bits_t *a, const bxg_bits_t *b, int64_t *count);
+/* Genome-wide form of the loop `for chrom in bits1: bits1[chrom].iand(bits2[chrom])` (bed_intersect_basewise.py:25-28):
+ * a[p] op= b[p] for n independent pairs in ONE persistent kernel launch.  op: 0 and, 1 or, 2 xor.
+ * counts (host, n entries, may be NULL; op 0 only) receives popcount(a[p]) of each result. */
+int bxg_bits_binop_batch(int op, bxg_bits_t *const *a, const bxg_bits_t *const *b, int32_t n, int64_t *counts);
 
 /* binBitsCountRange (binBits.c:130-178) / bitCountRange (bits.c:118-141) for n (start,count) pairs -> int32 counts.
  * strict != 0 reproduces the reference's ALL_ONE-sentinel arithmetic; strict == 0 returns the true popcount. */
@@ -153,6 +157,11 @@ int bxg_itree_order(const bxg_itree_t *t, int32_t *perm, int64_t *tree_offsets);
 int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe,
                    int64_t nq, int loc, int64_t *total);
 int bxg_itree_fetch(bxg_itree_t *t, int64_t *offsets /* nq+1 */, int32_t *hits /* total */);   /* to host */
+/* The same find for HOST query arrays with the PCIe copies overlapped with the kernels (queries are processed in
+ * chunks on copy-in / compute / copy-out streams).  *offsets (nq+1 int64) and *hits (*total int32) point into pinned
+ * host buffers owned by the index and stay valid until its next find or bxg_itree_free. */
+int bxg_itree_find_host(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
+                        const int64_t **offsets, const int32_t **hits, int64_t *total);
 int bxg_itree_result_dev(const bxg_itree_t *t, const int64_t **d_offsets, const int32_t **d_hits, int64_t *nq,
                          int64_t *total);
 /* len(find(...)) only (scripts/bed_count_overlapping.py:27-33): int32 counts[nq] written to `counts` (host or device

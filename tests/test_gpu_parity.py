@@ -370,6 +370,44 @@ def test_bitset_random_vs_oracle(bx, orc, seed):
         assert x.count_all() == int(np.unpackbits(y.words().view(np.uint8)).sum())
 
 
+def test_bitset_genome_batch_vs_oracle(bx, orc):
+    """iand_many / ior_many / and_count_many over 24 differently sized bitsets == per-pair reference ops."""
+    rng = np.random.default_rng(600)
+    sizes = [int(x) for x in rng.integers(1, 3_000_000, 24)]
+    sizes[3], sizes[7] = 1, 64 * 2048          # degenerate and exactly chunk-aligned
+    A, B, OA, OB = [], [], [], []
+    for size in sizes:
+        gran = int(rng.choice([1, 10, 1024]))
+        a, b = bx.bitset.BinnedBitSet(size, gran), bx.bitset.BinnedBitSet(size, gran)
+        oa, ob = orc.OracleBinnedBitSet(size, gran), orc.OracleBinnedBitSet(size, gran)
+        for x, ox in ((a, oa), (b, ob)):
+            m = int(rng.integers(0, 60))
+            s = rng.integers(0, size, m); c = rng.integers(0, np.minimum(size - s, max(1, size // 20)) + 1)
+            x.set_ranges(s, c); ox.set_ranges(s, c)
+            if rng.random() < 0.3:
+                x.invert(); ox.invert()
+        A.append(a); B.append(b); OA.append(oa); OB.append(ob)
+    counts = bx.bitset.and_count_many(A, B)
+    for oa, ob in zip(OA, OB):
+        oa.iand(ob)
+    for k, (a, oa) in enumerate(zip(A, OA)):
+        assert np.array_equal(a.to_words(), oa.words()), k
+        assert np.array_equal(a.bin_states(), oa.states()), k
+        assert counts[k] == int(np.unpackbits(oa.words().view(np.uint8)).sum()), k
+    bx.bitset.ior_many(A, B)
+    for oa, ob in zip(OA, OB):
+        oa.ior(ob)
+    for k, (a, oa) in enumerate(zip(A, OA)):
+        assert np.array_equal(a.to_words(), oa.words()) and np.array_equal(a.bin_states(), oa.states()), k
+    bx.bitset.iand_many(B, A)
+    for oa, ob in zip(OA, OB):
+        ob.iand(oa)
+    for k, (b, ob) in enumerate(zip(B, OB)):
+        assert np.array_equal(b.to_words(), ob.words()) and np.array_equal(b.bin_states(), ob.states()), k
+    with pytest.raises(ValueError):
+        bx.bitset.iand_many([A[0]], [A[1]])
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_flat_bitset_vs_oracle(bx, orc, seed):
     rng = np.random.default_rng(500 + seed)
@@ -403,14 +441,15 @@ def test_flat_bitset_vs_oracle(bx, orc, seed):
     assert np.array_equal(c.to_words(), b[0].to_words())
 
 
-def test_bitset_chromosome_scale_properties(bx):
+def test_bitset_chromosome_scale_properties(bx, orc):
     """C3 shape at full size for one chromosome pair: De Morgan, popcount identities, run/coverage consistency."""
     size = 250_000_000
     (sa, ca), (sb, cb), (qs, qc) = synth.c3_case(size, 400_000, 1, nq=100_000)
     a, b = bx.bitset.BinnedBitSet(size), bx.bitset.BinnedBitSet(size)
     a.set_ranges(sa, ca); b.set_ranges(sb, cb)
     na, nb = a.count_all(), b.count_all()
-    assert na == 199484802                       # SURVEY 8(d): probe of the compiled reference with seed 1
+    oa = orc.OracleBinnedBitSet(size); oa.set_ranges(sa, ca)
+    assert na == oa.count_range(0, size)         # full-size bitmap against the CPU restatement
     u = bx.bitset.BinnedBitSet(size); u.ior(a); u.ior(b)
     nand = a.and_count(b)                        # a := a & b
     assert u.count_all() == na + nb - nand       # inclusion-exclusion
