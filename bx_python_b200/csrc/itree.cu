@@ -22,8 +22,12 @@ constexpr int MAX_SPLIT = 4096;        // splitter entries per array (16 KB each
 constexpr int SMEM_TREES = 256;        // toff entries cached in shared memory
 constexpr int FIND_THREADS = 256;
 
+constexpr int MAX_KLEV = 5;            // 16-ary sampled search levels: strides 1, 16, 256, 4096, 65536
+
 struct IndexView {
     const int32_t *S, *E, *I, *PM;
+    const int32_t *KS[MAX_KLEV], *KP[MAX_KLEV];   // KS[j][i] = S[i << 4j], KP likewise for PM; padded with INT32_MAX
+    int32_t nk;                                   // levels in use (K*[0] are S / PM themselves)
     const int32_t *M[MAX_LEVELS];
     const int64_t *toff;
     const int32_t *spS, *spPM;   // contiguous: spS[nsplit_pad] then spPM[nsplit_pad]
@@ -42,6 +46,9 @@ struct bxg_itree {
     int64_t *toff = nullptr;
     int32_t *split = nullptr;
     int nsplit = 0, nsplit_pad = 0, shift = 0;
+    int32_t *KS[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases S
+    int32_t *KP[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases PM
+    int nk = 1;
     // query-side buffers (grow-only)
     int32_t *d_cnt = nullptr, *d_lo = nullptr, *d_hi = nullptr;
     int64_t *d_off = nullptr;
@@ -60,6 +67,8 @@ struct bxg_itree {
         IndexView v;
         v.S = S; v.E = E; v.I = I; v.PM = PM;
         for (int l = 0; l < MAX_LEVELS; l++) v.M[l] = M[l];
+        for (int j = 0; j < MAX_KLEV; j++) { v.KS[j] = KS[j]; v.KP[j] = KP[j]; }
+        v.nk = nk;
         v.toff = toff; v.spS = split; v.spPM = split + nsplit_pad;
         v.n = (uint32_t)n; v.ntrees = ntrees; v.nlev = nlev; v.nsplit = nsplit; v.nsplit_pad = nsplit_pad; v.shift = shift;
         return v;
@@ -136,6 +145,18 @@ __global__ void k_block_max(const int32_t *__restrict__ in, int64_t n, int32_t *
     }
 }
 
+// out[i] = A[i << ss] for i < nout, INT32_MAX padding up to nout_pad (sampled 16-ary search level)
+__global__ void k_sample_level(const int32_t *__restrict__ A, int64_t n, int ss, int32_t *__restrict__ out,
+                               int64_t nout, int64_t nout_pad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nout_pad; i += stride)
+        out[i] = (i < nout && (i << ss) < n) ? A[i << ss] : INT32_MAX;
+}
+__global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
 __global__ void k_sample(const int32_t *__restrict__ S, const int32_t *__restrict__ PM, int64_t n, int shift, int nsplit,
                          int nsplit_pad, int32_t *__restrict__ split) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,9 +205,9 @@ struct SmemIndex {
 };
 
 // first position p in [seg_lo, seg_hi) where !(A[p] < key)  (LESS_EQ: !(A[p] <= key)), else seg_hi.
-// `sp` = every 2^shift-th element of A, resident in shared memory.
+// `sp` = every 2^shift-th element of A, resident in shared memory; K[j] = every 16^j-th element of A in HBM.
 template <bool LESS_EQ>
-__device__ __forceinline__ uint32_t seg_search(const int32_t *__restrict__ A, const int32_t *sp, int shift,
+__device__ __forceinline__ uint32_t seg_search(const int32_t *const *K, int nk, const int32_t *sp, int shift,
                                                uint32_t seg_lo, uint32_t seg_hi, int32_t key) {
     auto before = [&](int32_t v) { return LESS_EQ ? (v <= key) : (v < key); };
     uint32_t lo = seg_lo, hi = seg_hi;
@@ -207,11 +228,39 @@ __device__ __forceinline__ uint32_t seg_search(const int32_t *__restrict__ A, co
             if (a < k1 && h < hi) hi = h;
         }
     }
-    while (lo < hi) {
-        uint32_t m = (lo + hi) >> 1;
-        if (before(__ldg(A + m))) lo = m + 1; else hi = m;
+    // The window [lo,hi) now lies inside one 2^shift-aligned block.  Finish with 16-ary rounds over the sampled
+    // levels K[j] (every 16^j-th element of A, K[0] = A): each round reads ONE aligned 64-byte group (2 sectors) and
+    // narrows the window 16x, instead of 4 dependent 4-byte probes that each pull their own 32-byte sector.
+    for (int j = nk - 1; j >= 0 && lo < hi; j--) {
+        const int ss = 4 * j;
+        const uint32_t m0 = (lo + (1u << ss) - 1) >> ss, m1 = ((hi - 1) >> ss) + 1;   // samples m with lo <= m<<ss < hi
+        if (m0 >= m1) continue;
+        const uint32_t g = m0 & ~15u;
+        if (m1 - g > 16u) {                   // cannot happen for aligned windows; stay correct if it ever does
+            while (lo < hi) {
+                uint32_t m = (lo + hi) >> 1;
+                if (before(__ldg(K[0] + m))) lo = m + 1; else hi = m;
+            }
+            break;
+        }
+        const int4 *p = reinterpret_cast<const int4 *>(K[j] + g);
+        const int4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
+        unsigned mask = (unsigned)before(v0.x) | (unsigned)before(v0.y) << 1 | (unsigned)before(v0.z) << 2 |
+                        (unsigned)before(v0.w) << 3 | (unsigned)before(v1.x) << 4 | (unsigned)before(v1.y) << 5 |
+                        (unsigned)before(v1.z) << 6 | (unsigned)before(v1.w) << 7 | (unsigned)before(v2.x) << 8 |
+                        (unsigned)before(v2.y) << 9 | (unsigned)before(v2.z) << 10 | (unsigned)before(v2.w) << 11 |
+                        (unsigned)before(v3.x) << 12 | (unsigned)before(v3.y) << 13 | (unsigned)before(v3.z) << 14 |
+                        (unsigned)before(v3.w) << 15;
+        const unsigned valid = ((1u << (m1 - g)) - 1u) & ~((1u << (m0 - g)) - 1u);
+        const uint32_t c = (uint32_t)__popc(mask & valid);   // sorted inside the segment: the before-entries are a prefix
+        if (c == 0) {
+            hi = m0 << ss;
+        } else {
+            lo = ((m0 + c - 1) << ss) + 1;
+            if (m0 + c < m1) hi = (m0 + c) << ss;
+        }
     }
-    return lo;
+    return lo < hi ? lo : hi;
 }
 
 // Walk k over [lo,hi) visiting every k with E[k] > qs, in order; aligned all-miss blocks are skipped through the
@@ -282,8 +331,8 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             int32_t c = 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
-                hi = seg_search<false>(ix.S, sm.spS, ix.shift, seg_lo, seg_hi, qe);     // start <  qe
-                lo = seg_search<true>(ix.PM, sm.spPM, ix.shift, seg_lo, seg_hi, qs);    // running max end > qs
+                hi = seg_search<false>(ix.KS, ix.nk, sm.spS, ix.shift, seg_lo, seg_hi, qe);    // start <  qe
+                lo = seg_search<true>(ix.KP, ix.nk, sm.spPM, ix.shift, seg_lo, seg_hi, qs);    // running max end > qs
                 if (lo > hi) lo = hi;
                 for_each_hit(ix, lo, hi, qs, [&](uint32_t) { c++; });
             }
@@ -315,6 +364,9 @@ struct CastI64 {
 static void free_index(bxg_itree *t) {
     cudaFree(t->S); cudaFree(t->E); cudaFree(t->I); cudaFree(t->PM); cudaFree(t->toff); cudaFree(t->split);
     for (int l = 0; l < MAX_LEVELS; l++) { cudaFree(t->M[l]); t->M[l] = nullptr; t->mlen[l] = 0; }
+    for (int j = 1; j < MAX_KLEV; j++) { cudaFree(t->KS[j]); cudaFree(t->KP[j]); }
+    for (int j = 0; j < MAX_KLEV; j++) t->KS[j] = t->KP[j] = nullptr;
+    t->nk = 1;
     t->S = t->E = t->I = t->PM = nullptr;
     t->toff = nullptr;
     t->split = nullptr;
@@ -350,7 +402,10 @@ static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
         BXG_CUDA(cudaFuncSetAttribute(k_find<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set = true;
     }
-    int grid = grid_for(cdiv(nq, FIND_THREADS), 8);
+    // persistent grid: exactly the CTAs that are co-resident (whole waves only), grid-stride over the queries
+    int occ = 0;
+    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<false>, FIND_THREADS, smem));
+    int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
     BXG_LAUNCH((k_find<false>), grid, FIND_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, nq,
                t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, (const int64_t *)nullptr, (int32_t *)nullptr, d_total);
     return BXG_OK;
@@ -358,7 +413,9 @@ static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
 
 // pass B over queries [q0, q0+nq): writes hits at the (global) CSR offsets d_off[q0..]
 static int launch_fill(bxg_itree *t, const int32_t *dqs, int64_t nq, int64_t q0 = 0) {
-    int grid = grid_for(cdiv(nq, FIND_THREADS), 8);
+    int occ = 0;
+    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<true>, FIND_THREADS, 0));
+    int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
     BXG_LAUNCH((k_find<true>), grid, FIND_THREADS, 0, t->view(), (const int32_t *)nullptr, dqs + q0,
                (const int32_t *)nullptr, nq, t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, (const int64_t *)(t->d_off + q0),
                t->d_hits, (unsigned long long *)nullptr);
@@ -497,10 +554,13 @@ int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, c
         c.launches += 1 + 2 * ((bits + 7) / 8);
         order = v0;
     }
-    BUILD_CUDA(cudaMalloc(&t->S, (size_t)n * 4));
+    const int64_t npad = ((n + 15) & ~15ll) + 16;     // S / PM are read in aligned 16-entry groups
+    BUILD_CUDA(cudaMalloc(&t->S, (size_t)npad * 4));
     BUILD_CUDA(cudaMalloc(&t->E, (size_t)n * 4));
     BUILD_CUDA(cudaMalloc(&t->I, (size_t)n * 4));
-    BUILD_CUDA(cudaMalloc(&t->PM, (size_t)n * 4));
+    BUILD_CUDA(cudaMalloc(&t->PM, (size_t)npad * 4));
+    BXG_LAUNCH(k_fill_i32, 1, 64, 0, t->S + n, npad - n, INT32_MAX);
+    BXG_LAUNCH(k_fill_i32, 1, 64, 0, t->PM + n, npad - n, INT32_MAX);
     BUILD_CUDA(cudaMemcpyAsync(t->I, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
     // k0/k1 are free now: reuse as TE / running max
     BXG_LAUNCH(k_gather_items, g, 256, 0, d_tree && ntrees > 1 ? d_tree : nullptr, d_start, d_end, t->I, n, t->S, t->E, k0);
@@ -535,6 +595,19 @@ int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, c
     t->nsplit_pad = (t->nsplit + 3) & ~3;
     BUILD_CUDA(cudaMalloc(&t->split, (size_t)t->nsplit_pad * 8));
     BXG_LAUNCH(k_sample, (t->nsplit_pad + 255) / 256, 256, 0, t->S, t->PM, n, t->shift, t->nsplit, t->nsplit_pad, t->split);
+    // 16-ary sampled levels between the shared-memory splitters (stride 2^shift) and the arrays themselves
+    t->KS[0] = t->S;
+    t->KP[0] = t->PM;
+    t->nk = std::max(1, (t->shift + 3) / 4);
+    for (int j = 1; j < t->nk; j++) {
+        const int ss = 4 * j;
+        const int64_t nout = cdiv(n, 1ll << ss), nout_pad = ((nout + 15) & ~15ll) + 16;
+        BUILD_CUDA(cudaMalloc(&t->KS[j], (size_t)nout_pad * 4));
+        BUILD_CUDA(cudaMalloc(&t->KP[j], (size_t)nout_pad * 4));
+        int gk = grid_for(cdiv(nout_pad, 256), 8);
+        BXG_LAUNCH(k_sample_level, gk, 256, 0, t->S, n, ss, t->KS[j], nout, nout_pad);
+        BXG_LAUNCH(k_sample_level, gk, 256, 0, t->PM, n, ss, t->KP[j], nout, nout_pad);
+    }
 
     BUILD_CUDA(cudaMemcpyAsync(c.mailbox + 4, c.d_mailbox + 4, 8, cudaMemcpyDeviceToHost, c.stream));
     BUILD_CUDA(cudaStreamSynchronize(c.stream));
