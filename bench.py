@@ -152,11 +152,20 @@ def reference_rate(db, qq, sample_frac, workers, repeats=1, chroms=None):
     import multiprocessing as mp
     chroms = list(range(len(db))) if chroms is None else chroms
     nq = {c: max(1, int(len(qq[c][0]) * sample_frac)) for c in chroms}
-    shards = lpt_assign([len(db[c][0]) + nq[c] for c in chroms], min(workers, len(chroms)))
     jobs = []
-    for sh in shards:
-        cs = [chroms[i] for i in sh]
-        jobs.append((cs, [db[c] for c in cs], [(qq[c][0][:nq[c]], qq[c][1][:nq[c]]) for c in cs], repeats))
+    if workers >= 2 * len(chroms):
+        # more cores than chromosomes: several processes per chromosome, each with its own copy of that chromosome's
+        # tree (build not timed) and a slice of its queries -- the way a user would spread the reference over cores
+        parts = workers // len(chroms)
+        for c in chroms:
+            for k in range(parts):
+                sl = slice(k * nq[c] // parts, (k + 1) * nq[c] // parts)
+                jobs.append(([c], [db[c]], [(qq[c][0][:nq[c]][sl], qq[c][1][:nq[c]][sl])], repeats))
+    else:
+        shards = lpt_assign([len(db[c][0]) + nq[c] for c in chroms], min(workers, len(chroms)))
+        for sh in shards:
+            cs = [chroms[i] for i in sh]
+            jobs.append((cs, [db[c] for c in cs], [(qq[c][0][:nq[c]], qq[c][1][:nq[c]]) for c in cs], repeats))
     if len(jobs) == 1:
         res = [_ref_worker(jobs[0])]
     else:
@@ -179,14 +188,15 @@ def run_reference(args):
         return
     db, qq, _ = make_workload(max(1, args.gpus), args.n_db, args.nq)
     cores = os.cpu_count() or 1
-    workers = min(cores, 24)
+    workers = max(1, cores - 2)
     frac = args.ref_sample
     r = reference_rate(db, qq, frac, workers, repeats=args.steps + args.warmup)
     times = r["times"][args.warmup:]
     val = r["queries"] * len(times) / sum(times)
     sample = (f"all 24 chromosomes at full database density ({args.n_db} intervals, built once in {r['build_s']:.1f} s, "
               f"not timed), first {frac:.3%} of each chromosome's queries ({r['queries']} queries, {r['hits']} hits) "
-              f"per step; {r['workers']} processes (one tree per chromosome, LPT)")
+              f"per step; {r['workers']} processes on {cores} host cores (every process holds the full tree of its "
+              f"chromosome and a slice of that chromosome's queries)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
@@ -388,8 +398,11 @@ def run_ours(args):
                             "share": round(v["avg_ms"] * v["launches"] / args.steps / step_ms, 4)} for k, v in kern.items()}
 
     # ---- bitset AND (configs[2]) -----------------------------------------------------------------------------------------
+    extra["pcie"] = bench_pcie()
     if not args.no_bitset:
         extra["bitset"] = bench_bitset(args, peak, peak_src)
+        extra["bed_intersect"] = bench_bed_intersect(peak)
+        extra["aggregate"] = bench_aggregate(peak)
 
     # ---- CPU baseline (bounded sample, single thread = the reference's only native mode) -----------------------------------
     cpu = None
@@ -509,6 +522,140 @@ def bench_bitset(args, peak, peak_src):
     return res
 
 
+def bench_pcie():
+    """Pinned-memory copy rates of this box (the ceiling of the e2e figure)."""
+    from bx_python_b200 import _lib
+    from bx_python_b200._lib import check, ptr
+    L = _lib.lib()
+    n = 64 << 20
+    h = _lib.PinnedArray(n, np.int32)
+    h.array[:] = 1
+    d = _lib.DeviceBuffer(np.zeros(n, np.int32))
+    t = _lib.Timer()
+    out = {}
+    for name, fn in (("h2d", lambda: check(L.bxg_memcpy_h2d(d.ptr, ptr(h.array), n * 4))),
+                     ("d2h", lambda: check(L.bxg_memcpy_d2h(ptr(h.array), d.ptr, n * 4)))):
+        fn()
+        _lib.sync()
+        t.start()
+        for _ in range(4):
+            fn()
+        t.stop()
+        out[name + "_gbs"] = 4 * n * 4 / (t.elapsed_ms() * 1e-3) / 1e9
+    return out
+
+
+def bench_bed_intersect(peak):
+    """configs[3] per-GPU share (scripts/bed_intersect.py): file-2 intervals -> per-chromosome bitsets (set_range),
+    file-1 intervals -> count_range(start, end-start) >= 1 flags.  6.25 M + 6.25 M intervals (50 M / 8 GPUs)."""
+    import ctypes as C
+
+    from bx_python_b200 import _lib
+    from bx_python_b200._lib import check
+    from bx_python_b200.bitset import BinnedBitSet
+    from oracle import oracle as orc
+    L = _lib.lib()
+    n = 6_250_000
+    f2 = synth.genome_intervals(n, 4002)
+    f1 = synth.genome_intervals(n, 4001)
+    bits = [BinnedBitSet(int(sz)) for sz in synth.HG38_LENS]
+    dev = []
+    for c in range(24):
+        s2, e2 = f2[c]
+        s1, e1 = f1[c]
+        dev.append((_lib.DeviceBuffer(s2), _lib.DeviceBuffer((e2 - s2).astype(np.int32)), len(s2),
+                    _lib.DeviceBuffer(s1), _lib.DeviceBuffer((e1 - s1).astype(np.int32)), len(s1),
+                    _lib.DeviceBuffer(np.zeros(len(s1), np.int32))))
+    timer = _lib.Timer()
+
+    def set_pass():
+        for b, (ds, dc, m, *_r) in zip(bits, dev):
+            check(L.bxg_bits_set_ranges(b._h, ds.ptr, dc.ptr, m, _lib.DEVICE))
+
+    def count_pass():
+        for b, (_a, _b, _m, qs, qc, mq, out) in zip(bits, dev):
+            check(L.bxg_bits_count_ranges(b._h, qs.ptr, qc.ptr, mq, out.ptr, 1, _lib.DEVICE))
+    res = {}
+    set_pass()
+    _lib.sync()
+    timer.start()
+    set_pass()
+    timer.stop()
+    ms = timer.elapsed_ms()
+    words_written = sum(int(np.sum((e - 1) // 64 - s // 64 + 1)) for s, e in f2)
+    res["set_ranges"] = {"ms": ms, "ranges_per_s": n / (ms * 1e-3), "algorithmic_bytes": 8 * n + 8 * words_written,
+                         "gbs": (8 * n + 8 * words_written) / (ms * 1e-3) / 1e9}
+    count_pass()       # builds the rank tables
+    _lib.sync()
+    timer.start()
+    count_pass()
+    timer.stop()
+    ms = timer.elapsed_ms()
+    res["count_ranges"] = {"ms": ms, "queries_per_s": n / (ms * 1e-3), "algorithmic_bytes": 12 * n,
+                           "gbs": 12 * n / (ms * 1e-3) / 1e9,
+                           "note": "rank-table lookups (2 table words + 2 bitmap words per query): latency/L2-bound"}
+    for r in res.values():
+        r["frac"] = r["gbs"] / peak
+    # parity of one chromosome against the oracle (strict count_range semantics)
+    c = 21
+    ob = orc.OracleBinnedBitSet(int(synth.HG38_LENS[c]))
+    ob.set_ranges(f2[c][0], f2[c][1] - f2[c][0])
+    got = np.empty(dev[c][5], np.int32)
+    check(L.bxg_memcpy_d2h(got.ctypes.data_as(C.c_void_p), dev[c][6].ptr, got.nbytes))
+    _lib.sync()
+    assert np.array_equal(got, ob.count_ranges(f1[c][0], f1[c][1] - f1[c][0])), "bed_intersect parity"
+    res["overlapping_chr22"] = int((got >= 1).sum())
+    res["parity"] = "chr22 counts bit-identical to oracle"
+    return res
+
+
+def bench_aggregate(peak):
+    """configs[4] per-GPU share (aggregate_scores_in_intervals): 12.5 M float32 positions, 625 k windows (1/8 of C5)."""
+    import ctypes as C
+
+    from bx_python_b200 import _lib
+    from bx_python_b200._lib import check
+    from oracle import oracle as orc
+    L = _lib.lib()
+    tracks = synth.genome_scores(12_500_000, 625_000, 5001)
+    handles = []
+    for origin, v, ws, we in tracks:
+        h = C.c_void_p()
+        check(L.bxg_scores_create(v.ctypes.data_as(C.c_void_p), len(v), origin, _lib.HOST, C.byref(h)))
+        nw = len(ws)
+        outs = [_lib.DeviceBuffer(np.zeros(nw, np.float32)) for _ in range(2)] + [_lib.DeviceBuffer(np.zeros(nw, np.int32))] + \
+               [_lib.DeviceBuffer(np.zeros(nw, np.float32)) for _ in range(2)]
+        handles.append((h, _lib.DeviceBuffer(ws), _lib.DeviceBuffer(we), nw, outs))
+    timer = _lib.Timer()
+
+    def one_pass():
+        for h, dws, dwe, nw, o in handles:
+            check(L.bxg_aggregate(h, None, dws.ptr, dwe.ptr, nw, _lib.DEVICE, o[0].ptr, o[1].ptr, o[2].ptr, o[3].ptr, o[4].ptr))
+    one_pass()
+    _lib.sync()
+    timer.start()
+    for _ in range(5):
+        one_pass()
+    timer.stop()
+    ms = timer.elapsed_ms() / 5
+    bases = sum(int(np.sum(we.astype(np.int64) - ws)) for _, _, ws, we in tracks)
+    nw_all = sum(len(t[2]) for t in tracks)
+    alg = 4 * bases + 28 * nw_all
+    origin, v, ws, we = tracks[20]
+    got = np.empty(len(ws), np.float32)
+    check(L.bxg_memcpy_d2h(got.ctypes.data_as(C.c_void_p), handles[20][4][1].ptr, got.nbytes))
+    _lib.sync()
+    dense = np.full(origin + len(v), np.nan, np.float32)
+    dense[origin:] = v
+    ref = orc.aggregate(dense, ws, we)["avg"]
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), "aggregate parity"
+    for h, *_r in handles:
+        L.bxg_scores_free(h)
+    return {"ms": ms, "windows_per_s": nw_all / (ms * 1e-3), "bases_per_s": bases / (ms * 1e-3),
+            "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
+            "parity": "chr21 float32 averages bit-identical to oracle"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -517,7 +664,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-db", dest="n_db", type=int, default=N_DB)
     ap.add_argument("--nq", type=int, default=NQ_PER_GPU, help="queries per GPU")
-    ap.add_argument("--ref-sample", type=float, default=0.02, help="fraction of each chromosome's queries per reference step")
+    ap.add_argument("--ref-sample", type=float, default=0.1, help="fraction of each chromosome's queries per reference step")
     ap.add_argument("--no-bitset", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

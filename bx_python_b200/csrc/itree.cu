@@ -49,6 +49,7 @@ struct bxg_itree {
     int32_t *KS[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases S
     int32_t *KP[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases PM
     int nk = 1;
+    int32_t *es_end = nullptr, *es_k = nullptr;   // per-tree (end, in-order position) ordering for before(); lazy
     // query-side buffers (grow-only)
     int32_t *d_cnt = nullptr, *d_lo = nullptr, *d_hi = nullptr;
     int64_t *d_off = nullptr;
@@ -367,6 +368,9 @@ static void free_index(bxg_itree *t) {
     for (int j = 1; j < MAX_KLEV; j++) { cudaFree(t->KS[j]); cudaFree(t->KP[j]); }
     for (int j = 0; j < MAX_KLEV; j++) t->KS[j] = t->KP[j] = nullptr;
     t->nk = 1;
+    cudaFree(t->es_end);
+    cudaFree(t->es_k);
+    t->es_end = t->es_k = nullptr;
     t->S = t->E = t->I = t->PM = nullptr;
     t->toff = nullptr;
     t->split = nullptr;
@@ -839,10 +843,171 @@ int bxg_itree_count(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, con
     return BXG_OK;
 }
 
-int bxg_itree_neighbors(bxg_itree_t *t, const int32_t *, const int32_t *, const int32_t *, const int32_t *, int64_t,
-                        int, int, int64_t *) {
-    (void)t;
-    return set_error(BXG_ERR_STATE, "bxg_itree_neighbors: not implemented in this build");
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Neighbour queries: IntervalNode.left / right (intersection.pyx:192-260) = IntervalTree.before / after (:408-426).
+//
+// after(pos, n, md):  p = pos+1; candidates = items with 0 <= start-p < md, collected in in-order; if exactly n they
+//   are returned as collected, else stable-sorted by start and cut to n.  In-order IS start order, so the answer is
+//   always the first min(n, count) items of the contiguous range [lb(S,p), lb(S,p+md)).
+// before(pos, n, md): p = pos-1; candidates = items with 0 <= p-end < md collected in REVERSED in-order; if exactly n
+//   they are returned as collected (descending in-order position k), else stable-sorted by end descending and cut to n.
+//   With a second per-tree ordering by (end, k) (built lazily, one stable radix sort) the candidates are the range
+//   [first end > p-md, first end > p) and "stable sort of the reversed sequence by -end" is exactly that range walked
+//   backwards; the count == n case sorts the n emitted entries by k descending.
+// ------------------------------------------------------------------------------------------------------------------
+struct EndOrder {
+    int32_t *end = nullptr;   // ends sorted per tree
+    int32_t *k = nullptr;     // in-order position of each entry
+};
+
+template <bool GT>   // first j in [lo,hi) with A[j] >= v (GT: A[j] > v); 64-bit compare so p +/- max_dist cannot wrap
+__device__ __forceinline__ uint32_t bound64(const int32_t *__restrict__ A, uint32_t lo, uint32_t hi, int64_t v) {
+    while (lo < hi) {
+        uint32_t m = (lo + hi) >> 1;
+        int64_t a = A[m];
+        if (GT ? (a <= v) : (a < v)) lo = m + 1; else hi = m;
+    }
+    return lo;
 }
 
-}  // extern "C"
+template <bool FILL>
+__global__ void k_neighbors(const __grid_constant__ IndexView ix, const int32_t *__restrict__ ES_end,
+                            const int32_t *__restrict__ ES_k, int dir, const int32_t *__restrict__ qtree,
+                            const int32_t *__restrict__ pos, const int32_t *__restrict__ nmax,
+                            const int32_t *__restrict__ maxd, int64_t nq, int32_t *__restrict__ cnt,
+                            const int64_t *__restrict__ off, int32_t *__restrict__ hits) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+        const int32_t t = qtree ? qtree[q] : 0;
+        int32_t c = 0;
+        if (t >= 0 && t < ix.ntrees) {
+            const uint32_t seg_lo = (uint32_t)ix.toff[t], seg_hi = (uint32_t)ix.toff[t + 1];
+            const int64_t md = maxd[q];
+            const int32_t want = nmax[q] > 0 ? nmax[q] : 0;
+            if (dir == 1) {                                   // after / right
+                const int64_t p = (int64_t)pos[q] + 1;
+                const uint32_t a = bound64<false>(ix.S, seg_lo, seg_hi, p);
+                const uint32_t b = md > 0 ? bound64<false>(ix.S, a, seg_hi, p + md) : a;
+                const uint32_t have = b - a;
+                c = (int32_t)(have < (uint32_t)want ? have : (uint32_t)want);
+                if (FILL) {
+                    int32_t *dst = hits + off[q];
+                    for (int32_t j = 0; j < c; j++) dst[j] = ix.I[a + j];
+                }
+            } else {                                          // before / left
+                const int64_t p = (int64_t)pos[q] - 1;
+                const uint32_t b = bound64<true>(ES_end, seg_lo, seg_hi, p);             // first end > p
+                const uint32_t a = md > 0 ? bound64<true>(ES_end, seg_lo, b, p - md) : b;  // first end > p - md
+                const uint32_t have = b - a;
+                c = (int32_t)(have < (uint32_t)want ? have : (uint32_t)want);
+                if (FILL && c > 0) {
+                    int32_t *dst = hits + off[q];
+                    if (have != (uint32_t)want) {
+                        for (int32_t j = 0; j < c; j++) dst[j] = ix.I[ES_k[b - 1 - j]];    // by end desc, then k desc
+                    } else {
+                        // exactly n candidates: the reference returns them as collected = by in-order position, descending
+                        for (int32_t j = 0; j < c; j++) {                                   // insertion sort on k
+                            int32_t kk = ES_k[a + j];
+                            int32_t i = j;
+                            while (i > 0 && dst[i - 1] < kk) { dst[i] = dst[i - 1]; i--; }
+                            dst[i] = kk;
+                        }
+                        for (int32_t j = 0; j < c; j++) dst[j] = ix.I[dst[j]];
+                    }
+                }
+            }
+        }
+        if (!FILL) cnt[q] = c;
+    }
+}
+
+// (tree, end) keys in in-order sequence; a stable sort then keeps ties in ascending in-order position
+__global__ void k_end_keys(const int32_t *__restrict__ E, const int64_t *__restrict__ toff, int32_t ntrees, int64_t n,
+                           uint64_t *__restrict__ keys, int32_t *__restrict__ vals) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        int lo = 0, hi = ntrees;                 // tree of position k: largest t with toff[t] <= k
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (toff[mid] <= k) lo = mid; else hi = mid;
+        }
+        keys[k] = ((uint64_t)lo << 32) | (uint64_t)((uint32_t)E[k] ^ 0x80000000u);
+        vals[k] = (int32_t)k;
+    }
+}
+__global__ void k_end_unpack(const uint64_t *__restrict__ keys, int64_t n, int32_t *__restrict__ end) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+        end[k] = (int32_t)((uint32_t)keys[k] ^ 0x80000000u);
+}
+
+static int ensure_end_order(bxg_itree *t) {
+    if (t->es_end || t->n == 0) return BXG_OK;
+    Context &c = ctx();
+    const int64_t n = t->n;
+    uint64_t *k0 = nullptr, *k1 = nullptr;
+    int32_t *v0 = nullptr;
+    BXG_CUDA(cudaMalloc(&k0, (size_t)n * 8));
+    BXG_CUDA(cudaMalloc(&k1, (size_t)n * 8));
+    BXG_CUDA(cudaMalloc(&v0, (size_t)n * 4));
+    BXG_CUDA(cudaMalloc(&t->es_end, (size_t)n * 4));
+    BXG_CUDA(cudaMalloc(&t->es_k, (size_t)n * 4));
+    int g = grid_for(cdiv(n, 256), 8);
+    BXG_LAUNCH(k_end_keys, g, 256, 0, t->E, t->toff, t->ntrees, n, k0, v0);
+    size_t tb = 0;
+    void *tmp;
+    BXG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, v0, t->es_k, n, 0, 64, c.stream));
+    BXG_TRY(scratch(7, tb, &tmp));
+    BXG_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k0, k1, v0, t->es_k, n, 0, 64, c.stream));
+    c.launches += 17;
+    BXG_LAUNCH(k_end_unpack, g, 256, 0, k1, n, t->es_end);
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    cudaFree(k0); cudaFree(k1); cudaFree(v0);
+    return BXG_OK;
+}
+
+extern "C" int bxg_itree_neighbors(bxg_itree_t *t, const int32_t *qtree, const int32_t *pos, const int32_t *n,
+                                   const int32_t *max_dist, int64_t nq, int dir, int loc, int64_t *total) {
+    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
+    if (nq < 0 || (dir != 0 && dir != 1)) return set_error(BXG_ERR_ARG, "bad arguments");
+    Context &c = ctx();
+    BXG_TRY(ensure_query_buffers(t, nq));
+    t->nq = nq;
+    t->total = 0;
+    if (nq == 0 || t->n == 0) {
+        BXG_CUDA(cudaMemsetAsync(t->d_off, 0, (size_t)(nq + 1) * 8, c.stream));
+        if (total) *total = 0;
+        return BXG_OK;
+    }
+    if (dir == 0) BXG_TRY(ensure_end_order(t));
+    const void *a = nullptr, *b, *d, *e;
+    if (qtree && t->ntrees > 1) BXG_TRY(stage_in(0, qtree, (size_t)nq * 4, loc, &a));
+    BXG_TRY(stage_in(1, pos, (size_t)nq * 4, loc, &b));
+    BXG_TRY(stage_in(2, n, (size_t)nq * 4, loc, &d));
+    BXG_TRY(stage_in(5, max_dist, (size_t)nq * 4, loc, &e));
+    int grid = grid_for(cdiv(nq, 256), 8);
+    BXG_CUDA(cudaMemsetAsync(t->d_cnt + nq, 0, 4, c.stream));
+    BXG_LAUNCH((k_neighbors<false>), grid, 256, 0, t->view(), t->es_end, t->es_k, dir, (const int32_t *)a,
+               (const int32_t *)b, (const int32_t *)d, (const int32_t *)e, nq, t->d_cnt, (const int64_t *)nullptr,
+               (int32_t *)nullptr);
+    cub::TransformInputIterator<int64_t, CastI64, const int32_t *> it(t->d_cnt, CastI64());
+    size_t tmp_bytes = 0;
+    void *tmp;
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, t->d_off, nq + 1, c.stream));
+    BXG_TRY(scratch(7, tmp_bytes, &tmp));
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, t->d_off, nq + 1, c.stream));
+    c.launches += 2;
+    BXG_CUDA(cudaMemcpyAsync(c.mailbox + 5, t->d_off + nq, 8, cudaMemcpyDeviceToHost, c.stream));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    t->total = c.mailbox[5];
+    BXG_TRY(grow_hits(t, t->total, false));
+    if (t->total > 0)
+        BXG_LAUNCH((k_neighbors<true>), grid, 256, 0, t->view(), t->es_end, t->es_k, dir, (const int32_t *)a,
+                   (const int32_t *)b, (const int32_t *)d, (const int32_t *)e, nq, t->d_cnt, (const int64_t *)t->d_off,
+                   t->d_hits);
+    if (loc == BXG_HOST) BXG_CUDA(cudaStreamSynchronize(c.stream));
+    if (total) *total = t->total;
+    return BXG_OK;
+}

@@ -223,6 +223,91 @@ def test_find_large_properties(bx):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# neighbours: before / after / *_interval / upstream / downstream  (intersection.pyx:192-260, 408-477)
+# ---------------------------------------------------------------------------------------------------------------
+def test_neighbors_golden(bx):
+    for case in json.load(open(os.path.join(G, "neighbors.json"))):
+        s, e, queries = synth.neighbor_case(case["seed"])
+        t = tree_of(bx, s, e)
+        for (pos, k, md), (b, a) in zip(queries, case["results"]):
+            assert t.before(pos, k, md) == b, (case["seed"], pos, k, md)
+            assert t.after(pos, k, md) == a, (case["seed"], pos, k, md)
+
+
+def test_neighbors_reference_unit_tests(bx):
+    Interval, IntervalTree = bx.ix.Interval, bx.ix.IntervalTree
+    # doctests intersection.pyx:363-378
+    it = IntervalTree()
+    for a, b in [(0, 10), (3, 7), (3, 40), (13, 50)]:
+        it.insert_interval(Interval(a, b))
+    assert repr(it.before_interval(Interval(10, 20))) == "[Interval(3, 7)]"
+    assert it.before_interval(Interval(5, 20)) == []
+    assert repr(it.upstream_of_interval(Interval(11, 12))) == "[Interval(0, 10)]"
+    assert repr(it.upstream_of_interval(Interval(11, 12, strand="-"))) == "[Interval(13, 50)]"
+    assert repr(it.upstream_of_interval(Interval(1, 2, strand="-"), num_intervals=3)) == \
+        "[Interval(3, 7), Interval(3, 40), Interval(13, 50)]"
+    # intersection_tests.py:57-101 UpDownStreamTestCase
+    iv = IntervalTree()
+    iv.add_interval(Interval(50, 59))
+    for i in range(0, 110, 10):
+        if i != 50:
+            iv.add_interval(Interval(i, i + 9))
+    assert all(u.end < 59 for u in iv.upstream_of_interval(Interval(59, 60), num_intervals=200))
+    assert all(u.start > 70 for u in iv.upstream_of_interval(Interval(60, 70, strand=-1), num_intervals=200))
+    assert all(u.start > 59 for u in iv.upstream_of_interval(Interval(58, 58, strand=-1), num_intervals=200))
+    assert all(d.start > 60 for d in iv.downstream_of_interval(Interval(59, 60), num_intervals=200))
+    assert all(d.start < 59 for d in iv.downstream_of_interval(Interval(59, 60, strand=-1), num_intervals=200))
+    for i in range(0, 90, 10):
+        r = iv.after(i, max_dist=20, num_intervals=2)
+        assert (r[0].start, r[1].start) == (i + 10, i + 20)
+        r = iv.after_interval(Interval(i, i), max_dist=20, num_intervals=2)
+        assert (r[0].start, r[1].start) == (i + 10, i + 20)
+    # intersection_tests.py:17-54 NeighborTestCase (left == before, right == after)
+    assert str(iv.before(60, 2)) == str([Interval(50, 59), Interval(40, 49)])
+    for i in range(10, 100, 10):
+        assert iv.before(i, 1, 10)[0].end == i - 1
+    assert len(iv.before(60, 200)) == 6
+    for i in range(10, 100, 10):
+        assert iv.after(i + 1, 1)[0].start == i + 10
+    for i in range(0, 100, 10):
+        assert iv.after(i - 1, 1, 10)[0].start == i
+    # empty tree (:188-201)
+    e = IntervalTree()
+    assert e.after(100) == e.before(100) == e.after_interval(100) == e.before_interval(100) == []
+    assert e.upstream_of_interval(100) == e.downstream_of_interval(100) == []
+
+
+def test_neighbors_lotsa(bx):
+    # intersection_tests.py:104-140 LotsaTestCase.test_count / test_max_dist
+    mx = 1000000
+    s = [1] + list(range(0, mx, 10)) + [0] * 600
+    e = [2] + list(range(0, mx, 10)) + [1] * 600
+    t = tree_of(bx, s, e)
+    assert len(t.after(1, 33)) == 33
+    assert len(t.before(1, 33)) == 1
+    assert len(t.after(1, 9999)) == 250
+    assert len(t.after(1, 9999, 99999)) == 9999
+    assert len(t.after(1, 10, 0)) == 0
+    for n, d in enumerate(range(10, 1000, 10)):
+        assert len(t.after(1, 10000, d)) == n + 1
+
+
+def test_neighbors_random_vs_oracle(bx, orc):
+    rng = np.random.default_rng(808)
+    for trial in range(6):
+        n = int(rng.integers(1, 50000))
+        G_ = int(rng.integers(50, 2_000_000))
+        s = rng.integers(0, G_, n).astype(np.int32)
+        e = (s + rng.integers(0, 300, n)).astype(np.int32)
+        t = tree_of(bx, s, e)
+        o = orc.OracleIntervalTree(s, e)
+        for _ in range(60):
+            pos = int(rng.integers(-5, G_ + 300)); k = int(rng.integers(1, 8)); md = int(rng.choice([0, 1, 30, 2500, 10**6]))
+            assert t.before(pos, k, md) == o.before(pos, k, md).tolist()
+            assert t.after(pos, k, md) == o.after(pos, k, md).tolist()
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # bitsets
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cls", ["flat", "binned"])
