@@ -178,6 +178,29 @@ def reference_rate(db, qq, sample_frac, workers, repeats=1, chroms=None):
             "build_s": max(r[0] for r in res), "workers": len(jobs)}
 
 
+def usable_cores():
+    """Cores this process may actually use: affinity mask and cgroup CPU quota, not just os.cpu_count()."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+        except (OSError, ValueError, IndexError):
+            pass
+    return n
+
+
 def run_reference(args):
     rank, world, _ = env_rank()
     if rank != 0:
@@ -187,8 +210,10 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
         return
     db, qq, _ = make_workload(max(1, args.gpus), args.n_db, args.nq)
-    cores = os.cpu_count() or 1
-    workers = max(1, cores - 2)
+    cores = usable_cores()
+    workers = max(1, cores - 1) if cores > 2 else cores
+    if args.ref_workers:
+        workers = args.ref_workers
     frac = args.ref_sample
     r = reference_rate(db, qq, frac, workers, repeats=args.steps + args.warmup)
     times = r["times"][args.warmup:]
@@ -515,6 +540,20 @@ def bench_bitset(args, peak, peak_src):
         res[name] = {"ms_per_pass": ms, "gbs": gbs, "frac": gbs / peak,
                      "launches_per_pass": 24 if fn is one_pass else 1}
     assert int(counts.sum()) == sum(a.count_all() for a in A), "fused genome-wide popcount differs from count_all"
+    # kernel-only durations (CUDA events around each launch) -> the per-launch roofline of the bitset kernels
+    _lib.profile_enable(True)
+    for _ in range(5):
+        batch_pass(False)
+        batch_pass(True)
+        one_pass(False)
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    for kname, (nl, tot) in prof.items():
+        per_launch_bytes = 3 * words * 8 if "batch" in kname else 3 * words * 8 / 24
+        avg_ms = tot / nl
+        res.setdefault("kernels", {})[kname.strip("()")] = {
+            "launches": nl, "avg_ms": avg_ms, "gbs": per_launch_bytes / (avg_ms * 1e-3) / 1e9,
+            "frac": per_launch_bytes / (avg_ms * 1e-3) / 1e9 / peak}
     check(L.bxg_bits_count_all(A[0]._h, C.byref(n)))
     res.update({"bitmaps": 48, "total_bits": int(synth.HG38_LENS.sum()), "algorithmic_bytes_per_pass": 3 * words * 8,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "bound": "hbm",
@@ -665,6 +704,7 @@ def main():
     ap.add_argument("--n-db", dest="n_db", type=int, default=N_DB)
     ap.add_argument("--nq", type=int, default=NQ_PER_GPU, help="queries per GPU")
     ap.add_argument("--ref-sample", type=float, default=0.1, help="fraction of each chromosome's queries per reference step")
+    ap.add_argument("--ref-workers", type=int, default=0, help="processes for --impl reference (0 = usable cores - 1)")
     ap.add_argument("--no-bitset", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

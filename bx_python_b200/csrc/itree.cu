@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "itree_search.cuh"
 
 using namespace bxg;
 
@@ -205,88 +206,14 @@ struct SmemIndex {
     const int64_t *toff;         // shared (ntrees <= SMEM_TREES) or global
 };
 
-// first position p in [seg_lo, seg_hi) where !(A[p] < key)  (LESS_EQ: !(A[p] <= key)), else seg_hi.
-// `sp` = every 2^shift-th element of A, resident in shared memory; K[j] = every 16^j-th element of A in HBM.
-template <bool LESS_EQ>
-__device__ __forceinline__ uint32_t seg_search(const int32_t *const *K, int nk, const int32_t *sp, int shift,
-                                               uint32_t seg_lo, uint32_t seg_hi, int32_t key) {
-    auto before = [&](int32_t v) { return LESS_EQ ? (v <= key) : (v < key); };
-    uint32_t lo = seg_lo, hi = seg_hi;
-    if (lo >= hi) return hi;
-    // splitters whose sampled position lies inside the segment: k in [k0, k1)
-    uint32_t k0 = (seg_lo + (1u << shift) - 1) >> shift, k1 = ((seg_hi - 1) >> shift) + 1;
-    if (k0 < k1) {
-        uint32_t a = k0, b = k1;              // count splitters `before` key
-        while (a < b) {
-            uint32_t m = (a + b) >> 1;
-            if (before(sp[m])) a = m + 1; else b = m;
-        }
-        if (a == k0) {
-            hi = k0 << shift;                 // A[k0<<shift] is not before key
-        } else {
-            lo = ((a - 1) << shift) + 1;      // A[(a-1)<<shift] is before key
-            uint32_t h = a << shift;
-            if (a < k1 && h < hi) hi = h;
-        }
-    }
-    // The window [lo,hi) now lies inside one 2^shift-aligned block.  Finish with 16-ary rounds over the sampled
-    // levels K[j] (every 16^j-th element of A, K[0] = A): each round reads ONE aligned 64-byte group (2 sectors) and
-    // narrows the window 16x, instead of 4 dependent 4-byte probes that each pull their own 32-byte sector.
-    for (int j = nk - 1; j >= 0 && lo < hi; j--) {
-        const int ss = 4 * j;
-        const uint32_t m0 = (lo + (1u << ss) - 1) >> ss, m1 = ((hi - 1) >> ss) + 1;   // samples m with lo <= m<<ss < hi
-        if (m0 >= m1) continue;
-        const uint32_t g = m0 & ~15u;
-        if (m1 - g > 16u) {                   // cannot happen for aligned windows; stay correct if it ever does
-            while (lo < hi) {
-                uint32_t m = (lo + hi) >> 1;
-                if (before(__ldg(K[0] + m))) lo = m + 1; else hi = m;
-            }
-            break;
-        }
-        const int4 *p = reinterpret_cast<const int4 *>(K[j] + g);
-        const int4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
-        unsigned mask = (unsigned)before(v0.x) | (unsigned)before(v0.y) << 1 | (unsigned)before(v0.z) << 2 |
-                        (unsigned)before(v0.w) << 3 | (unsigned)before(v1.x) << 4 | (unsigned)before(v1.y) << 5 |
-                        (unsigned)before(v1.z) << 6 | (unsigned)before(v1.w) << 7 | (unsigned)before(v2.x) << 8 |
-                        (unsigned)before(v2.y) << 9 | (unsigned)before(v2.z) << 10 | (unsigned)before(v2.w) << 11 |
-                        (unsigned)before(v3.x) << 12 | (unsigned)before(v3.y) << 13 | (unsigned)before(v3.z) << 14 |
-                        (unsigned)before(v3.w) << 15;
-        const unsigned valid = ((1u << (m1 - g)) - 1u) & ~((1u << (m0 - g)) - 1u);
-        const uint32_t c = (uint32_t)__popc(mask & valid);   // sorted inside the segment: the before-entries are a prefix
-        if (c == 0) {
-            hi = m0 << ss;
-        } else {
-            lo = ((m0 + c - 1) << ss) + 1;
-            if (m0 + c < m1) hi = (m0 + c) << ss;
-        }
-    }
-    return lo < hi ? lo : hi;
-}
-
-// Walk k over [lo,hi) visiting every k with E[k] > qs, in order; aligned all-miss blocks are skipped through the
-// max hierarchy (M[0] covers 32 items, M[l] covers 32^(l+1)).
-template <typename F>
-__device__ __forceinline__ void for_each_hit(const IndexView &ix, uint32_t lo, uint32_t hi, int32_t qs, F &&emit) {
-    uint32_t k = lo;
-    while (k < hi) {
-        if ((k & 31u) == 0 && k + 32u <= hi && __ldg(ix.M[0] + (k >> 5)) <= qs) {
-            uint32_t idx = k >> 5;
-            int lvl = 0;
-            while (lvl + 1 < ix.nlev && (idx & 31u) == 0) {
-                uint32_t up = idx >> 5;
-                uint64_t span_end = ((uint64_t)up + 1) << (5 * (lvl + 2));
-                if (span_end > hi || __ldg(ix.M[lvl + 1] + up) > qs) break;
-                idx = up;
-                lvl++;
-            }
-            k = (idx + 1u) << (5 * (lvl + 1));
-            continue;
-        }
-        if (__ldg(ix.E + k) > qs) emit(k);
-        k++;
-    }
-}
+// The search (dual_search) and walk (walk_hits) arithmetic lives in itree_search.cuh so that the CPU fuzz harness
+// (tests/search_fuzz.cpp) compiles exactly the code the kernels run.
+struct Ld4 {
+    __device__ __forceinline__ int4 operator()(const int4 *p) const { return __ldg(p); }
+};
+struct Ld1 {
+    __device__ __forceinline__ int32_t operator()(const int32_t *p) const { return __ldg(p); }
+};
 
 __device__ __forceinline__ const SmemIndex stage_index(const IndexView &ix, unsigned char *smem_raw) {
     // layout: [mbarrier 8 B][pad 8 B][spS nsplit_pad x 4][spPM nsplit_pad x 4][toff (ntrees+1) x 8]
@@ -332,10 +259,11 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             int32_t c = 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
-                hi = seg_search<false>(ix.KS, ix.nk, sm.spS, ix.shift, seg_lo, seg_hi, qe);    // start <  qe
-                lo = seg_search<true>(ix.KP, ix.nk, sm.spPM, ix.shift, seg_lo, seg_hi, qs);    // running max end > qs
+                bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(),
+                                 hi, lo);          // hi: start < qe ends here; lo: running max end > qs starts here
                 if (lo > hi) lo = hi;
-                for_each_hit(ix, lo, hi, qs, [&](uint32_t) { c++; });
+                bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                               [&](uint32_t, unsigned mask) { c += __popc(mask); });
             }
             cnt[q] = c;
             lo_[q] = (int32_t)lo;
@@ -344,7 +272,13 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
         } else {
             const uint32_t lo = (uint32_t)lo_[q], hi = (uint32_t)hi_[q];
             int32_t *dst = hits + off[q];
-            for_each_hit(ix, lo, hi, qs, [&](uint32_t k) { *dst++ = __ldg(ix.I + k); });
+            bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t k0, unsigned mask) {
+                while (mask) {
+                    const int b = __ffs((int)mask) - 1;
+                    mask &= mask - 1;
+                    *dst++ = __ldg(ix.I + k0 + b);
+                }
+            });
         }
     }
     if (!FILL && total) {
@@ -560,11 +494,12 @@ int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, c
     }
     const int64_t npad = ((n + 15) & ~15ll) + 16;     // S / PM are read in aligned 16-entry groups
     BUILD_CUDA(cudaMalloc(&t->S, (size_t)npad * 4));
-    BUILD_CUDA(cudaMalloc(&t->E, (size_t)n * 4));
+    BUILD_CUDA(cudaMalloc(&t->E, (size_t)npad * 4));       // walked in aligned 16-item groups; pad never hits
     BUILD_CUDA(cudaMalloc(&t->I, (size_t)n * 4));
     BUILD_CUDA(cudaMalloc(&t->PM, (size_t)npad * 4));
     BXG_LAUNCH(k_fill_i32, 1, 64, 0, t->S + n, npad - n, INT32_MAX);
     BXG_LAUNCH(k_fill_i32, 1, 64, 0, t->PM + n, npad - n, INT32_MAX);
+    BXG_LAUNCH(k_fill_i32, 1, 64, 0, t->E + n, npad - n, INT32_MIN);
     BUILD_CUDA(cudaMemcpyAsync(t->I, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
     // k0/k1 are free now: reuse as TE / running max
     BXG_LAUNCH(k_gather_items, g, 256, 0, d_tree && ntrees > 1 ? d_tree : nullptr, d_start, d_end, t->I, n, t->S, t->E, k0);

@@ -1,0 +1,195 @@
+// itree_search.cuh -- the search / walk logic of the find kernels, written once for device and host.
+//
+// Compiled by nvcc into k_find (csrc/itree.cu) and by g++ into the CPU fuzz harness (tests/search_fuzz.cpp), so the
+// index arithmetic that cannot be watched on a GPU-less box is still exercised against std::lower_bound there.
+//
+//   S-search : hi = first k in the tree segment with S[k]  >= qe      (items with start <  qe are candidates)
+//   PM-search: lo = first k in the tree segment with PM[k] >  qs      (first item whose running max end > qs)
+// Both run in lock-step so their loads overlap: a fixed-trip binary-lifting search over the shared-memory splitters,
+// then 16-ary rounds over the sampled levels (one aligned 64-byte group per round and search).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BXG_HD __host__ __device__ __forceinline__
+#else
+#define BXG_HD inline
+struct int4 {
+    int x, y, z, w;
+};
+#endif
+
+namespace bxs {
+
+struct Win {
+    uint32_t lo, hi;   // answer lies in [lo, hi]; everything below lo is "before", position hi is not (or is seg end)
+};
+
+template <bool LESS_EQ>
+BXG_HD bool before(int32_t v, int32_t key) {
+    return LESS_EQ ? (v <= key) : (v < key);
+}
+
+// number of splitters in [k0,k1) that are before `key`, as k0 + count; fixed trip count for a given (k0,k1)
+template <bool LESS_EQ, typename SP>
+BXG_HD uint32_t lift_step(const SP &sp, uint32_t a, uint32_t step, uint32_t k1, int32_t key) {
+    return (a + step <= k1 && before<LESS_EQ>(sp[a + step - 1], key)) ? a + step : a;
+}
+
+// window after the splitter phase: a = k0 + (#splitters in [k0,k1) before key)
+BXG_HD Win splitter_window(uint32_t a, uint32_t k0, uint32_t k1, int shift, uint32_t seg_lo, uint32_t seg_hi) {
+    Win w{seg_lo, seg_hi};
+    if (k0 < k1) {
+        if (a == k0) {
+            w.hi = k0 << shift;                     // A[k0<<shift] is not before key
+        } else {
+            w.lo = ((a - 1) << shift) + 1;          // A[(a-1)<<shift] is before key
+            uint32_t h = a << shift;
+            if (a < k1 && h < w.hi) w.hi = h;
+        }
+    }
+    return w;
+}
+
+struct Round {
+    uint32_t m0, m1, g;
+    bool active;
+};
+
+// samples m of level stride 2^ss with lo <= m<<ss < hi; they live in one aligned 16-entry group starting at g
+BXG_HD Round round_prepare(const Win &w, int ss) {
+    Round r{0, 0, 0, false};
+    if (w.lo >= w.hi) return r;
+    r.m0 = (w.lo + (1u << ss) - 1) >> ss;
+    r.m1 = ((w.hi - 1) >> ss) + 1;
+    r.g = r.m0 & ~15u;
+    r.active = r.m0 < r.m1 && r.m1 - r.g <= 16u;
+    return r;
+}
+
+template <bool LESS_EQ>
+BXG_HD unsigned group_mask(const int4 &v0, const int4 &v1, const int4 &v2, const int4 &v3, int32_t key) {
+    return (unsigned)before<LESS_EQ>(v0.x, key) | (unsigned)before<LESS_EQ>(v0.y, key) << 1 |
+           (unsigned)before<LESS_EQ>(v0.z, key) << 2 | (unsigned)before<LESS_EQ>(v0.w, key) << 3 |
+           (unsigned)before<LESS_EQ>(v1.x, key) << 4 | (unsigned)before<LESS_EQ>(v1.y, key) << 5 |
+           (unsigned)before<LESS_EQ>(v1.z, key) << 6 | (unsigned)before<LESS_EQ>(v1.w, key) << 7 |
+           (unsigned)before<LESS_EQ>(v2.x, key) << 8 | (unsigned)before<LESS_EQ>(v2.y, key) << 9 |
+           (unsigned)before<LESS_EQ>(v2.z, key) << 10 | (unsigned)before<LESS_EQ>(v2.w, key) << 11 |
+           (unsigned)before<LESS_EQ>(v3.x, key) << 12 | (unsigned)before<LESS_EQ>(v3.y, key) << 13 |
+           (unsigned)before<LESS_EQ>(v3.z, key) << 14 | (unsigned)before<LESS_EQ>(v3.w, key) << 15;
+}
+
+BXG_HD int popc32(unsigned x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+BXG_HD int ffs32(unsigned x) {   // 1-based index of the lowest set bit
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x);
+#else
+    return __builtin_ffs((int)x);
+#endif
+}
+
+// entries are sorted inside the segment, so the before-entries among the valid samples form a prefix
+BXG_HD void round_apply(Win &w, const Round &r, int ss, unsigned mask) {
+    const unsigned valid = ((1u << (r.m1 - r.g)) - 1u) & ~((1u << (r.m0 - r.g)) - 1u);
+    const uint32_t c = (uint32_t)popc32(mask & valid);
+    if (c == 0) {
+        w.hi = r.m0 << ss;
+    } else {
+        w.lo = ((r.m0 + c - 1) << ss) + 1;
+        if (r.m0 + c < r.m1) w.hi = (r.m0 + c) << ss;
+    }
+}
+
+// Plain binary search on level 0: the safety net when a window does not fit one aligned group (cannot happen for
+// the aligned windows the splitter phase produces) and the finisher used by the host-only callers.
+template <bool LESS_EQ, typename LD>
+BXG_HD uint32_t finish_binary(const int32_t *A, Win w, int32_t key, const LD &ld) {
+    while (w.lo < w.hi) {
+        uint32_t m = (w.lo + w.hi) >> 1;
+        if (before<LESS_EQ>(ld(A + m), key)) w.lo = m + 1; else w.hi = m;
+    }
+    return w.lo;
+}
+
+// Both searches of one query, in lock-step.  SP: shared-memory splitter arrays; KS/KP: sampled levels (K*[0] = S / PM,
+// padded to 16-entry groups with INT32_MAX); ld4(ptr) loads one 16-byte group quarter.
+template <typename SP, typename LD4, typename LD>
+BXG_HD void dual_search(const int32_t *const *KS, const int32_t *const *KP, int nk, const SP &spS, const SP &spPM,
+                        int shift, uint32_t seg_lo, uint32_t seg_hi, int32_t qe, int32_t qs, const LD4 &ld4,
+                        const LD &ld, uint32_t &hi_out, uint32_t &lo_out) {
+    if (seg_lo >= seg_hi) {
+        hi_out = lo_out = seg_hi;
+        return;
+    }
+    const uint32_t k0 = (seg_lo + (1u << shift) - 1) >> shift, k1 = ((seg_hi - 1) >> shift) + 1;
+    uint32_t a_s = k0, a_p = k0;
+    if (k0 < k1) {
+        uint32_t step = 1;
+        while (step * 2 <= k1 - k0) step *= 2;
+        for (; step > 0; step >>= 1) {               // same trip count for both searches: the loads interleave
+            a_s = lift_step<false>(spS, a_s, step, k1, qe);
+            a_p = lift_step<true>(spPM, a_p, step, k1, qs);
+        }
+    }
+    Win ws = splitter_window(a_s, k0, k1, shift, seg_lo, seg_hi);
+    Win wp = splitter_window(a_p, k0, k1, shift, seg_lo, seg_hi);
+    for (int j = nk - 1; j >= 0; j--) {
+        const int ss = 4 * j;
+        const Round rs = round_prepare(ws, ss), rp = round_prepare(wp, ss);
+        int4 s0{}, s1{}, s2{}, s3{}, p0{}, p1{}, p2{}, p3{};
+        if (rs.active) {
+            const int4 *p = reinterpret_cast<const int4 *>(KS[j] + rs.g);
+            s0 = ld4(p); s1 = ld4(p + 1); s2 = ld4(p + 2); s3 = ld4(p + 3);
+        }
+        if (rp.active) {
+            const int4 *p = reinterpret_cast<const int4 *>(KP[j] + rp.g);
+            p0 = ld4(p); p1 = ld4(p + 1); p2 = ld4(p + 2); p3 = ld4(p + 3);
+        }
+        if (rs.active) round_apply(ws, rs, ss, group_mask<false>(s0, s1, s2, s3, qe));
+        if (rp.active) round_apply(wp, rp, ss, group_mask<true>(p0, p1, p2, p3, qs));
+    }
+    hi_out = finish_binary<false>(KS[0], ws, qe, ld);   // no-ops when the rounds converged (lo == hi)
+    lo_out = finish_binary<true>(KP[0], wp, qs, ld);
+}
+
+// Walk [lo,hi) in aligned 16-item groups of E (padded with INT32_MIN): f(k0, mask) gets the bit mask of hits
+// (bit i <=> item k0+i has E > qs and lies in [lo,hi)).  After an empty group, 32-aligned all-miss blocks are skipped
+// through the max hierarchy M[l] (M[l][b] = max E over 32^(l+1) items) -- O(32 log n) per hit in the worst case.
+template <typename LD4, typename LD, typename F>
+BXG_HD void walk_hits(const int32_t *E, const int32_t *const *M, int nlev, uint32_t lo, uint32_t hi, int32_t qs,
+                      const LD4 &ld4, const LD &ld, F &&f) {
+    if (lo >= hi) return;
+    uint32_t k = lo & ~15u;
+    bool prev_empty = false;
+    while (k < hi) {
+        if (prev_empty && (k & 31u) == 0 && k + 32u <= hi && ld(M[0] + (k >> 5)) <= qs) {
+            uint32_t idx = k >> 5;
+            int lvl = 0;
+            while (lvl + 1 < nlev && (idx & 31u) == 0) {
+                const uint32_t up = idx >> 5;
+                const uint64_t span_end = ((uint64_t)up + 1) << (5 * (lvl + 2));
+                if (span_end > hi || ld(M[lvl + 1] + up) > qs) break;
+                idx = up;
+                lvl++;
+            }
+            k = (idx + 1u) << (5 * (lvl + 1));
+            continue;
+        }
+        const int4 *p = reinterpret_cast<const int4 *>(E + k);
+        const int4 v0 = ld4(p), v1 = ld4(p + 1), v2 = ld4(p + 2), v3 = ld4(p + 3);
+        unsigned mask = 0xffffu & ~group_mask<true>(v0, v1, v2, v3, qs);      // E > qs
+        if (k < lo) mask &= ~0u << (lo - k);
+        if (k + 16u > hi) mask &= (1u << (hi - k)) - 1u;
+        prev_empty = mask == 0;
+        if (mask) f(k, mask);
+        k += 16;
+    }
+}
+
+}  // namespace bxs

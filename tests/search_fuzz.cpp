@@ -1,0 +1,124 @@
+// search_fuzz.cpp -- CPU fuzz of the find kernels' index arithmetic (bx_python_b200/csrc/itree_search.cuh compiled
+// by g++): dual_search against std::lower_bound / std::upper_bound over multi-tree segments, and walk_hits (with the
+// max-hierarchy skipping) against a naive scan.  Built and run by tests/test_search_logic.py.
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../bx_python_b200/csrc/itree_search.cuh"
+
+static uint32_t rnd_state = 12345;
+static uint32_t rnd() {
+    rnd_state = rnd_state * 1664525u + 1013904223u;
+    return rnd_state >> 8;
+}
+
+int main(int argc, char **argv) {
+    const int trials = argc > 1 ? atoi(argv[1]) : 1500;
+    auto ld4 = [](const int4 *p) { return *p; };
+    auto ld = [](const int32_t *p) { return *p; };
+    long checks = 0;
+    for (int trial = 0; trial < trials; trial++) {
+        const int n = 1 + (int)(rnd() % (trial % 4 == 0 ? 200000 : 3000));
+        const int maxsplit = (trial % 2) ? 4096 : 8;      // a tiny splitter budget exercises the deep levels
+        const int ntrees = 1 + (int)(rnd() % 6);
+        std::vector<uint32_t> toff(ntrees + 1);
+        for (int t = 1; t < ntrees; t++) toff[t] = rnd() % (uint32_t)(n + 1);
+        toff[0] = 0;
+        toff[ntrees] = (uint32_t)n;
+        std::sort(toff.begin(), toff.end());
+        const int range = 1 + (int)(rnd() % 100000);
+        const long npad = ((n + 15) & ~15l) + 16;
+        std::vector<int32_t> S(npad, INT_MAX), PM(npad, INT_MAX), E(npad, INT_MIN);
+        for (int t = 0; t < ntrees; t++) {
+            for (uint32_t i = toff[t]; i < toff[t + 1]; i++) S[i] = (int)(rnd() % (uint32_t)range) - 50;
+            std::sort(S.begin() + toff[t], S.begin() + toff[t + 1]);
+            int pm = INT_MIN;
+            const bool adversarial = trial % 5 == 0;
+            for (uint32_t i = toff[t]; i < toff[t + 1]; i++) {
+                int len = (int)(rnd() % 40) - 2;
+                if (adversarial && i < toff[t] + 2) len = range * 2;     // chromosome-long items in front
+                E[i] = S[i] + len;
+                pm = std::max(pm, E[i]);
+                PM[i] = pm;
+            }
+        }
+        int shift = 0;
+        while ((n + (1ll << shift) - 1) / (1ll << shift) > maxsplit) shift++;
+        const int nsplit = (int)((n + (1ll << shift) - 1) >> shift);
+        std::vector<int32_t> spS(nsplit + 4, INT_MAX), spPM(nsplit + 4, INT_MAX);
+        for (int k = 0; k < nsplit; k++) {
+            spS[k] = S[(size_t)k << shift];
+            spPM[k] = PM[(size_t)k << shift];
+        }
+        const int nk = std::max(1, (shift + 3) / 4);
+        std::vector<std::vector<int32_t>> ls(nk), lp(nk);
+        std::vector<const int32_t *> KS(nk), KP(nk);
+        for (int j = 0; j < nk; j++) {
+            const int ss = 4 * j;
+            const long nout = (n + (1l << ss) - 1) >> ss, pad = ((nout + 15) & ~15l) + 16;
+            ls[j].assign(pad, INT_MAX);
+            lp[j].assign(pad, INT_MAX);
+            for (long i = 0; i < nout; i++) {
+                ls[j][i] = S[i << ss];
+                lp[j][i] = PM[i << ss];
+            }
+            KS[j] = ls[j].data();
+            KP[j] = lp[j].data();
+        }
+        // max hierarchy
+        std::vector<std::vector<int32_t>> M;
+        {
+            const int32_t *src = E.data();
+            long len = n;
+            while (true) {
+                long nout = (len + 31) / 32;
+                std::vector<int32_t> lvl(nout, INT_MIN);
+                for (long b = 0; b < nout; b++)
+                    for (long k = b * 32; k < std::min(len, b * 32 + 32); k++) lvl[b] = std::max(lvl[b], src[k]);
+                M.push_back(lvl);
+                src = M.back().data();
+                len = nout;
+                if (nout <= 1 || M.size() >= 6) break;
+            }
+        }
+        std::vector<const int32_t *> Mp;
+        for (auto &m : M) Mp.push_back(m.data());
+        for (int q = 0; q < 150; q++) {
+            const int t = (int)(rnd() % (uint32_t)ntrees);
+            const int32_t qs = (int)(rnd() % (uint32_t)(range + 40)) - 70;
+            const int32_t qe = qs + (int)(rnd() % 60) - 5;
+            uint32_t hi, lo;
+            bxs::dual_search(KS.data(), KP.data(), nk, spS.data(), spPM.data(), shift, toff[t], toff[t + 1], qe, qs, ld4,
+                             ld, hi, lo);
+            const uint32_t ehi = (uint32_t)(std::lower_bound(S.begin() + toff[t], S.begin() + toff[t + 1], qe) - S.begin());
+            const uint32_t elo = (uint32_t)(std::upper_bound(PM.begin() + toff[t], PM.begin() + toff[t + 1], qs) - PM.begin());
+            if (hi != ehi || lo != elo) {
+                printf("SEARCH MISMATCH trial %d n=%d shift=%d nk=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u\n", trial, n,
+                       shift, nk, toff[t], toff[t + 1], qs, qe, hi, ehi, lo, elo);
+                return 1;
+            }
+            if (lo > hi) lo = hi;
+            std::vector<uint32_t> got, want;
+            bxs::walk_hits(E.data(), Mp.data(), (int)Mp.size(), lo, hi, qs, ld4, ld, [&](uint32_t k0, unsigned mask) {
+                while (mask) {
+                    int b = bxs::ffs32(mask) - 1;
+                    mask &= mask - 1;
+                    got.push_back(k0 + b);
+                }
+            });
+            for (uint32_t k = lo; k < hi; k++)
+                if (E[k] > qs) want.push_back(k);
+            if (got != want) {
+                printf("WALK MISMATCH trial %d n=%d lo=%u hi=%u qs=%d got=%zu want=%zu\n", trial, n, lo, hi, qs, got.size(),
+                       want.size());
+                return 1;
+            }
+            checks++;
+        }
+    }
+    printf("ok %ld\n", checks);
+    return 0;
+}
