@@ -313,6 +313,18 @@ def run_ours(args):
     q_all = int(comm.allreduce_sum_i64(np.array([nq]))[0])
     value = q_all * args.steps / (ms_max * 1e-3)
 
+    # ---- A/B: the three-pass implementation (count kernel, CUB scan, fill kernel) on the same inputs ------------------
+    check(L.bxg_set_find_mode(0))
+    for _ in range(2):
+        step_dev()
+    timer.start()
+    for _ in range(args.steps):
+        step_dev()
+    timer.stop()
+    three_pass_ms = timer.elapsed_ms() / args.steps
+    check(L.bxg_set_find_mode(1))
+    step_dev()
+
     # ---- per-kernel CUDA-event times for the roofline (separate pass so event overhead is not in `value`) --------------
     _lib.profile_enable(True)
     for _ in range(args.steps):
@@ -380,7 +392,7 @@ def run_ours(args):
 
     extra = {"build_ms": min(build_ms), "hits_per_step": hits_all, "hits_per_query": hits_all / q_all,
              "per_chrom_hits_checksum": int((per_chrom * np.arange(1, 25)).sum()), "parity_spot_check": parity,
-             "e2e_serial_copies": e2e_serial}
+             "e2e_serial_copies": e2e_serial, "three_pass_ms_per_step": three_pass_ms}
 
     if rank != 0:
         comm.close()
@@ -401,6 +413,9 @@ def run_ours(args):
         "k_find<false>": 24 * nq + 12 * n_items,
         # fill pass: read start,lo,hi,offset 20 B/query, read E once 4 B/item, read I + write hit 8 B/hit
         "k_find<true>": 20 * nq + 4 * n_items + 8 * hits_total,
+        # single-pass kernel: read (chrom,start,end) 12 B/query, write offset 8 B/query, S,PM,E once 12 B/item,
+        # read I + write hit 8 B/hit
+        "k_find_fused": 20 * nq + 12 * n_items + 8 * hits_total,
     }
     kern = {}
     for name, (n_l, tot_ms) in prof.items():

@@ -72,6 +72,7 @@ SIGNATURES = {
     "bxg_itree_order": [vp, vp, vp],
     "bxg_itree_find": [vp, vp, vp, vp, i64, cint, pi64],
     "bxg_itree_fetch": [vp, vp, vp],
+    "bxg_set_find_mode": [cint],
     "bxg_itree_find_host": [vp, vp, vp, vp, i64, pvp, pvp, pi64],
     "bxg_itree_result_dev": [vp, pvp, pvp, pi64, pi64],
     "bxg_itree_count": [vp, vp, vp, vp, i64, cint, vp, pi64],

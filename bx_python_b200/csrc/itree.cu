@@ -11,6 +11,8 @@
 // and find is: count pass (searches + scan of [lo,hi)), exclusive scan to int64 CSR offsets, fill pass.
 #include <cub/cub.cuh>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -64,6 +66,12 @@ struct bxg_itree {
     int64_t *h_off = nullptr, *h_tot = nullptr;
     int32_t *h_hits = nullptr;
     int64_t h_off_cap = 0, h_hits_cap = 0;
+    // single-pass find: tile-state words, per-chunk tickets and {end offset, overflow} results
+    unsigned long long *d_tiles = nullptr;
+    int64_t tiles_cap = 0;
+    unsigned int *d_ticket = nullptr;       // MAX_CHUNKS + 1
+    long long *d_result = nullptr;          // 2 x (MAX_CHUNKS + 1)
+    long long *h_result = nullptr;          // pinned mirror
     // the staged query arrays of the last find (device pointers valid until the next call)
     IndexView view() const {
         IndexView v;
@@ -294,6 +302,119 @@ struct CastI64 {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+// Single-pass find: count, CSR offsets and fill in ONE launch.
+//
+// Tiles of 256 queries are handed out in order by an atomic ticket to a persistent grid.  A tile counts its hits,
+// block-scans them, publishes its total in a 64-bit tile-state word (2-bit flag + 62-bit value), obtains its global
+// base with a warp-parallel decoupled look-back over its predecessors' words (as in single-pass prefix scans), writes
+// offsets[q] and immediately re-walks its queries to emit the hits while their E / I lines are still in L1.
+// Compared with count + cub scan + fill this drops two launches, the cnt/lo/hi round trip (24 B/query written and read)
+// and the second DRAM fetch of every candidate window.  Hit order inside a query is the walk order, so the lists are
+// the same ordered lists; no atomics touch the output.
+// If the hit buffer is too small the kernel still finishes the scan (offsets and total are exact), raises result[1]
+// and the host re-runs it with a larger buffer.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int FUSED_THREADS = 256;
+constexpr unsigned long long TS_PARTIAL = 1ull << 62, TS_INCLUSIVE = 2ull << 62, TS_VALUE = (1ull << 62) - 1ull;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS)
+k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, const int32_t *__restrict__ qs_,
+             const int32_t *__restrict__ qe_, int64_t nq, int64_t *__restrict__ off, int32_t *__restrict__ hits,
+             int64_t hits_cap, const int64_t *__restrict__ base_ptr, unsigned long long *__restrict__ tile_state,
+             unsigned int *__restrict__ ticket, long long *__restrict__ result) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef cub::BlockScan<long long, FUSED_THREADS> BS;
+    __shared__ typename BS::TempStorage scan_tmp;
+    __shared__ unsigned int s_tile;
+    __shared__ long long s_base;
+    const SmemIndex sm = stage_index(ix, smem_raw);
+    const unsigned int ntiles = (unsigned int)((nq + FUSED_THREADS - 1) / FUSED_THREADS);
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const unsigned int tile = s_tile;
+        if (tile >= ntiles) break;
+        const int64_t q = (int64_t)tile * FUSED_THREADS + threadIdx.x;
+        uint32_t lo = 0, hi = 0;
+        int32_t qs = 0;
+        long long c = 0;
+        if (q < nq) {
+            qs = __ldg(qs_ + q);
+            const int32_t qe = __ldg(qe_ + q);
+            const int32_t t = qtree ? __ldg(qtree + q) : 0;
+            if (t >= 0 && t < ix.ntrees) {
+                const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
+                bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo);
+                if (lo > hi) lo = hi;
+                int32_t cc = 0;
+                bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t, unsigned mask) { cc += __popc(mask); });
+                c = cc;
+            }
+        }
+        long long excl, tile_total;
+        BS(scan_tmp).ExclusiveSum(c, excl, tile_total);
+        if (threadIdx.x < 32) {
+            if (lane == 0) atomicExch(tile_state + tile, TS_PARTIAL | (unsigned long long)tile_total);
+            // decoupled look-back: 32 predecessors per step; tile -1 is a virtual INCLUSIVE holding the chunk base
+            unsigned long long base = 0;
+            long long p0 = (long long)tile - 1;
+            while (true) {
+                const long long p = p0 - lane;
+                unsigned long long s;
+                if (p >= 0) {
+                    do { s = ld_volatile_u64(tile_state + p); } while ((s >> 62) == 0);
+                } else {
+                    s = TS_INCLUSIVE | (p == -1 ? (unsigned long long)*base_ptr : 0ull);
+                }
+                const unsigned incl = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+                const int first = __ffs((int)incl) - 1;
+                unsigned long long v = (first < 0 || lane <= first) ? (s & TS_VALUE) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                base += v;
+                if (incl) break;
+                p0 -= 32;
+            }
+            if (lane == 0) {
+                atomicExch(tile_state + tile, TS_INCLUSIVE | (base + (unsigned long long)tile_total));
+                s_base = (long long)base;
+            }
+        }
+        __syncthreads();
+        const long long base = s_base;
+        const bool fits = base + tile_total <= hits_cap;
+        if (q < nq) {
+            off[q] = base + excl;
+            if (fits && c > 0) {
+                int32_t *dst = hits + base + excl;
+                bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t k0, unsigned mask) {
+                    while (mask) {
+                        const int b = __ffs((int)mask) - 1;
+                        mask &= mask - 1;
+                        *dst++ = __ldg(ix.I + k0 + b);
+                    }
+                });
+            }
+        }
+        if (threadIdx.x == 0) {
+            if (!fits) result[1] = 1;
+            if (tile == ntiles - 1) {
+                off[nq] = base + tile_total;
+                result[0] = base + tile_total;
+            }
+        }
+        __syncthreads();      // s_tile / s_base / scan_tmp are reused by the next tile
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 static void free_index(bxg_itree *t) {
@@ -410,6 +531,10 @@ int bxg_itree_free(bxg_itree_t *t) {
     }
     if (t->h_off) cudaFreeHost(t->h_off);
     if (t->h_hits) cudaFreeHost(t->h_hits);
+    cudaFree(t->d_tiles);
+    cudaFree(t->d_ticket);
+    cudaFree(t->d_result);
+    if (t->h_result) cudaFreeHost(t->h_result);
     delete t;
     return BXG_OK;
 }
@@ -583,10 +708,8 @@ static int stage_queries(bxg_itree *t, const int32_t *qtree, const int32_t *qs, 
     return BXG_OK;
 }
 
-int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq, int loc,
-                   int64_t *total) {
-    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
-    if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
+static int find_three_pass(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq, int loc,
+                           int64_t *total) {
     Context &c = ctx();
     BXG_TRY(ensure_query_buffers(t, nq));
     t->nq = nq;
@@ -625,12 +748,13 @@ int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, cons
 // counted while chunk c is filled and its hits / offsets travel back (copy-out stream).  The CSR offsets stay global:
 // each chunk's exclusive scan starts from the previous chunk's end offset, read on the device (cub::FutureValue).
 // Results land in pinned host buffers owned by the index, valid until its next find / free.
-int bxg_itree_find_host(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
-                        const int64_t **offsets, const int32_t **hits, int64_t *total) {
-    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
-    if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
+static int ensure_pipeline(bxg_itree *t);
+
+static int find_host_three_pass(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
+                                const int64_t **offsets, const int32_t **hits, int64_t *total) {
     Context &c = ctx();
-    if (!t->s_in) {
+    BXG_TRY(ensure_pipeline(t));
+    if (false) {
         BXG_CUDA(cudaStreamCreateWithFlags(&t->s_in, cudaStreamNonBlocking));
         BXG_CUDA(cudaStreamCreateWithFlags(&t->s_out, cudaStreamNonBlocking));
         for (int k = 0; k < bxg_itree::MAX_CHUNKS; k++) {
@@ -732,6 +856,219 @@ int bxg_itree_find_host(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs,
     if (hits) *hits = t->h_hits;
     if (total) *total = t->total;
     return BXG_OK;
+}
+
+static int ensure_pipeline(bxg_itree *t) {
+    if (t->s_in) return BXG_OK;
+    BXG_CUDA(cudaStreamCreateWithFlags(&t->s_in, cudaStreamNonBlocking));
+    BXG_CUDA(cudaStreamCreateWithFlags(&t->s_out, cudaStreamNonBlocking));
+    for (int k = 0; k < bxg_itree::MAX_CHUNKS; k++) {
+        BXG_CUDA(cudaEventCreateWithFlags(&t->ev_in[k], cudaEventDisableTiming));
+        BXG_CUDA(cudaEventCreateWithFlags(&t->ev_scan[k], cudaEventDisableTiming));
+        BXG_CUDA(cudaEventCreateWithFlags(&t->ev_fill[k], cudaEventDisableTiming));
+    }
+    BXG_CUDA(cudaMallocHost(&t->h_tot, (bxg_itree::MAX_CHUNKS + 1) * 8));
+    return BXG_OK;
+}
+
+// ---- single-pass path --------------------------------------------------------------------------------------------
+static int ensure_fused_state(bxg_itree *t, int64_t nq) {
+    const int64_t need = cdiv(nq, FUSED_THREADS) + bxg_itree::MAX_CHUNKS + 1;
+    if (!t->d_ticket) {
+        BXG_CUDA(cudaMalloc(&t->d_ticket, (bxg_itree::MAX_CHUNKS + 1) * sizeof(unsigned int)));
+        BXG_CUDA(cudaMalloc(&t->d_result, 2 * (bxg_itree::MAX_CHUNKS + 1) * sizeof(long long)));
+        BXG_CUDA(cudaMallocHost(&t->h_result, 2 * (bxg_itree::MAX_CHUNKS + 1) * sizeof(long long)));
+    }
+    if (need > t->tiles_cap) {
+        BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+        cudaFree(t->d_tiles);
+        t->d_tiles = nullptr;
+        t->tiles_cap = need + need / 4;
+        BXG_CUDA(cudaMalloc(&t->d_tiles, (size_t)t->tiles_cap * 8));
+    }
+    return BXG_OK;
+}
+
+// one fused launch over queries [q0, q0+n); slot selects the ticket / result pair, tile0 the tile-state region;
+// the chunk's base offset is read on the device from d_off[q0]
+static int launch_fused(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t n, int64_t q0,
+                        int slot, int64_t tile0) {
+    Context &c = ctx();
+    const int64_t ntiles = cdiv(n, FUSED_THREADS);
+    BXG_CUDA(cudaMemsetAsync(t->d_tiles + tile0, 0, (size_t)ntiles * 8, c.stream));
+    BXG_CUDA(cudaMemsetAsync(t->d_ticket + slot, 0, sizeof(unsigned int), c.stream));
+    BXG_CUDA(cudaMemsetAsync(t->d_result + 2 * slot, 0, 2 * sizeof(long long), c.stream));
+    size_t smem = find_smem_bytes(t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        BXG_CUDA(cudaFuncSetAttribute(k_find_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
+    int occ = 0;
+    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_fused, FUSED_THREADS, smem));
+    int grid = grid_for(ntiles, occ > 0 ? occ : 1);     // every CTA is resident: the look-back cannot starve
+    BXG_LAUNCH(k_find_fused, grid, FUSED_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, n,
+               t->d_off + q0, t->d_hits, t->hits_cap, (const int64_t *)(t->d_off + q0), t->d_tiles + tile0,
+               t->d_ticket + slot, t->d_result + 2 * slot);
+    return BXG_OK;
+}
+
+static int find_fused(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq, int loc,
+                      int64_t *total) {
+    Context &c = ctx();
+    BXG_TRY(ensure_query_buffers(t, nq));
+    BXG_TRY(ensure_fused_state(t, nq));
+    t->nq = nq;
+    t->total = 0;
+    BXG_CUDA(cudaMemsetAsync(t->d_off, 0, 8, c.stream));
+    if (nq == 0) {
+        if (total) *total = 0;
+        return BXG_OK;
+    }
+    const int32_t *dqt, *dqs, *dqe;
+    BXG_TRY(stage_queries(t, qtree, qs, qe, nq, loc, &dqt, &dqs, &dqe));
+    if (t->hits_cap == 0) BXG_TRY(grow_hits(t, 8 * nq + 1024, false));      // first guess; exact after one overflow
+    for (int attempt = 0; attempt < 2; attempt++) {
+        BXG_TRY(launch_fused(t, dqt, dqs, dqe, nq, 0, 0, 0));
+        BXG_CUDA(cudaMemcpyAsync(t->h_result, t->d_result, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+        BXG_CUDA(cudaStreamSynchronize(c.stream));
+        t->total = t->h_result[0];
+        if (!t->h_result[1]) break;
+        if (attempt == 1) return set_error(BXG_ERR_STATE, "hit buffer overflow persisted after regrowth");
+        BXG_TRY(grow_hits(t, t->total, false));                                // too small: offsets/total are exact, redo
+        BXG_CUDA(cudaMemsetAsync(t->d_off, 0, 8, c.stream));
+    }
+    if (total) *total = t->total;
+    return BXG_OK;
+}
+
+static int grow_host_hits(bxg_itree *t, int64_t end, int64_t keep, double progress) {
+    if (end <= t->h_hits_cap) return BXG_OK;
+    BXG_CUDA(cudaStreamSynchronize(t->s_out));
+    int64_t cap = std::max<int64_t>(end + end / 4, (int64_t)((double)end / progress * 1.05)) + 1024;
+    int32_t *nh = nullptr;
+    BXG_CUDA(cudaMallocHost(&nh, (size_t)cap * 4));
+    if (t->h_hits) {
+        if (keep) memcpy(nh, t->h_hits, (size_t)keep * 4);
+        BXG_CUDA(cudaFreeHost(t->h_hits));
+    }
+    t->h_hits = nh;
+    t->h_hits_cap = cap;
+    return BXG_OK;
+}
+
+// Host arrays, copies overlapped with the fused kernel: chunk k+1 is uploaded and searched while chunk k's hits and
+// offsets travel back.  Each chunk's kernel reads its base offset from d_off[q0], written by the previous chunk.
+static int find_host_fused(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
+                           const int64_t **offsets, const int32_t **hits, int64_t *total) {
+    Context &c = ctx();
+    BXG_TRY(ensure_pipeline(t));
+    BXG_TRY(ensure_query_buffers(t, nq));
+    BXG_TRY(ensure_fused_state(t, nq));
+    if (nq + 1 > t->h_off_cap) {
+        BXG_CUDA(cudaStreamSynchronize(t->s_out));
+        if (t->h_off) BXG_CUDA(cudaFreeHost(t->h_off));
+        t->h_off_cap = nq + 1 + nq / 8;
+        BXG_CUDA(cudaMallocHost(&t->h_off, (size_t)t->h_off_cap * 8));
+    }
+    t->nq = nq;
+    t->total = 0;
+    t->h_off[0] = 0;
+    if (offsets) *offsets = t->h_off;
+    if (hits) *hits = t->h_hits;
+    if (total) *total = 0;
+    if (nq == 0) return BXG_OK;
+    const bool has_tree = qtree && t->ntrees > 1;
+    void *p0 = nullptr, *p1, *p2;
+    if (has_tree) BXG_TRY(scratch(0, (size_t)nq * 4, &p0));
+    BXG_TRY(scratch(1, (size_t)nq * 4, &p1));
+    BXG_TRY(scratch(2, (size_t)nq * 4, &p2));
+    int32_t *dqt = (int32_t *)p0, *dqs = (int32_t *)p1, *dqe = (int32_t *)p2;
+    int nchunks = (int)std::min<int64_t>(bxg_itree::MAX_CHUNKS, std::max<int64_t>(1, nq / (1 << 20)));
+    const int64_t per = cdiv(cdiv(nq, nchunks), FUSED_THREADS) * FUSED_THREADS;     // whole tiles per chunk
+    nchunks = (int)cdiv(nq, per);
+    const int64_t tiles_per = per / FUSED_THREADS;
+    if (t->hits_cap == 0) BXG_TRY(grow_hits(t, 8 * nq + 1024, false));
+    BXG_CUDA(cudaMemsetAsync(t->d_off, 0, 8, c.stream));
+
+    auto launch_chunk = [&](int k) -> int {
+        const int64_t q0 = k * per, n = std::min(per, nq - q0);
+        BXG_TRY(launch_fused(t, has_tree ? dqt : nullptr, dqs, dqe, n, q0, k, k * tiles_per));
+        BXG_CUDA(cudaMemcpyAsync(t->h_result + 2 * k, t->d_result + 2 * k, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+        BXG_CUDA(cudaEventRecord(t->ev_scan[k], c.stream));
+        return BXG_OK;
+    };
+    auto stage_a = [&](int k) -> int {      // upload + fused find of chunk k
+        const int64_t q0 = k * per, n = std::min(per, nq - q0);
+        if (has_tree) BXG_CUDA(cudaMemcpyAsync(dqt + q0, qtree + q0, (size_t)n * 4, cudaMemcpyHostToDevice, t->s_in));
+        BXG_CUDA(cudaMemcpyAsync(dqs + q0, qs + q0, (size_t)n * 4, cudaMemcpyHostToDevice, t->s_in));
+        BXG_CUDA(cudaMemcpyAsync(dqe + q0, qe + q0, (size_t)n * 4, cudaMemcpyHostToDevice, t->s_in));
+        BXG_CUDA(cudaEventRecord(t->ev_in[k], t->s_in));
+        BXG_CUDA(cudaStreamWaitEvent(c.stream, t->ev_in[k], 0));
+        return launch_chunk(k);
+    };
+    int64_t base = 0;
+    auto stage_b = [&](int k) -> int {      // download of chunk k (re-running it first if the hit buffer was too small)
+        const int64_t q0 = k * per, n = std::min(per, nq - q0);
+        BXG_CUDA(cudaEventSynchronize(t->ev_scan[k]));
+        int64_t end = t->h_result[2 * k];
+        if (t->h_result[2 * k + 1]) {
+            BXG_TRY(grow_hits(t, std::max<int64_t>(end, (int64_t)((double)end * nq / (q0 + n) * 1.05)), true));
+            BXG_TRY(launch_chunk(k));        // same base (d_off[q0] is intact), now with room
+            BXG_CUDA(cudaEventSynchronize(t->ev_scan[k]));
+            end = t->h_result[2 * k];
+            if (t->h_result[2 * k + 1]) return set_error(BXG_ERR_STATE, "hit buffer overflow persisted after regrowth");
+        }
+        BXG_TRY(grow_host_hits(t, end, base, (double)(q0 + n) / nq));
+        BXG_CUDA(cudaStreamWaitEvent(t->s_out, t->ev_scan[k], 0));
+        if (end > base)
+            BXG_CUDA(cudaMemcpyAsync(t->h_hits + base, t->d_hits + base, (size_t)(end - base) * 4, cudaMemcpyDeviceToHost, t->s_out));
+        BXG_CUDA(cudaMemcpyAsync(t->h_off + q0 + 1, t->d_off + q0 + 1, (size_t)n * 8, cudaMemcpyDeviceToHost, t->s_out));
+        base = end;
+        return BXG_OK;
+    };
+    BXG_TRY(stage_a(0));
+    for (int k = 0; k < nchunks; k++) {
+        if (k + 1 < nchunks) BXG_TRY(stage_a(k + 1));
+        BXG_TRY(stage_b(k));
+    }
+    BXG_CUDA(cudaStreamSynchronize(t->s_out));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    t->total = base;
+    if (offsets) *offsets = t->h_off;
+    if (hits) *hits = t->h_hits;
+    if (total) *total = t->total;
+    return BXG_OK;
+}
+
+static int g_find_mode = -1;    // 1 = single-pass fused kernel (default), 0 = count / scan / fill
+static int find_mode() {
+    if (g_find_mode < 0) {
+        const char *e = getenv("BXB200_FIND_MODE");
+        g_find_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_find_mode;
+}
+
+int bxg_set_find_mode(int mode) {
+    if (mode != 0 && mode != 1) return set_error(BXG_ERR_ARG, "find mode must be 0 (three-pass) or 1 (single-pass)");
+    g_find_mode = mode;
+    return BXG_OK;
+}
+
+int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq, int loc,
+                   int64_t *total) {
+    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
+    if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
+    return find_mode() ? find_fused(t, qtree, qs, qe, nq, loc, total) : find_three_pass(t, qtree, qs, qe, nq, loc, total);
+}
+
+int bxg_itree_find_host(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
+                        const int64_t **offsets, const int32_t **hits, int64_t *total) {
+    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
+    if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
+    return find_mode() ? find_host_fused(t, qtree, qs, qe, nq, offsets, hits, total)
+                       : find_host_three_pass(t, qtree, qs, qe, nq, offsets, hits, total);
 }
 
 int bxg_itree_fetch(bxg_itree_t *t, int64_t *offsets, int32_t *hits) {

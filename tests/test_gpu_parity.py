@@ -59,6 +59,34 @@ def test_find_c1_golden(bx):
     assert np.array_equal(t.count_batch(qs, qe), np.diff(g["c1_offsets"]).astype(np.int32))
 
 
+def test_find_single_pass_and_three_pass_agree(bx, orc):
+    """Both find implementations (single-pass look-back kernel / count+scan+fill) give the oracle's ordered CSR, on the
+    device-array path and on the chunk-pipelined host path (>1 chunk, hit-buffer regrowth on a fresh index)."""
+    import ctypes as C
+    rng = np.random.default_rng(4242)
+    n, nq = 600_000, 2_500_000
+    s, e = synth.uniform_intervals(rng, n, 30_000_000, 3000)
+    qs, qe = synth.uniform_intervals(rng, nq, 30_000_000, 3000)
+    ooff, ohits = orc.OracleIntervalTree(s, e).find(qs, qe)
+    L = bx.lib.lib()
+    try:
+        for mode in (0, 1):
+            bx.lib.check(L.bxg_set_find_mode(mode))
+            t = tree_of(bx, s, e)                       # fresh index: first find must grow its hit buffers
+            off, hits = t.find_batch(qs, qe)            # pipelined host path, 2 chunks
+            assert np.array_equal(off, ooff) and np.array_equal(hits, ohits), mode
+            off, hits = t.find_batch(qs[:1000], qe[:1000])
+            assert np.array_equal(off, ooff[:1001]) and np.array_equal(hits, ohits[:ooff[1000]]), mode
+            total = C.c_int64()
+            h = t._index._h
+            bx.lib.check(L.bxg_itree_find(h, None, bx.lib.ptr(qs), bx.lib.ptr(qe), nq, bx.lib.HOST, C.byref(total)))
+            off2 = np.empty(nq + 1, np.int64); hits2 = np.empty(total.value, np.int32)
+            bx.lib.check(L.bxg_itree_fetch(h, bx.lib.ptr(off2), bx.lib.ptr(hits2)))
+            assert np.array_equal(off2, ooff) and np.array_equal(hits2, ohits), mode
+    finally:
+        bx.lib.check(L.bxg_set_find_mode(1))
+
+
 def test_find_edge_sets_golden(bx):
     g = np.load(os.path.join(G, "find.npz"))
     for k, (s, e, qs, qe) in enumerate(synth.edge_sets()):
