@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbxb200.so")
 SOURCES = ["runtime.cu", "bits.cu", "itree.cu", "aggregate.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "bxb200.h")]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "itree_search.cuh"),
+           os.path.join(HERE, "..", "include", "bxb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--expt-extended-lambda",
@@ -38,11 +39,13 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
+    # tuning experiments: BXB200_NVCC_FLAGS="-DFIND_MIN_CTAS=5" rebuilds itree.cu with extra defines
+    extra = os.environ.get("BXB200_NVCC_FLAGS", "").split()
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
-        if force or _stale(o, [s] + HEADERS):
-            cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        if force or _stale(o, [s] + HEADERS) or (extra and src == "itree.cu"):
+            cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             subprocess.check_call(cmd)
         objs.append(o)
     if force or _stale(LIB, objs):

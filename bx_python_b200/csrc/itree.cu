@@ -24,6 +24,9 @@ constexpr int MAX_LEVELS = 6;          // 32^7 > 2^31
 constexpr int MAX_SPLIT = 4096;        // splitter entries per array (16 KB each in shared memory)
 constexpr int SMEM_TREES = 256;        // toff entries cached in shared memory
 constexpr int FIND_THREADS = 256;
+#ifndef FIND_MIN_CTAS
+#define FIND_MIN_CTAS 4            // co-resident CTAs per SM the find kernels are compiled for (register budget 64)
+#endif
 
 constexpr int MAX_KLEV = 5;            // 16-ary sampled search levels: strides 1, 16, 256, 4096, 65536
 
@@ -249,7 +252,7 @@ __device__ __forceinline__ const SmemIndex stage_index(const IndexView &ix, unsi
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(FIND_THREADS)
+__global__ void __launch_bounds__(FIND_THREADS, FIND_MIN_CTAS)
 k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, const int32_t *__restrict__ qs_, const int32_t *__restrict__ qe_,
        int64_t nq, int32_t *__restrict__ cnt, int32_t *__restrict__ lo_, int32_t *__restrict__ hi_,
        const int64_t *__restrict__ off, int32_t *__restrict__ hits, unsigned long long *total) {
@@ -280,13 +283,8 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
         } else {
             const uint32_t lo = (uint32_t)lo_[q], hi = (uint32_t)hi_[q];
             int32_t *dst = hits + off[q];
-            bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t k0, unsigned mask) {
-                while (mask) {
-                    const int b = __ffs((int)mask) - 1;
-                    mask &= mask - 1;
-                    *dst++ = __ldg(ix.I + k0 + b);
-                }
-            });
+            bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                           [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.I, k0, mask, dst, Ld4()); });
         }
     }
     if (!FILL && total) {
@@ -323,7 +321,7 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS)
+__global__ void __launch_bounds__(FUSED_THREADS, FIND_MIN_CTAS)
 k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, const int32_t *__restrict__ qs_,
              const int32_t *__restrict__ qe_, int64_t nq, int64_t *__restrict__ off, int32_t *__restrict__ hits,
              int64_t hits_cap, const int64_t *__restrict__ base_ptr, unsigned long long *__restrict__ tile_state,
@@ -394,13 +392,8 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
             off[q] = base + excl;
             if (fits && c > 0) {
                 int32_t *dst = hits + base + excl;
-                bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t k0, unsigned mask) {
-                    while (mask) {
-                        const int b = __ffs((int)mask) - 1;
-                        mask &= mask - 1;
-                        *dst++ = __ldg(ix.I + k0 + b);
-                    }
-                });
+                bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                               [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.I, k0, mask, dst, Ld4()); });
             }
         }
         if (threadIdx.x == 0) {
@@ -620,11 +613,12 @@ int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, c
     const int64_t npad = ((n + 15) & ~15ll) + 16;     // S / PM are read in aligned 16-entry groups
     BUILD_CUDA(cudaMalloc(&t->S, (size_t)npad * 4));
     BUILD_CUDA(cudaMalloc(&t->E, (size_t)npad * 4));       // walked in aligned 16-item groups; pad never hits
-    BUILD_CUDA(cudaMalloc(&t->I, (size_t)n * 4));
+    BUILD_CUDA(cudaMalloc(&t->I, (size_t)npad * 4));       // read in aligned 16-item groups by the fill
     BUILD_CUDA(cudaMalloc(&t->PM, (size_t)npad * 4));
     BXG_LAUNCH(k_fill_i32, 1, 64, 0, t->S + n, npad - n, INT32_MAX);
     BXG_LAUNCH(k_fill_i32, 1, 64, 0, t->PM + n, npad - n, INT32_MAX);
     BXG_LAUNCH(k_fill_i32, 1, 64, 0, t->E + n, npad - n, INT32_MIN);
+    BXG_LAUNCH(k_fill_i32, 1, 64, 0, t->I + n, npad - n, -1);
     BUILD_CUDA(cudaMemcpyAsync(t->I, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, c.stream));
     // k0/k1 are free now: reuse as TE / running max
     BXG_LAUNCH(k_gather_items, g, 256, 0, d_tree && ntrees > 1 ? d_tree : nullptr, d_start, d_end, t->I, n, t->S, t->E, k0);

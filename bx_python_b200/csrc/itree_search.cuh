@@ -192,4 +192,30 @@ BXG_HD void walk_hits(const int32_t *E, const int32_t *const *M, int nlev, uint3
     }
 }
 
+// Write the item ids of the hits of one 16-item group: the whole aligned group of I is fetched with four 16-byte
+// loads issued back to back (one 64-byte line), THEN the selected ids are stored -- a load per hit interleaved with
+// the stores would serialise on every store (the compiler must assume hits[] may alias I[]).
+template <typename LD4>
+BXG_HD int32_t *emit_group(const int32_t *I, uint32_t k0, unsigned mask, int32_t *dst, const LD4 &ld4) {
+    const int4 *p = reinterpret_cast<const int4 *>(I + k0);
+    const int4 a = ld4(p), b = ld4(p + 1), c = ld4(p + 2), d = ld4(p + 3);
+    if (mask & 0x0001u) *dst++ = a.x;
+    if (mask & 0x0002u) *dst++ = a.y;
+    if (mask & 0x0004u) *dst++ = a.z;
+    if (mask & 0x0008u) *dst++ = a.w;
+    if (mask & 0x0010u) *dst++ = b.x;
+    if (mask & 0x0020u) *dst++ = b.y;
+    if (mask & 0x0040u) *dst++ = b.z;
+    if (mask & 0x0080u) *dst++ = b.w;
+    if (mask & 0x0100u) *dst++ = c.x;
+    if (mask & 0x0200u) *dst++ = c.y;
+    if (mask & 0x0400u) *dst++ = c.z;
+    if (mask & 0x0800u) *dst++ = c.w;
+    if (mask & 0x1000u) *dst++ = d.x;
+    if (mask & 0x2000u) *dst++ = d.y;
+    if (mask & 0x4000u) *dst++ = d.z;
+    if (mask & 0x8000u) *dst++ = d.w;
+    return dst;
+}
+
 }  // namespace bxs

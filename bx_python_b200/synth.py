@@ -175,3 +175,29 @@ def genome_scores(n_total, nw_total, seed, chrom_lens=HG38_LENS, mask_density=0.
         we = ws + rng.integers(1, 41, nw, dtype=np.int64)
         out.append((origin, v, ws.astype(np.int32), we.astype(np.int32)))
     return out
+
+
+# ---- text inputs for the bitset_builders / bitset_utils drop-ins ------------------------------------------------------
+def bed_lines(seed, n=400):
+    """-> (lines, lens): BED-like text incl. comments, blank lines, a strand column, unsorted chromosomes."""
+    rng = np.random.default_rng(6000 + seed)
+    lens = {"chr1": 50000, "chr2": 20000, "chrX": 7777}
+    names = list(lens) + ["chrUn"]            # chrUn has no length -> MAX-sized bitset
+    lines = ["# header", "\n"]
+    for _ in range(n):
+        c = names[int(rng.integers(0, len(names)))]
+        L = lens.get(c, 100000)
+        s = int(rng.integers(0, L - 300))
+        e = s + int(rng.integers(0, 300))
+        strand = "+-"[int(rng.integers(0, 2))]
+        lines.append(f"{c}\t{s}\t{e}\tname\t0\t{strand}\n")
+    return lines, lens
+
+
+def exon_lists(seed):
+    rng = np.random.default_rng(6100 + seed)
+
+    def one():
+        s = np.sort(rng.integers(0, 5000, int(rng.integers(1, 30))))
+        return [(int(a), int(a + rng.integers(1, 120))) for a in s]
+    return one(), one()

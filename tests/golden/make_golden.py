@@ -171,6 +171,42 @@ def golden_aggregate():
     print("aggregate.json:", len(cases), "cases;", cases[0]["lines"][:3])
 
 
+def golden_builders():
+    """Reference lib/bx/bitset_builders.py + lib/bx/bitset_utils.py (pure Python over the compiled bx.bitset)."""
+    import bx
+    if os.path.join(REFERENCE, "lib", "bx") not in bx.__path__:
+        bx.__path__.append(os.path.join(REFERENCE, "lib", "bx"))
+    from bx import bitset_builders as bb
+    from bx import bitset_utils as bu
+    cases = []
+    for seed in range(4):
+        lines, lens = synth.bed_lines(seed)
+        out = {}
+        for name, fn, kw in (("file", bb.binned_bitsets_from_file, {"lens": lens}),
+                             ("file_pad", bb.binned_bitsets_from_file, {"lens": lens, "upstream_pad": 25}),
+                             ("bed", bb.binned_bitsets_from_bed_file, {"lens": lens}),
+                             ("prox", bb.binned_bitsets_proximity, {"upstream": 30, "downstream": 10})):
+            d = fn(lines if name != "prox" else [ln for ln in lines if not ln.isspace()], **kw)   # prox does not skip blanks
+            out[name] = {c: bu.bits2list(b) for c, b in d.items()}
+        chr1 = [ln for ln in lines if ln.startswith("chr1\t")]
+        out["file_pad1"] = {c: bu.bits2list(b) for c, b in
+                            bb.binned_bitsets_from_file(chr1, lens=lens, upstream_pad=10, downstream_pad=40).items()}
+        lst = [ln.split()[:3] for ln in lines if not ln.startswith("#") and not ln.isspace()]
+        out["list"] = {c: bu.bits2list(b) for c, b in bb.binned_bitsets_from_list(lst).items()}
+        noblank = [ln for ln in lines if not ln.isspace()]            # by_chrom does not skip blank lines either
+        out["by_chrom"] = bu.bits2list(bb.binned_bitsets_by_chrom(noblank, "chr2"))
+        ex1, ex2 = synth.exon_lists(seed)
+        out["intersect"] = bu.bitset_intersect(ex1, ex2)
+        out["subtract"] = bu.bitset_subtract(ex1, ex2)
+        out["complement"] = bu.bitset_complement(ex1)
+        out["union"] = bu.bitset_union(ex1 + ex2)
+        bits = bu.list2bits(ex1)
+        out["interval_intersect"] = [bu.bitset_interval_intersect(bits, a, b) for a, b in ((0, 5000), (100, 900), (2500, 2600))]
+        cases.append({"seed": seed, "out": out})
+    json.dump(cases, open(os.path.join(HERE, "builders.json"), "w"))
+    print("builders.json:", len(cases), "cases")
+
+
 if __name__ == "__main__":
     orc.build_ref(REFERENCE)
     bs, ix = orc.ref_modules()
@@ -178,3 +214,4 @@ if __name__ == "__main__":
     golden_neighbors(ix)
     golden_bitset(bs)
     golden_aggregate()
+    golden_builders()

@@ -577,6 +577,44 @@ def test_bitset_chromosome_scale_properties(bx, orc):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# callers: bitset_builders / bitset_utils drop-ins against the reference's own outputs
+# ---------------------------------------------------------------------------------------------------------------
+def test_builders_and_utils_golden(bx):
+    from bx_python_b200 import bitset_builders as bb
+    from bx_python_b200 import bitset_utils as bu
+
+    def runs(d):
+        return {c: [list(r) for r in bu.bits2list(b)] for c, b in d.items()}
+    for case in json.load(open(os.path.join(G, "builders.json"))):
+        lines, lens = synth.bed_lines(case["seed"])
+        g = case["out"]
+        noblank = [ln for ln in lines if not ln.isspace()]
+        assert runs(bb.binned_bitsets_from_file(lines, lens=lens)) == g["file"]
+        assert runs(bb.binned_bitsets_from_file(lines, lens=lens, upstream_pad=25)) == g["file_pad"]
+        chr1 = [ln for ln in lines if ln.startswith("chr1\t")]
+        assert runs(bb.binned_bitsets_from_file(chr1, lens=lens, upstream_pad=10, downstream_pad=40)) == g["file_pad1"]
+        assert runs(bb.binned_bitsets_from_bed_file(lines, lens=lens)) == g["bed"]
+        assert runs(bb.binned_bitsets_proximity(noblank, upstream=30, downstream=10)) == g["prox"]
+        lst = [ln.split()[:3] for ln in noblank if not ln.startswith("#")]
+        assert runs(bb.binned_bitsets_from_list(lst)) == g["list"]
+        assert [list(r) for r in bu.bits2list(bb.binned_bitsets_by_chrom(noblank, "chr2"))] == g["by_chrom"]
+        ex1, ex2 = synth.exon_lists(case["seed"])
+        assert [list(r) for r in bu.bitset_intersect(ex1, ex2)] == g["intersect"]
+        assert [list(r) for r in bu.bitset_subtract(ex1, ex2)] == g["subtract"]
+        assert [list(r) for r in bu.bitset_complement(ex1)] == g["complement"]
+        assert [list(r) for r in bu.bitset_union(ex1 + ex2)] == g["union"]
+        bits = bu.list2bits(ex1)
+        got = [[list(r) for r in bu.bitset_interval_intersect(bits, a, b)] for a, b in ((0, 5000), (100, 900), (2500, 2600))]
+        assert got == g["interval_intersect"]
+    # the reference raises on the offending line (here: end < start -> negative count), before touching the device
+    with pytest.raises(IndexError, match="must be non-negative"):
+        bb.binned_bitsets_from_file(["chr1\t50\t10\n"], lens={"chr1": 1000})
+    chroms = np.array([0, 1, 0, 1]); s = np.array([5, 10, 100, 0]); e = np.array([50, 20, 130, 5])
+    out = bb.binned_bitsets_from_arrays(chroms, s, e, [1000, 500])
+    assert bu.bits2list(out[0]) == [(5, 50), (100, 130)] and bu.bits2list(out[1]) == [(0, 5), (10, 20)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # aggregate
 # ---------------------------------------------------------------------------------------------------------------
 def test_aggregate_golden(bx):
