@@ -315,16 +315,16 @@ def run_ours(args):
     q_all = int(comm.allreduce_sum_i64(np.array([nq]))[0])
     value = q_all * args.steps / (ms_max * 1e-3)
 
-    # ---- A/B: the three-pass implementation (count kernel, CUB scan, fill kernel) on the same inputs ------------------
-    check(L.bxg_set_find_mode(0))
+    # ---- A/B: the single-pass implementation (ticketed tiles + decoupled look-back) on the same inputs ----------------
+    check(L.bxg_set_find_mode(1))
     for _ in range(2):
         step_dev()
     timer.start()
     for _ in range(args.steps):
         step_dev()
     timer.stop()
-    three_pass_ms = timer.elapsed_ms() / args.steps
-    check(L.bxg_set_find_mode(1))
+    single_pass_ms = timer.elapsed_ms() / args.steps
+    check(L.bxg_set_find_mode(-1))
     step_dev()
 
     # ---- per-kernel CUDA-event times for the roofline (separate pass so event overhead is not in `value`) --------------
@@ -394,7 +394,7 @@ def run_ours(args):
 
     extra = {"build_ms": min(build_ms), "hits_per_step": hits_all, "hits_per_query": hits_all / q_all,
              "per_chrom_hits_checksum": int((per_chrom * np.arange(1, 25)).sum()), "parity_spot_check": parity,
-             "e2e_serial_copies": e2e_serial, "three_pass_ms_per_step": three_pass_ms}
+             "e2e_serial_copies": e2e_serial, "single_pass_kernel_ms_per_step": single_pass_ms}
 
     if rank != 0:
         comm.close()

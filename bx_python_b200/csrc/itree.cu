@@ -1035,17 +1035,21 @@ static int find_host_fused(bxg_itree_t *t, const int32_t *qtree, const int32_t *
     return BXG_OK;
 }
 
-static int g_find_mode = -1;    // 1 = single-pass fused kernel (default), 0 = count / scan / fill
+// find implementation: -1 = auto (default), 0 = count / scan / fill everywhere, 1 = single-pass kernel everywhere.
+// Measured on B200 (profiles/r01g): with queries resident in HBM the three independent passes win (1.53 vs 1.62 ms per
+// 10 M queries: no per-tile barriers, more loads in flight); on the chunk-pipelined host path the single-pass kernel
+// wins (1.4e9 vs 1.2e9 queries/s end to end: one launch and one host round trip per chunk).  Auto picks accordingly.
+static int g_find_mode = -2;
 static int find_mode() {
-    if (g_find_mode < 0) {
+    if (g_find_mode == -2) {
         const char *e = getenv("BXB200_FIND_MODE");
-        g_find_mode = (e && e[0] == '0') ? 0 : 1;
+        g_find_mode = !e ? -1 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : -1));
     }
     return g_find_mode;
 }
 
 int bxg_set_find_mode(int mode) {
-    if (mode != 0 && mode != 1) return set_error(BXG_ERR_ARG, "find mode must be 0 (three-pass) or 1 (single-pass)");
+    if (mode < -1 || mode > 1) return set_error(BXG_ERR_ARG, "find mode must be -1 (auto), 0 (three-pass) or 1 (single-pass)");
     g_find_mode = mode;
     return BXG_OK;
 }
@@ -1054,15 +1058,15 @@ int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, cons
                    int64_t *total) {
     if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
     if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
-    return find_mode() ? find_fused(t, qtree, qs, qe, nq, loc, total) : find_three_pass(t, qtree, qs, qe, nq, loc, total);
+    return find_mode() == 1 ? find_fused(t, qtree, qs, qe, nq, loc, total) : find_three_pass(t, qtree, qs, qe, nq, loc, total);
 }
 
 int bxg_itree_find_host(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
                         const int64_t **offsets, const int32_t **hits, int64_t *total) {
     if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
     if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
-    return find_mode() ? find_host_fused(t, qtree, qs, qe, nq, offsets, hits, total)
-                       : find_host_three_pass(t, qtree, qs, qe, nq, offsets, hits, total);
+    return find_mode() != 0 ? find_host_fused(t, qtree, qs, qe, nq, offsets, hits, total)
+                            : find_host_three_pass(t, qtree, qs, qe, nq, offsets, hits, total);
 }
 
 int bxg_itree_fetch(bxg_itree_t *t, int64_t *offsets, int32_t *hits) {

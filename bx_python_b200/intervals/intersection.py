@@ -53,15 +53,44 @@ class Interval:
 
 
 class IntervalNode:
-    """What ``traverse`` hands to its callback (intersection.pyx:61-101): start, end and the stored object."""
+    """intersection.pyx:61-268.  Two roles, as in the reference: the object ``traverse`` hands to its callback
+    (``start``, ``end``, ``interval``), and -- when used directly -- the root handle of a tree:
+    ``root = IntervalNode(s, e, obj); root = root.insert(s2, e2, obj2); root.find(a, b); root.left(p, n, max_dist)``.
+    The treap itself does not exist here; a root handle forwards to a device-backed ``IntervalTree``."""
 
-    __slots__ = ("start", "end", "interval")
+    __slots__ = ("start", "end", "interval", "_tree")
 
-    def __init__(self, start, end, interval):
-        self.start, self.end, self.interval = start, end, interval
+    def __init__(self, start, end, interval, _tree=None):
+        self.start, self.end, self.interval = _c_int(start), _c_int(end), interval
+        self._tree = _tree
 
     def __repr__(self):
         return "IntervalNode(%i, %i)" % (self.start, self.end)
+
+    def _root(self):
+        if self._tree is None:              # first use as a root: the node's own interval is the first item
+            self._tree = IntervalTree()
+            self._tree.insert(self.start, self.end, self.interval)
+        return self._tree
+
+    def insert(self, start, end, interval):
+        """Insert into the tree rooted here; returns the (new) root, like the reference (:103-138)."""
+        self._root().insert(start, end, interval)
+        return self
+
+    def intersect(self, start, end, sort=True):
+        return self._root().find(start, end)
+
+    find = intersect
+
+    def left(self, position, n=1, max_dist=2500):
+        return self._root().before(position, n, max_dist)
+
+    def right(self, position, n=1, max_dist=2500):
+        return self._root().after(position, n, max_dist)
+
+    def traverse(self, func):
+        self._root().traverse(func)
 
 
 class _DeviceIndex:

@@ -56,5 +56,30 @@ def raw(path):
         print()
 
 
+def traffic(path):
+    """Merge dram bytes per launch (read + write, averaged over the captured launches) into profiles/traffic.json,
+    keyed by the kernel names bench.py uses."""
+    import json
+    import os
+    import re
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = {}
+    for r in rows[2:]:
+        m = re.match(r"(?:void )?([A-Za-z_0-9]+(?:<[^>]*>)?)", r[ik])
+        name = m.group(1).replace("<0>", "<false>").replace("<1>", "<true>")
+        b = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+        acc.setdefault(name, []).append(b)
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
+    cur = json.load(open(dst)) if os.path.exists(dst) else {}
+    for k, v in acc.items():
+        cur[k] = int(sum(v) / len(v))
+    json.dump(cur, open(dst, "w"), indent=1, sort_keys=True)
+    print(json.dumps(cur, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](sys.argv[2])

@@ -84,7 +84,7 @@ def test_find_single_pass_and_three_pass_agree(bx, orc):
             bx.lib.check(L.bxg_itree_fetch(h, bx.lib.ptr(off2), bx.lib.ptr(hits2)))
             assert np.array_equal(off2, ooff) and np.array_equal(hits2, ohits), mode
     finally:
-        bx.lib.check(L.bxg_set_find_mode(1))
+        bx.lib.check(L.bxg_set_find_mode(-1))
 
 
 def test_find_edge_sets_golden(bx):
@@ -303,6 +303,30 @@ def test_neighbors_reference_unit_tests(bx):
     e = IntervalTree()
     assert e.after(100) == e.before(100) == e.after_interval(100) == e.before_interval(100) == []
     assert e.upstream_of_interval(100) == e.downstream_of_interval(100) == []
+
+
+def test_interval_node_root_handle(bx):
+    """intersection_tests.py:17-54 NeighborTestCase, written against IntervalNode exactly as the reference test is."""
+    Interval, IntervalNode = bx.ix.Interval, bx.ix.IntervalNode
+    iv = IntervalNode(50, 59, Interval(50, 59))
+    for i in range(0, 110, 10):
+        if i == 50:
+            continue
+        f = Interval(i, i + 9)
+        iv = iv.insert(f.start, f.end, f)
+    assert str(iv.left(60, n=2)) == str([Interval(50, 59), Interval(40, 49)])
+    for i in range(10, 100, 10):
+        assert iv.left(i, max_dist=10, n=1)[0].end == i - 1
+    assert len(iv.left(60, n=200)) == 6
+    for i in range(10, 100, 10):
+        r = iv.right(i + 1, n=1)
+        assert len(r) == 1 and r[0].start == i + 10
+    for i in range(0, 100, 10):
+        assert iv.right(i - 1, max_dist=10, n=1)[0].start == i
+    assert [x.start for x in iv.find(45, 72)] == [40, 50, 60, 70]
+    seen = []
+    iv.traverse(lambda node: seen.append((node.start, node.end)))
+    assert seen == [(i, i + 9) for i in range(0, 110, 10)]
 
 
 def test_neighbors_lotsa(bx):
