@@ -327,6 +327,21 @@ def run_ours(args):
     check(L.bxg_set_find_mode(-1))
     step_dev()
 
+    # ---- the same queries in sorted-BED order (chrom, start): what locality buys (not the headline: `value` is shuffled) --
+    order = np.lexsort((qs, qt))
+    s_qt, s_qs, s_qe = (_lib.DeviceBuffer(a[order]) for a in (qt, qs, qe))
+    tot2 = C.c_int64()
+    for _ in range(2):
+        check(L.bxg_itree_find(forest.handle, s_qt.ptr, s_qs.ptr, s_qe.ptr, nq, _lib.DEVICE, C.byref(tot2)))
+    timer.start()
+    for _ in range(args.steps):
+        check(L.bxg_itree_find(forest.handle, s_qt.ptr, s_qs.ptr, s_qe.ptr, nq, _lib.DEVICE, C.byref(tot2)))
+    timer.stop()
+    sorted_ms = timer.elapsed_ms() / args.steps
+    assert tot2.value == hits_total
+    del s_qt, s_qs, s_qe
+    step_dev()
+
     # ---- per-kernel CUDA-event times for the roofline (separate pass so event overhead is not in `value`) --------------
     _lib.profile_enable(True)
     for _ in range(args.steps):
@@ -394,7 +409,8 @@ def run_ours(args):
 
     extra = {"build_ms": min(build_ms), "hits_per_step": hits_all, "hits_per_query": hits_all / q_all,
              "per_chrom_hits_checksum": int((per_chrom * np.arange(1, 25)).sum()), "parity_spot_check": parity,
-             "e2e_serial_copies": e2e_serial, "single_pass_kernel_ms_per_step": single_pass_ms}
+             "e2e_serial_copies": e2e_serial, "single_pass_kernel_ms_per_step": single_pass_ms,
+             "sorted_queries_ms_per_step": sorted_ms}
 
     if rank != 0:
         comm.close()

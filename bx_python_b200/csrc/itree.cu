@@ -748,16 +748,6 @@ static int find_host_three_pass(bxg_itree_t *t, const int32_t *qtree, const int3
                                 const int64_t **offsets, const int32_t **hits, int64_t *total) {
     Context &c = ctx();
     BXG_TRY(ensure_pipeline(t));
-    if (false) {
-        BXG_CUDA(cudaStreamCreateWithFlags(&t->s_in, cudaStreamNonBlocking));
-        BXG_CUDA(cudaStreamCreateWithFlags(&t->s_out, cudaStreamNonBlocking));
-        for (int k = 0; k < bxg_itree::MAX_CHUNKS; k++) {
-            BXG_CUDA(cudaEventCreateWithFlags(&t->ev_in[k], cudaEventDisableTiming));
-            BXG_CUDA(cudaEventCreateWithFlags(&t->ev_scan[k], cudaEventDisableTiming));
-            BXG_CUDA(cudaEventCreateWithFlags(&t->ev_fill[k], cudaEventDisableTiming));
-        }
-        BXG_CUDA(cudaMallocHost(&t->h_tot, (bxg_itree::MAX_CHUNKS + 1) * 8));
-    }
     BXG_TRY(ensure_query_buffers(t, nq));
     if (nq + 1 > t->h_off_cap) {
         BXG_CUDA(cudaStreamSynchronize(t->s_out));

@@ -1,0 +1,33 @@
+"""GPU: a plain C program drives libbxb200.so through include/bxb200.h (no Python shim, no torch) -- the drop-in
+boundary itself.  Expected values come from the oracle and from the probes recorded in SURVEY 8(a) addendum 2."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_client(tmp_path):
+    from oracle import oracle as orc
+    exe = str(tmp_path / "abi_client")
+    pkg = os.path.join(ROOT, "bx_python_b200")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "abi_client.c"), "-L", pkg, "-l:libbxb200.so",
+                           "-Wl,-rpath," + pkg])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    a, b = orc.OracleBinnedBitSet(10000, 10), orc.OracleBinnedBitSet(10000, 10)
+    a.set_ranges([0, 100, 5000], [10, 900, 2500])
+    b.set_ranges([50, 6000], [500, 100])
+    a.iand(b)
+    exp = ["and_count %d" % a.count_range(0, 10000)]
+    rs, re = a.runs()
+    exp += ["run %d %d" % (x, y) for x, y in zip(rs.tolist(), re.tolist())]
+    a.invert()
+    exp.append("strict_counts %d %d %d" % tuple(a.count_range(s, c) for s, c in ((1500, 100), (1000, 1000), (0, 10000))))
+    exp.append("next_set %d" % a.next_set(100))
+    exp += ["find 0: 3 0 1 4 2", "find 1: 0", "find 2: 0 4", "find 3: 2", "total 9"]
+    assert lines == exp
