@@ -251,6 +251,11 @@ def run_ours(args):
 
     rank, world, local_rank = env_rank()
     os.environ.setdefault("BXB200_DEVICE", str(local_rank))
+    # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at
+    # NCCL_DEBUG=VERSION) out of it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     from bx_python_b200 import _lib
     from bx_python_b200._lib import check, ptr
     from bx_python_b200.intervals import IntervalForest
@@ -666,6 +671,29 @@ def bench_bed_intersect(peak):
     res["count_ranges"] = {"ms": ms, "queries_per_s": n / (ms * 1e-3), "algorithmic_bytes": 12 * n,
                            "gbs": 12 * n / (ms * 1e-3) / 1e9,
                            "note": "rank-table lookups (2 table words + 2 bitmap words per query): latency/L2-bound"}
+    # genome-wide form: every BED line carries its chromosome id; one launch
+    which = np.concatenate([np.full(len(f1[c][0]), c, np.int32) for c in range(24)])
+    qs_all = np.concatenate([f1[c][0] for c in range(24)])
+    qc_all = np.concatenate([(f1[c][1] - f1[c][0]).astype(np.int32) for c in range(24)])
+    perm = np.random.default_rng(2).permutation(len(which))
+    d_w, d_s, d_c = (_lib.DeviceBuffer(a[perm]) for a in (which, qs_all, qc_all))
+    d_out = _lib.DeviceBuffer(np.zeros(len(which), np.int32))
+    hs = (C.c_void_p * 24)(*[b._h for b in bits])
+
+    def genome_count():
+        check(L.bxg_bits_count_ranges_multi(hs, 24, d_w.ptr, d_s.ptr, d_c.ptr, len(which), d_out.ptr, 1, _lib.DEVICE))
+    genome_count()
+    _lib.sync()
+    timer.start()
+    for _ in range(5):
+        genome_count()
+    timer.stop()
+    ms = timer.elapsed_ms() / 5
+    res["count_ranges_genome"] = {"ms": ms, "queries_per_s": n / (ms * 1e-3), "algorithmic_bytes": 16 * n,
+                                  "gbs": 16 * n / (ms * 1e-3) / 1e9, "launches_per_pass": 1}
+    gout = np.empty(len(which), np.int32)
+    check(L.bxg_memcpy_d2h(gout.ctypes.data_as(C.c_void_p), d_out.ptr, gout.nbytes))
+    _lib.sync()
     for r in res.values():
         r["frac"] = r["gbs"] / peak
     # parity of one chromosome against the oracle (strict count_range semantics)
@@ -676,6 +704,11 @@ def bench_bed_intersect(peak):
     check(L.bxg_memcpy_d2h(got.ctypes.data_as(C.c_void_p), dev[c][6].ptr, got.nbytes))
     _lib.sync()
     assert np.array_equal(got, ob.count_ranges(f1[c][0], f1[c][1] - f1[c][0])), "bed_intersect parity"
+    sel = which[perm] == c
+    inv = np.empty(len(perm), np.int64)
+    inv[perm] = np.arange(len(perm))
+    first = int(np.nonzero(which == c)[0][0])
+    assert np.array_equal(gout[inv[first:first + len(got)]], got) and int(sel.sum()) == len(got), "genome-wide count parity"
     res["overlapping_chr22"] = int((got >= 1).sum())
     res["parity"] = "chr22 counts bit-identical to oracle"
     return res
@@ -721,11 +754,40 @@ def bench_aggregate(peak):
     dense[origin:] = v
     ref = orc.aggregate(dense, ws, we)["avg"]
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), "aggregate parity"
+    # genome-wide form: all windows (with their chromosome id) in one launch
+    wt_all = np.concatenate([np.full(len(t[2]), k, np.int32) for k, t in enumerate(tracks)])
+    ws_all = np.concatenate([t[2] for t in tracks])
+    we_all = np.concatenate([t[3] for t in tracks])
+    perm = np.random.default_rng(1).permutation(nw_all)          # BED order, not grouped by chromosome
+    d_wt, d_ws, d_we = (_lib.DeviceBuffer(a[perm]) for a in (wt_all, ws_all, we_all))
+    outs = [_lib.DeviceBuffer(np.zeros(nw_all, np.float32)) for _ in range(2)] + [_lib.DeviceBuffer(np.zeros(nw_all, np.int32))] + \
+           [_lib.DeviceBuffer(np.zeros(nw_all, np.float32)) for _ in range(2)]
+    ht = (C.c_void_p * len(handles))(*[h[0] for h in handles])
+
+    def genome_pass():
+        check(L.bxg_aggregate_multi(ht, None, len(handles), d_wt.ptr, d_ws.ptr, d_we.ptr, nw_all, _lib.DEVICE,
+                                    outs[0].ptr, outs[1].ptr, outs[2].ptr, outs[3].ptr, outs[4].ptr))
+    genome_pass()
+    _lib.sync()
+    timer.start()
+    for _ in range(5):
+        genome_pass()
+    timer.stop()
+    gms = timer.elapsed_ms() / 5
+    gavg = np.empty(nw_all, np.float32)
+    check(L.bxg_memcpy_d2h(gavg.ctypes.data_as(C.c_void_p), outs[1].ptr, gavg.nbytes))
+    _lib.sync()
+    sel = np.nonzero(wt_all[perm] == 20)[0]
+    ref2 = orc.aggregate(dense, ws_all[perm][sel], we_all[perm][sel])["avg"]
+    assert np.array_equal(gavg[sel].view(np.uint32), ref2.view(np.uint32)), "genome-wide aggregate parity"
     for h, *_r in handles:
         L.bxg_scores_free(h)
     return {"ms": ms, "windows_per_s": nw_all / (ms * 1e-3), "bases_per_s": bases / (ms * 1e-3),
             "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
-            "parity": "chr21 float32 averages bit-identical to oracle"}
+            "launches_per_pass": 24,
+            "genome": {"ms": gms, "windows_per_s": nw_all / (gms * 1e-3), "gbs": alg / (gms * 1e-3) / 1e9,
+                       "frac": alg / (gms * 1e-3) / 1e9 / peak, "launches_per_pass": 1},
+            "parity": "chr21 float32 averages bit-identical to oracle (per-chromosome and genome-wide launches)"}
 
 
 def main():

@@ -58,6 +58,7 @@ SIGNATURES = {
     "bxg_bits_binop_batch": [cint, pvp, pvp, i32, vp],
     "bxg_bits_count_ranges": [vp, vp, vp, i64, vp, cint, cint],
     "bxg_bits_count_all": [vp, pi64],
+    "bxg_bits_count_ranges_multi": [pvp, i32, vp, vp, vp, i64, vp, cint, cint],
     "bxg_bits_next": [vp, i32, i32, cint, pi32],
     "bxg_bits_runs_count": [vp, pi64],
     "bxg_bits_runs_fetch": [vp, vp, vp, i64],
@@ -80,6 +81,7 @@ SIGNATURES = {
     "bxg_scores_create": [vp, i64, i32, cint, pvp],
     "bxg_scores_free": [vp],
     "bxg_aggregate": [vp, vp, vp, vp, i64, cint, vp, vp, vp, vp, vp],
+    "bxg_aggregate_multi": [pvp, pvp, i32, vp, vp, vp, i64, cint, vp, vp, vp, vp, vp],
     "bxg_comm_unique_id": [C.c_char_p],
     "bxg_comm_init": [C.c_char_p, cint, cint],
     "bxg_comm_allreduce_i64": [vp, i64],

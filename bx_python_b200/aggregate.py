@@ -50,6 +50,27 @@ class ScoreTrack:
         return out
 
 
+def aggregate_genome(tracks, track_ids, starts, ends, masks=None):
+    """The whole BED file in one launch: window w is reduced over ``tracks[track_ids[w]]`` (the script's
+    ``scores_by_chrom[chrom]``); ``masks`` is an optional list (entries may be None) of bit sets, one per track.
+    A track id outside the list behaves like a chromosome without scores (count 0, NaN columns)."""
+    tracks = list(tracks)
+    wt, ws, we = as_i32(track_ids), as_i32(starts), as_i32(ends)
+    nw, nt = len(ws), len(tracks)
+    out = dict(sum=np.empty(nw, np.float32), avg=np.empty(nw, np.float32), count=np.empty(nw, np.int32),
+               min=np.empty(nw, np.float32), max=np.empty(nw, np.float32))
+    ht = (C.c_void_p * nt)(*[t._h for t in tracks])
+    hm = None
+    if masks is not None:
+        for m in masks:
+            if m is not None:
+                m._flush()
+        hm = (C.c_void_p * nt)(*[(m._h if m is not None else None) for m in masks])
+    check(_lib.lib().bxg_aggregate_multi(ht, hm, nt, ptr(wt), ptr(ws), ptr(we), nw, _lib.HOST, ptr(out["sum"]),
+                                        ptr(out["avg"]), ptr(out["count"]), ptr(out["min"]), ptr(out["max"])))
+    return out
+
+
 def format_line(res, w):
     """The three columns the script prints for window w (:126-134)."""
     if res["count"][w] == 0:

@@ -253,6 +253,24 @@ def and_count_many(dst, src):
     return _batch(0, dst, src, True)
 
 
+def count_ranges_many(sets, which, starts, counts, strict=True):
+    """``sets[which[i]].count_range(starts[i], counts[i])`` for every i in one kernel launch -- the per-line lookup
+    of scripts/bed_intersect.py:46-53 (`bitsets[chrom].count_range(start, end - start)`).  Entries whose ``which`` is
+    outside the list count 0 (the script's `fields[0] in bitsets` test)."""
+    sets = list(sets)
+    w, s, c = as_i32(which), as_i32(starts), as_i32(counts)
+    for k, b in enumerate(sets):
+        sel = w == k
+        if sel.any():
+            b._check_arrays(s[sel], c[sel])        # same IndexError as the scalar call, before any device work
+        b._flush()
+    out = np.empty(len(s), np.int32)
+    h = (C.c_void_p * len(sets))(*[b._h for b in sets])
+    check(_lib.lib().bxg_bits_count_ranges_multi(h, len(sets), ptr(w), ptr(s), ptr(c), len(s), ptr(out),
+                                                 1 if strict else 0, _lib.HOST))
+    return out
+
+
 class BitSet(_DeviceBits):
     """bx.bitset.BitSet (bitset.pyx:107-173) on the device."""
 

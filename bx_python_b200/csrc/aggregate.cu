@@ -21,42 +21,72 @@ struct bxg_scores {
     bool owned = true;
 };
 
+// one window: strict left-to-right float32 accumulation over positions [ws,we) of one track
+__device__ __forceinline__ void aggregate_window(const float *__restrict__ v, int64_t n, int64_t origin,
+                                                 const uint64_t *__restrict__ mask, int64_t mask_size, int64_t ws, int64_t we,
+                                                 float &sum, float &avg, int32_t &cnt, float &mn, float &mx) {
+    int64_t a = ws - origin, b = we - origin;
+    if (a < 0) a = 0;                     // positions without a score read as NaN -> skipped
+    if (b > n) b = n;
+    float total = 0.0f, lo = 100000000.0f, hi = -100000000.0f;   // script sentinels (:112-113), exact in float32
+    int32_t c = 0;
+    for (int64_t i = a; i < b; i++) {
+        float s = __ldg(v + i);
+        if (s == 0.0f || s != s) continue;
+        if (mask) {
+            int64_t p = i + origin;
+            if (p < mask_size && ((__ldg((const unsigned long long *)mask + (p >> 6)) >> (p & 63)) & 1ull)) continue;
+        }
+        total = __fadd_rn(total, s);      // strict left-to-right float32 (no fma contraction possible, but be explicit)
+        c++;
+        hi = s > hi ? s : hi;
+        lo = s < lo ? s : lo;
+    }
+    cnt = c;
+    sum = total;
+    if (c > 0) {
+        avg = __fdiv_rn(total, (float)c);
+        mn = lo;
+        mx = hi;
+    } else {
+        const float qnan = __int_as_float(0x7fc00000);
+        avg = mn = mx = qnan;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_aggregate(const float *__restrict__ v, int64_t n, int64_t origin, const uint64_t *__restrict__ mask, int64_t mask_size,
             const int32_t *__restrict__ ws, const int32_t *__restrict__ we, int64_t nw,
             float *__restrict__ sum, float *__restrict__ avg, int32_t *__restrict__ cnt, float *__restrict__ mn,
             float *__restrict__ mx) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += stride)
+        aggregate_window(v, n, origin, mask, mask_size, __ldg(ws + w), __ldg(we + w), sum[w], avg[w], cnt[w], mn[w], mx[w]);
+}
+
+// genome-wide form: every window names its track (chromosome); one launch for the whole BED file
+struct TrackDesc {
+    const float *v;
+    int64_t n, origin;
+    const uint64_t *mask;
+    int64_t mask_size;
+};
+
+__global__ void __launch_bounds__(256)
+k_aggregate_multi(const TrackDesc *__restrict__ tracks, int ntracks, const int32_t *__restrict__ wt,
+                  const int32_t *__restrict__ ws, const int32_t *__restrict__ we, int64_t nw,
+                  float *__restrict__ sum, float *__restrict__ avg, int32_t *__restrict__ cnt, float *__restrict__ mn,
+                  float *__restrict__ mx) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += stride) {
-        int64_t a = (int64_t)__ldg(ws + w) - origin, b = (int64_t)__ldg(we + w) - origin;
-        const int64_t shift = origin;
-        if (a < 0) a = 0;                 // positions without a score read as NaN -> skipped
-        if (b > n) b = n;
-        float total = 0.0f, lo = 100000000.0f, hi = -100000000.0f;   // script sentinels (:112-113), exact in float32
-        int32_t c = 0;
-        for (int64_t i = a; i < b; i++) {
-            float s = __ldg(v + i);
-            if (s == 0.0f || s != s) continue;
-            if (mask) {
-                int64_t p = i + shift;
-                if (p < mask_size && ((__ldg((const unsigned long long *)mask + (p >> 6)) >> (p & 63)) & 1ull)) continue;
-            }
-            total = __fadd_rn(total, s);  // strict left-to-right float32 (no fma contraction possible, but be explicit)
-            c++;
-            hi = s > hi ? s : hi;
-            lo = s < lo ? s : lo;
-        }
-        cnt[w] = c;
-        sum[w] = total;
-        if (c > 0) {
-            avg[w] = __fdiv_rn(total, (float)c);
-            mn[w] = lo;
-            mx[w] = hi;
-        } else {
+        const int32_t t = __ldg(wt + w);
+        if (t >= 0 && t < ntracks) {
+            const TrackDesc d = tracks[t];
+            aggregate_window(d.v, d.n, d.origin, d.mask, d.mask_size, __ldg(ws + w), __ldg(we + w), sum[w], avg[w], cnt[w],
+                             mn[w], mx[w]);
+        } else {                          // `chrom not in scores_by_chrom` (:115): nothing counted
             const float qnan = __int_as_float(0x7fc00000);
-            avg[w] = qnan;
-            mn[w] = qnan;
-            mx[w] = qnan;
+            sum[w] = 0.0f; cnt[w] = 0; avg[w] = mn[w] = mx[w] = qnan;
         }
     }
 }
@@ -108,6 +138,52 @@ int bxg_aggregate(const bxg_scores_t *s, const bxg_bits_t *mask, const int32_t *
     BXG_LAUNCH(k_aggregate, grid_for(cdiv(nw, 256), 8), 256, 0, s->v, s->n, (int64_t)s->origin,
                bxg_bits_words_internal((const bxg_bits *)mask), (int64_t)bxg_bits_size_internal((const bxg_bits *)mask),
                (const int32_t *)dws, (const int32_t *)dwe, nw, dsum, davg, dcnt, dmn, dmx);
+    if (loc == BXG_HOST) {
+        cudaStream_t st = c.stream;
+        BXG_CUDA(cudaMemcpyAsync(sum, dsum, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        BXG_CUDA(cudaMemcpyAsync(avg, davg, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        BXG_CUDA(cudaMemcpyAsync(mn, dmn, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        BXG_CUDA(cudaMemcpyAsync(mx, dmx, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        BXG_CUDA(cudaMemcpyAsync(count, dcnt, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        BXG_CUDA(cudaStreamSynchronize(st));
+    }
+    return BXG_OK;
+}
+
+int bxg_aggregate_multi(const bxg_scores_t *const *tracks, const bxg_bits_t *const *masks, int32_t ntracks,
+                        const int32_t *wtrack, const int32_t *ws, const int32_t *we, int64_t nw, int loc,
+                        float *sum, float *avg, int32_t *count, float *mn, float *mx) {
+    BXG_TRY(ensure_init());
+    if (ntracks <= 0 || ntracks > 4096) return set_error(BXG_ERR_ARG, "ntracks must be in [1, 4096]");
+    if (nw <= 0) return BXG_OK;
+    Context &c = ctx();
+    static TrackDesc h_desc[4096];
+    for (int t = 0; t < ntracks; t++) {
+        if (!tracks[t]) return set_error(BXG_ERR_ARG, "null scores handle %d", t);
+        const bxg_bits *m = masks ? (const bxg_bits *)masks[t] : nullptr;
+        h_desc[t] = TrackDesc{tracks[t]->v, tracks[t]->n, (int64_t)tracks[t]->origin, bxg_bits_words_internal(m),
+                              (int64_t)bxg_bits_size_internal(m)};
+    }
+    void *d_desc;
+    BXG_TRY(scratch(3, sizeof(TrackDesc) * (size_t)ntracks, &d_desc));
+    BXG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(TrackDesc) * (size_t)ntracks, cudaMemcpyHostToDevice, c.stream));
+    const void *dwt, *dws, *dwe;
+    BXG_TRY(stage_in(0, wtrack, (size_t)nw * 4, loc, &dwt));
+    BXG_TRY(stage_in(1, ws, (size_t)nw * 4, loc, &dws));
+    BXG_TRY(stage_in(5, we, (size_t)nw * 4, loc, &dwe));
+    float *dsum = sum, *davg = avg, *dmn = mn, *dmx = mx;
+    int32_t *dcnt = count;
+    if (loc == BXG_HOST) {
+        void *o;
+        BXG_TRY(scratch(2, (size_t)nw * 20, &o));
+        dsum = (float *)o;
+        davg = dsum + nw;
+        dmn = davg + nw;
+        dmx = dmn + nw;
+        dcnt = (int32_t *)(dmx + nw);
+    }
+    BXG_LAUNCH(k_aggregate_multi, grid_for(cdiv(nw, 256), 8), 256, 0, (const TrackDesc *)d_desc, ntracks,
+               (const int32_t *)dwt, (const int32_t *)dws, (const int32_t *)dwe, nw, dsum, davg, dcnt, dmn, dmx);
     if (loc == BXG_HOST) {
         cudaStream_t st = c.stream;
         BXG_CUDA(cudaMemcpyAsync(sum, dsum, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));

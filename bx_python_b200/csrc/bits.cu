@@ -347,6 +347,33 @@ k_count_ranges(const uint64_t *__restrict__ words, const uint32_t *__restrict__ 
     }
 }
 
+// genome-wide form: query i addresses bit set which[i] (the dict lookup `bitsets[chrom]` of scripts/bed_intersect.py:46-53)
+struct CountDesc {
+    const uint64_t *words;
+    const uint32_t *rank;
+    const uint8_t *state;
+    int32_t bin_size, strict, size;
+};
+
+__global__ void __launch_bounds__(256)
+k_count_ranges_multi(const CountDesc *__restrict__ descs, int nsets, const int32_t *__restrict__ which,
+                     const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n,
+                     int32_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t w = __ldg(which + i), s = __ldg(start + i), c = __ldg(count + i);
+        int32_t r = 0;
+        if (w >= 0 && w < nsets && c > 0) {
+            const CountDesc d = descs[w];
+            if (s >= 0 && (int64_t)s + c <= d.size) {          // out-of-range queries are the host shim's IndexError
+                r = (int32_t)(rank_at(d.words, d.rank, (uint32_t)s + (uint32_t)c) - rank_at(d.words, d.rank, (uint32_t)s));
+                if (d.strict && d.state[s / d.bin_size] == BO) r -= s % d.bin_size;
+            }
+        }
+        out[i] = r;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // next_set / next_clear  (binBits.c:180-228, bits.c:143-190): first p in [start,end) with bit == val, else end
 // ------------------------------------------------------------------------------------------------------------------
@@ -730,6 +757,41 @@ int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *co
     if (loc == BXG_HOST) {
         BXG_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx().stream));
         BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
+    return BXG_OK;
+}
+
+int bxg_bits_count_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int32_t *which, const int32_t *start,
+                                const int32_t *count, int64_t n, int32_t *out, int strict, int loc) {
+    BXG_TRY(ensure_init());
+    if (nsets <= 0 || nsets > BATCH_MAX_PAIRS) return set_error(BXG_ERR_ARG, "nsets must be in [1, %d]", BATCH_MAX_PAIRS);
+    if (n <= 0) return BXG_OK;
+    static CountDesc h_desc[BATCH_MAX_PAIRS];
+    for (int k = 0; k < nsets; k++) {
+        bxg_bits *b = sets[k];
+        if (!b) return set_error(BXG_ERR_ARG, "null bitset handle %d", k);
+        BXG_TRY(build_rank(b));
+        h_desc[k] = CountDesc{b->words, b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0, b->size};
+    }
+    Context &c = ctx();
+    void *d_desc;
+    BXG_TRY(scratch(3, sizeof(CountDesc) * (size_t)nsets, &d_desc));
+    BXG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(CountDesc) * (size_t)nsets, cudaMemcpyHostToDevice, c.stream));
+    const void *dw, *ds, *dc;
+    BXG_TRY(stage_in(0, which, (size_t)n * 4, loc, &dw));
+    BXG_TRY(stage_in(1, start, (size_t)n * 4, loc, &ds));
+    BXG_TRY(stage_in(5, count, (size_t)n * 4, loc, &dc));
+    int32_t *dout = out;
+    if (loc == BXG_HOST) {
+        void *t;
+        BXG_TRY(scratch(2, (size_t)n * 4, &t));
+        dout = (int32_t *)t;
+    }
+    BXG_LAUNCH(k_count_ranges_multi, grid_for(cdiv(n, 256), 8), 256, 0, (const CountDesc *)d_desc, nsets,
+               (const int32_t *)dw, (const int32_t *)ds, (const int32_t *)dc, n, dout);
+    if (loc == BXG_HOST) {
+        BXG_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, c.stream));
+        BXG_CUDA(cudaStreamSynchronize(c.stream));
     }
     return BXG_OK;
 }

@@ -111,6 +111,11 @@ int bxg_bits_binop_batch(int op, bxg_bits_t *const *a, const bxg_bits_t *const *
 int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *count, int64_t n,
                           int32_t *out, int strict, int loc);
 int bxg_bits_count_all(const bxg_bits_t *b, int64_t *count);                  /* count_range(0, size)          */
+/* Genome-wide form of `bitsets[chrom].count_range(start, end-start)` per BED line (scripts/bed_intersect.py:46-53):
+ * query i addresses sets[which[i]]; which outside [0,nsets) (chromosome without a bitset) or an out-of-range span
+ * yields 0.  One launch. */
+int bxg_bits_count_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int32_t *which, const int32_t *start,
+                                const int32_t *count, int64_t n, int32_t *out, int strict, int loc);
 
 /* binBitsFindSet / binBitsFindClear (binBits.c:180-228) ; bitFindSet/Clear with an end bound (bits.c:143-190).
  * first position p in [start, end) whose bit == val, else `end`; end <= size. */
@@ -191,6 +196,11 @@ int bxg_scores_free(bxg_scores_t *s);
 int bxg_aggregate(const bxg_scores_t *s, const bxg_bits_t *mask /* or NULL */,
                   const int32_t *ws, const int32_t *we, int64_t nw, int loc,
                   float *sum, float *avg, int32_t *count, float *mn, float *mx);
+/* Genome-wide form: window w reads track tracks[wtrack[w]] (the script's `scores_by_chrom[chrom]`, :115; a track id
+ * outside [0,ntracks) behaves like a chromosome without scores).  masks may be NULL, or hold NULL entries.  One launch. */
+int bxg_aggregate_multi(const bxg_scores_t *const *tracks, const bxg_bits_t *const *masks, int32_t ntracks,
+                        const int32_t *wtrack, const int32_t *ws, const int32_t *we, int64_t nw, int loc,
+                        float *sum, float *avg, int32_t *count, float *mn, float *mx);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Multi-GPU: one process per GPU; chromosomes are sharded with no data-path exchange; only the final per-chromosome

@@ -545,6 +545,38 @@ def test_bitset_genome_batch_vs_oracle(bx, orc):
         bx.bitset.iand_many([A[0]], [A[1]])
 
 
+def test_count_ranges_many_vs_oracle(bx, orc):
+    """bed_intersect's per-line `bitsets[chrom].count_range(...)` as one launch over several bit sets (strict mode incl.
+    inverted sets), with lines naming a chromosome that has no bitset."""
+    rng = np.random.default_rng(601)
+    sets, osets = [], []
+    for k in range(5):
+        size = int(rng.integers(1000, 400_000)); gran = int(rng.choice([10, 1024]))
+        b, o = bx.bitset.BinnedBitSet(size, gran), orc.OracleBinnedBitSet(size, gran)
+        s = rng.integers(0, size, 80); c = rng.integers(0, np.minimum(size - s, 500) + 1)
+        b.set_ranges(s, c); o.set_ranges(s, c)
+        if k % 2:
+            b.invert(); o.invert()
+        sets.append(b); osets.append(o)
+    n = 20000
+    which = rng.integers(-1, 6, n).astype(np.int32)
+    start = np.zeros(n, np.int32); count = np.zeros(n, np.int32)
+    for k in range(5):
+        sel = which == k
+        m = int(sel.sum())
+        start[sel] = rng.integers(0, sets[k].size, m)
+        count[sel] = rng.integers(0, np.minimum(sets[k].size - start[sel], 3000) + 1)
+    for strict in (True, False):
+        got = bx.bitset.count_ranges_many(sets, which, start, count, strict=strict)
+        for k in range(5):
+            sel = which == k
+            exp = osets[k].count_ranges(start[sel], count[sel]) if strict else sets[k].count_ranges(start[sel], count[sel], strict=False)
+            assert np.array_equal(got[sel], exp), (k, strict)
+        assert np.all(got[(which < 0) | (which > 4)] == 0)
+    with pytest.raises(IndexError):
+        bx.bitset.count_ranges_many(sets, [0], [sets[0].size - 1], [5])
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_flat_bitset_vs_oracle(bx, orc, seed):
     rng = np.random.default_rng(500 + seed)
@@ -662,6 +694,43 @@ def test_aggregate_survey_probe(bx):
     assert f(res, 0) == ["0.2", "0.1", "0.3"]
     assert f(res, 1) == ["2.3967452e+06", "0.001", "1.6777216e+07"]
     assert f(res, 2) == ["nan", "nan", "nan"]
+
+
+def test_aggregate_genome_vs_oracle(bx, orc):
+    """One launch over several chromosomes (track ids per window) == per-chromosome oracle, incl. a masked track,
+    an unmasked one, and windows naming a chromosome that has no scores."""
+    rng = np.random.default_rng(56)
+    tracks, masks, dense, mwords = [], [], [], []
+    for t in range(4):
+        n = int(rng.integers(10_000, 200_000)); origin = int(rng.integers(0, 5000))
+        v = synth.aggregate_scores(rng, n)
+        tracks.append(bx.aggregate.ScoreTrack(v, origin))
+        d = np.full(origin + n, np.nan, np.float32); d[origin:] = v
+        dense.append(d)
+        if t % 2 == 0:
+            m = bx.bitset.BinnedBitSet(origin + n + 100)
+            ms = rng.integers(origin, origin + n, 300); mc = rng.integers(1, 40, 300)
+            m.set_ranges(ms, mc)
+            masks.append(m); mwords.append(m.to_words())
+        else:
+            masks.append(None); mwords.append(None)
+    nw = 50_000
+    wt = rng.integers(-1, 5, nw).astype(np.int32)            # -1 and 4 name tracks that do not exist
+    ws = np.empty(nw, np.int32); we = np.empty(nw, np.int32)
+    for t in range(-1, 5):
+        sel = wt == t
+        hi = len(dense[t]) if 0 <= t < 4 else 1000
+        ws[sel] = rng.integers(-20, hi + 20, int(sel.sum()))
+        we[sel] = ws[sel] + rng.integers(0, 70, int(sel.sum()))
+    res = bx.aggregate.aggregate_genome(tracks, wt, ws, we, masks)
+    for t in range(4):
+        sel = np.nonzero(wt == t)[0]
+        o = orc.aggregate(dense[t], ws[sel], we[sel], mwords[t])
+        for k in ("sum", "avg", "min", "max"):
+            assert np.array_equal(res[k][sel].view(np.uint32), o[k].view(np.uint32)), (t, k)
+        assert np.array_equal(res["count"][sel], o["count"])
+    none = (wt < 0) | (wt > 3)
+    assert np.all(res["count"][none] == 0) and np.all(np.isnan(res["avg"][none]))
 
 
 def test_aggregate_random_vs_oracle(bx, orc):
