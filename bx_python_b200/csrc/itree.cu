@@ -225,6 +225,18 @@ struct Ld4 {
 struct Ld1 {
     __device__ __forceinline__ int32_t operator()(const int32_t *p) const { return __ldg(p); }
 };
+// prefetch the aligned 16-item (64-byte) group of up to two arrays into L1; no registers are tied up
+struct PrefetchGroups {
+    const int32_t *a, *b;
+    __device__ __forceinline__ void operator()(uint32_t g) const {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a + g));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a + g + 8));
+        if (b) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(b + g));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(b + g + 8));
+        }
+    }
+};
 
 __device__ __forceinline__ const SmemIndex stage_index(const IndexView &ix, unsigned char *smem_raw) {
     // layout: [mbarrier 8 B][pad 8 B][spS nsplit_pad x 4][spPM nsplit_pad x 4][toff (ntrees+1) x 8]
@@ -271,7 +283,8 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
                 bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(),
-                                 hi, lo);          // hi: start < qe ends here; lo: running max end > qs starts here
+                                 hi, lo,           // hi: start < qe ends here; lo: running max end > qs starts here
+                                 PrefetchGroups{ix.E, nullptr});
                 if (lo > hi) lo = hi;
                 bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
                                [&](uint32_t, unsigned mask) { c += __popc(mask); });
@@ -284,7 +297,8 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             const uint32_t lo = (uint32_t)lo_[q], hi = (uint32_t)hi_[q];
             int32_t *dst = hits + off[q];
             bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
-                           [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.I, k0, mask, dst, Ld4()); });
+                           [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.I, k0, mask, dst, Ld4()); },
+                           PrefetchGroups{ix.I, nullptr});
         }
     }
     if (!FILL && total) {
@@ -349,7 +363,8 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
             const int32_t t = qtree ? __ldg(qtree + q) : 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
-                bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo);
+                bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo,
+                                 PrefetchGroups{ix.E, ix.I});
                 if (lo > hi) lo = hi;
                 int32_t cc = 0;
                 bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t, unsigned mask) { cc += __popc(mask); });

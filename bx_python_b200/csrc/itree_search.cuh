@@ -119,10 +119,16 @@ BXG_HD uint32_t finish_binary(const int32_t *A, Win w, int32_t key, const LD &ld
 
 // Both searches of one query, in lock-step.  SP: shared-memory splitter arrays; KS/KP: sampled levels (K*[0] = S / PM,
 // padded to 16-entry groups with INT32_MAX); ld4(ptr) loads one 16-byte group quarter.
-template <typename SP, typename LD4, typename LD>
+struct NoPrefetch {
+    BXG_HD void operator()(uint32_t) const {}
+};
+
+// pf(g) is called with the 16-aligned positions the two searches are about to resolve (final round): the walk that
+// follows reads E (and the fill reads I) at exactly those groups, so the kernels prefetch them one DRAM latency early.
+template <typename SP, typename LD4, typename LD, typename PF = NoPrefetch>
 BXG_HD void dual_search(const int32_t *const *KS, const int32_t *const *KP, int nk, const SP &spS, const SP &spPM,
                         int shift, uint32_t seg_lo, uint32_t seg_hi, int32_t qe, int32_t qs, const LD4 &ld4,
-                        const LD &ld, uint32_t &hi_out, uint32_t &lo_out) {
+                        const LD &ld, uint32_t &hi_out, uint32_t &lo_out, const PF &pf = PF()) {
     if (seg_lo >= seg_hi) {
         hi_out = lo_out = seg_hi;
         return;
@@ -143,6 +149,10 @@ BXG_HD void dual_search(const int32_t *const *KS, const int32_t *const *KP, int 
         const int ss = 4 * j;
         const Round rs = round_prepare(ws, ss), rp = round_prepare(wp, ss);
         int4 s0{}, s1{}, s2{}, s3{}, p0{}, p1{}, p2{}, p3{};
+        if (j == 0) {
+            if (rp.active) pf(rp.g);
+            if (rs.active && (!rp.active || rs.g != rp.g)) pf(rs.g);
+        }
         if (rs.active) {
             const int4 *p = reinterpret_cast<const int4 *>(KS[j] + rs.g);
             s0 = ld4(p); s1 = ld4(p + 1); s2 = ld4(p + 2); s3 = ld4(p + 3);
@@ -161,9 +171,9 @@ BXG_HD void dual_search(const int32_t *const *KS, const int32_t *const *KP, int 
 // Walk [lo,hi) in aligned 16-item groups of E (padded with INT32_MIN): f(k0, mask) gets the bit mask of hits
 // (bit i <=> item k0+i has E > qs and lies in [lo,hi)).  After an empty group, 32-aligned all-miss blocks are skipped
 // through the max hierarchy M[l] (M[l][b] = max E over 32^(l+1) items) -- O(32 log n) per hit in the worst case.
-template <typename LD4, typename LD, typename F>
+template <typename LD4, typename LD, typename F, typename PF = NoPrefetch>
 BXG_HD void walk_hits(const int32_t *E, const int32_t *const *M, int nlev, uint32_t lo, uint32_t hi, int32_t qs,
-                      const LD4 &ld4, const LD &ld, F &&f) {
+                      const LD4 &ld4, const LD &ld, F &&f, const PF &pf = PF()) {
     if (lo >= hi) return;
     uint32_t k = lo & ~15u;
     bool prev_empty = false;
@@ -181,6 +191,7 @@ BXG_HD void walk_hits(const int32_t *E, const int32_t *const *M, int nlev, uint3
             k = (idx + 1u) << (5 * (lvl + 1));
             continue;
         }
+        pf(k);          // the emitter will read the same group of I: start that fetch together with the E loads
         const int4 *p = reinterpret_cast<const int4 *>(E + k);
         const int4 v0 = ld4(p), v1 = ld4(p + 1), v2 = ld4(p + 2), v3 = ld4(p + 3);
         unsigned mask = 0xffffu & ~group_mask<true>(v0, v1, v2, v3, qs);      // E > qs
