@@ -225,7 +225,10 @@ struct Ld4 {
 struct Ld1 {
     __device__ __forceinline__ int32_t operator()(const int32_t *p) const { return __ldg(p); }
 };
-// prefetch the aligned 16-item (64-byte) group of up to two arrays into L1; no registers are tied up
+// prefetch the aligned 16-item (64-byte) group of up to two arrays into L1; no registers are tied up.
+// Measured (profiles/r01k): prefetching E at the final search round and I alongside the E loads of the fill made the
+// kernels SLOWER (count 0.977 -> 0.991 ms, fill 0.50 -> 0.60 ms: I lines of hit-less groups are fetched for nothing and
+// the extra requests queue in front of demand loads), so the kernels pass bxs::NoPrefetch; kept for experiments.
 struct PrefetchGroups {
     const int32_t *a, *b;
     __device__ __forceinline__ void operator()(uint32_t g) const {
@@ -283,8 +286,7 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
                 bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(),
-                                 hi, lo,           // hi: start < qe ends here; lo: running max end > qs starts here
-                                 PrefetchGroups{ix.E, nullptr});
+                                 hi, lo);          // hi: start < qe ends here; lo: running max end > qs starts here
                 if (lo > hi) lo = hi;
                 bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
                                [&](uint32_t, unsigned mask) { c += __popc(mask); });
@@ -297,8 +299,7 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             const uint32_t lo = (uint32_t)lo_[q], hi = (uint32_t)hi_[q];
             int32_t *dst = hits + off[q];
             bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
-                           [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.I, k0, mask, dst, Ld4()); },
-                           PrefetchGroups{ix.I, nullptr});
+                           [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.I, k0, mask, dst, Ld4()); });
         }
     }
     if (!FILL && total) {
@@ -363,8 +364,7 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
             const int32_t t = qtree ? __ldg(qtree + q) : 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
-                bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo,
-                                 PrefetchGroups{ix.E, ix.I});
+                bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo);
                 if (lo > hi) lo = hi;
                 int32_t cc = 0;
                 bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t, unsigned mask) { cc += __popc(mask); });
