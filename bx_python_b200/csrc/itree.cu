@@ -759,6 +759,18 @@ static int find_three_pass(bxg_itree_t *t, const int32_t *qtree, const int32_t *
 // Results land in pinned host buffers owned by the index, valid until its next find / free.
 static int ensure_pipeline(bxg_itree *t);
 
+// queries per pipeline chunk of the host path (env BXB200_CHUNK_QUERIES, default 1 Mi): large enough that a chunk's
+// kernel and copies dwarf the per-chunk launch/event overhead, small enough that the first D2H starts early
+static int64_t chunk_queries() {
+    static int64_t v = 0;
+    if (!v) {
+        const char *e = getenv("BXB200_CHUNK_QUERIES");
+        v = e ? atoll(e) : (1 << 20);
+        if (v < 1024) v = 1024;
+    }
+    return v;
+}
+
 static int find_host_three_pass(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
                                 const int64_t **offsets, const int32_t **hits, int64_t *total) {
     Context &c = ctx();
@@ -784,7 +796,7 @@ static int find_host_three_pass(bxg_itree_t *t, const int32_t *qtree, const int3
     BXG_TRY(scratch(1, (size_t)nq * 4, &p1));
     BXG_TRY(scratch(2, (size_t)nq * 4, &p2));
     int32_t *dqt = (int32_t *)p0, *dqs = (int32_t *)p1, *dqe = (int32_t *)p2;
-    int nchunks = (int)std::min<int64_t>(bxg_itree::MAX_CHUNKS, std::max<int64_t>(1, nq / (1 << 20)));
+    int nchunks = (int)std::min<int64_t>(bxg_itree::MAX_CHUNKS, std::max<int64_t>(1, nq / chunk_queries()));
     const int64_t per = cdiv(nq, nchunks);
     nchunks = (int)cdiv(nq, per);
     size_t tmp_bytes = 0;
@@ -983,7 +995,7 @@ static int find_host_fused(bxg_itree_t *t, const int32_t *qtree, const int32_t *
     BXG_TRY(scratch(1, (size_t)nq * 4, &p1));
     BXG_TRY(scratch(2, (size_t)nq * 4, &p2));
     int32_t *dqt = (int32_t *)p0, *dqs = (int32_t *)p1, *dqe = (int32_t *)p2;
-    int nchunks = (int)std::min<int64_t>(bxg_itree::MAX_CHUNKS, std::max<int64_t>(1, nq / (1 << 20)));
+    int nchunks = (int)std::min<int64_t>(bxg_itree::MAX_CHUNKS, std::max<int64_t>(1, nq / chunk_queries()));
     const int64_t per = cdiv(cdiv(nq, nchunks), FUSED_THREADS) * FUSED_THREADS;     // whole tiles per chunk
     nchunks = (int)cdiv(nq, per);
     const int64_t tiles_per = per / FUSED_THREADS;
