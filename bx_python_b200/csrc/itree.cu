@@ -33,7 +33,11 @@ constexpr int MAX_KLEV = 5;            // 16-ary sampled search levels: strides 
 struct IndexView {
     const int32_t *S, *E, *I, *PM;
     const int32_t *KS[MAX_KLEV], *KP[MAX_KLEV];   // KS[j][i] = S[i << 4j], KP likewise for PM; padded with INT32_MAX
-    int32_t nk;                                   // levels in use (K*[0] are S / PM themselves)
+    int32_t nk;                                   // levels in use; K*[0] point into SP (see below)
+    // level-0 arrays of the find kernels, interleaved per 16-item group so that the lines one query touches are adjacent:
+    //   SP = [S x16 | PM x16] ...   (KS[0] = SP, KP[0] = SP + 16),   EI = [E x16 | I x16] ...   (WE = EI, WI = EI + 16)
+    const int32_t *WE, *WI;
+    int32_t mul;                                  // group pitch of those arrays in 16-int units (2)
     const int32_t *M[MAX_LEVELS];
     const int64_t *toff;
     const int32_t *spS, *spPM;   // contiguous: spS[nsplit_pad] then spPM[nsplit_pad]
@@ -55,6 +59,7 @@ struct bxg_itree {
     int32_t *KS[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases S
     int32_t *KP[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases PM
     int nk = 1;
+    int32_t *SP = nullptr, *EI = nullptr;         // interleaved level-0 arrays (find kernels only)
     int32_t *es_end = nullptr, *es_k = nullptr;   // per-tree (end, in-order position) ordering for before(); lazy
     // query-side buffers (grow-only)
     int32_t *d_cnt = nullptr, *d_lo = nullptr, *d_hi = nullptr;
@@ -82,6 +87,9 @@ struct bxg_itree {
         for (int l = 0; l < MAX_LEVELS; l++) v.M[l] = M[l];
         for (int j = 0; j < MAX_KLEV; j++) { v.KS[j] = KS[j]; v.KP[j] = KP[j]; }
         v.nk = nk;
+        v.KS[0] = SP; v.KP[0] = SP ? SP + 16 : nullptr;
+        v.WE = EI; v.WI = EI ? EI + 16 : nullptr;
+        v.mul = 2;
         v.toff = toff; v.spS = split; v.spPM = split + nsplit_pad;
         v.n = (uint32_t)n; v.ntrees = ntrees; v.nlev = nlev; v.nsplit = nsplit; v.nsplit_pad = nsplit_pad; v.shift = shift;
         return v;
@@ -164,6 +172,16 @@ __global__ void k_sample_level(const int32_t *__restrict__ A, int64_t n, int ss,
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nout_pad; i += stride)
         out[i] = (i < nout && (i << ss) < n) ? A[i << ss] : INT32_MAX;
+}
+// out = [a x16 | b x16] per 16-item group (npad is a multiple of 16)
+__global__ void k_interleave(const int32_t *__restrict__ a, const int32_t *__restrict__ b, int64_t npad,
+                             int32_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < npad; k += stride) {
+        const int64_t o = (k & ~15ll) * 2 + (k & 15);
+        out[o] = a[k];
+        out[o + 16] = b[k];
+    }
 }
 __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -286,10 +304,11 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
                 bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(),
-                                 hi, lo);          // hi: start < qe ends here; lo: running max end > qs starts here
+                                 hi, lo,           // hi: start < qe ends here; lo: running max end > qs starts here
+                                 bxs::NoPrefetch(), ix.mul);
                 if (lo > hi) lo = hi;
-                bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
-                               [&](uint32_t, unsigned mask) { c += __popc(mask); });
+                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                               [&](uint32_t, unsigned mask) { c += __popc(mask); }, bxs::NoPrefetch(), ix.mul);
             }
             cnt[q] = c;
             lo_[q] = (int32_t)lo;
@@ -298,8 +317,9 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
         } else {
             const uint32_t lo = (uint32_t)lo_[q], hi = (uint32_t)hi_[q];
             int32_t *dst = hits + off[q];
-            bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
-                           [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.I, k0, mask, dst, Ld4()); });
+            bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                           [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.WI, k0, mask, dst, Ld4(), ix.mul); },
+                           bxs::NoPrefetch(), ix.mul);
         }
     }
     if (!FILL && total) {
@@ -364,10 +384,12 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
             const int32_t t = qtree ? __ldg(qtree + q) : 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
-                bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo);
+                bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo,
+                                 bxs::NoPrefetch(), ix.mul);
                 if (lo > hi) lo = hi;
                 int32_t cc = 0;
-                bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t, unsigned mask) { cc += __popc(mask); });
+                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t, unsigned mask) { cc += __popc(mask); },
+                               bxs::NoPrefetch(), ix.mul);
                 c = cc;
             }
         }
@@ -407,8 +429,9 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
             off[q] = base + excl;
             if (fits && c > 0) {
                 int32_t *dst = hits + base + excl;
-                bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
-                               [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.I, k0, mask, dst, Ld4()); });
+                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                               [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.WI, k0, mask, dst, Ld4(), ix.mul); },
+                               bxs::NoPrefetch(), ix.mul);
             }
         }
         if (threadIdx.x == 0) {
@@ -434,6 +457,9 @@ static void free_index(bxg_itree *t) {
     cudaFree(t->es_end);
     cudaFree(t->es_k);
     t->es_end = t->es_k = nullptr;
+    cudaFree(t->SP);
+    cudaFree(t->EI);
+    t->SP = t->EI = nullptr;
     t->S = t->E = t->I = t->PM = nullptr;
     t->toff = nullptr;
     t->split = nullptr;
@@ -671,6 +697,10 @@ int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, c
     // 16-ary sampled levels between the shared-memory splitters (stride 2^shift) and the arrays themselves
     t->KS[0] = t->S;
     t->KP[0] = t->PM;
+    BUILD_CUDA(cudaMalloc(&t->SP, (size_t)npad * 8));
+    BUILD_CUDA(cudaMalloc(&t->EI, (size_t)npad * 8));
+    BXG_LAUNCH(k_interleave, grid_for(cdiv(npad, 256), 8), 256, 0, t->S, t->PM, npad, t->SP);
+    BXG_LAUNCH(k_interleave, grid_for(cdiv(npad, 256), 8), 256, 0, t->E, t->I, npad, t->EI);
     t->nk = std::max(1, (t->shift + 3) / 4);
     for (int j = 1; j < t->nk; j++) {
         const int ss = 4 * j;

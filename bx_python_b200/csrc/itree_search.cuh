@@ -108,11 +108,19 @@ BXG_HD void round_apply(Win &w, const Round &r, int ss, unsigned mask) {
 
 // Plain binary search on level 0: the safety net when a window does not fit one aligned group (cannot happen for
 // the aligned windows the splitter phase produces) and the finisher used by the host-only callers.
+// `mul` is the level-0 group pitch in 16-int units: 1 for a plain array, 2 when two arrays are interleaved group by
+// group ([S x16 | PM x16] ..., [E x16 | I x16] ...) so that the lines the two searches / the walk and the emitter touch
+// are adjacent in HBM.
+BXG_HD const int32_t *group_ptr(const int32_t *A, uint32_t g, int mul) { return A + (size_t)g * (size_t)mul; }
+BXG_HD const int32_t *elem_ptr(const int32_t *A, uint32_t m, int mul) {
+    return A + (size_t)(m & ~15u) * (size_t)mul + (m & 15u);
+}
+
 template <bool LESS_EQ, typename LD>
-BXG_HD uint32_t finish_binary(const int32_t *A, Win w, int32_t key, const LD &ld) {
+BXG_HD uint32_t finish_binary(const int32_t *A, Win w, int32_t key, const LD &ld, int mul = 1) {
     while (w.lo < w.hi) {
         uint32_t m = (w.lo + w.hi) >> 1;
-        if (before<LESS_EQ>(ld(A + m), key)) w.lo = m + 1; else w.hi = m;
+        if (before<LESS_EQ>(ld(elem_ptr(A, m, mul)), key)) w.lo = m + 1; else w.hi = m;
     }
     return w.lo;
 }
@@ -128,7 +136,7 @@ struct NoPrefetch {
 template <typename SP, typename LD4, typename LD, typename PF = NoPrefetch>
 BXG_HD void dual_search(const int32_t *const *KS, const int32_t *const *KP, int nk, const SP &spS, const SP &spPM,
                         int shift, uint32_t seg_lo, uint32_t seg_hi, int32_t qe, int32_t qs, const LD4 &ld4,
-                        const LD &ld, uint32_t &hi_out, uint32_t &lo_out, const PF &pf = PF()) {
+                        const LD &ld, uint32_t &hi_out, uint32_t &lo_out, const PF &pf = PF(), int mul0 = 1) {
     if (seg_lo >= seg_hi) {
         hi_out = lo_out = seg_hi;
         return;
@@ -154,18 +162,18 @@ BXG_HD void dual_search(const int32_t *const *KS, const int32_t *const *KP, int 
             if (rs.active && (!rp.active || rs.g != rp.g)) pf(rs.g);
         }
         if (rs.active) {
-            const int4 *p = reinterpret_cast<const int4 *>(KS[j] + rs.g);
+            const int4 *p = reinterpret_cast<const int4 *>(j ? KS[j] + rs.g : group_ptr(KS[0], rs.g, mul0));
             s0 = ld4(p); s1 = ld4(p + 1); s2 = ld4(p + 2); s3 = ld4(p + 3);
         }
         if (rp.active) {
-            const int4 *p = reinterpret_cast<const int4 *>(KP[j] + rp.g);
+            const int4 *p = reinterpret_cast<const int4 *>(j ? KP[j] + rp.g : group_ptr(KP[0], rp.g, mul0));
             p0 = ld4(p); p1 = ld4(p + 1); p2 = ld4(p + 2); p3 = ld4(p + 3);
         }
         if (rs.active) round_apply(ws, rs, ss, group_mask<false>(s0, s1, s2, s3, qe));
         if (rp.active) round_apply(wp, rp, ss, group_mask<true>(p0, p1, p2, p3, qs));
     }
-    hi_out = finish_binary<false>(KS[0], ws, qe, ld);   // no-ops when the rounds converged (lo == hi)
-    lo_out = finish_binary<true>(KP[0], wp, qs, ld);
+    hi_out = finish_binary<false>(KS[0], ws, qe, ld, mul0);   // no-ops when the rounds converged (lo == hi)
+    lo_out = finish_binary<true>(KP[0], wp, qs, ld, mul0);
 }
 
 // Walk [lo,hi) in aligned 16-item groups of E (padded with INT32_MIN): f(k0, mask) gets the bit mask of hits
@@ -173,7 +181,7 @@ BXG_HD void dual_search(const int32_t *const *KS, const int32_t *const *KP, int 
 // through the max hierarchy M[l] (M[l][b] = max E over 32^(l+1) items) -- O(32 log n) per hit in the worst case.
 template <typename LD4, typename LD, typename F, typename PF = NoPrefetch>
 BXG_HD void walk_hits(const int32_t *E, const int32_t *const *M, int nlev, uint32_t lo, uint32_t hi, int32_t qs,
-                      const LD4 &ld4, const LD &ld, F &&f, const PF &pf = PF()) {
+                      const LD4 &ld4, const LD &ld, F &&f, const PF &pf = PF(), int mul = 1) {
     if (lo >= hi) return;
     uint32_t k = lo & ~15u;
     bool prev_empty = false;
@@ -192,7 +200,7 @@ BXG_HD void walk_hits(const int32_t *E, const int32_t *const *M, int nlev, uint3
             continue;
         }
         pf(k);          // the emitter will read the same group of I: start that fetch together with the E loads
-        const int4 *p = reinterpret_cast<const int4 *>(E + k);
+        const int4 *p = reinterpret_cast<const int4 *>(group_ptr(E, k, mul));
         const int4 v0 = ld4(p), v1 = ld4(p + 1), v2 = ld4(p + 2), v3 = ld4(p + 3);
         unsigned mask = 0xffffu & ~group_mask<true>(v0, v1, v2, v3, qs);      // E > qs
         if (k < lo) mask &= ~0u << (lo - k);
@@ -207,8 +215,8 @@ BXG_HD void walk_hits(const int32_t *E, const int32_t *const *M, int nlev, uint3
 // loads issued back to back (one 64-byte line), THEN the selected ids are stored -- a load per hit interleaved with
 // the stores would serialise on every store (the compiler must assume hits[] may alias I[]).
 template <typename LD4>
-BXG_HD int32_t *emit_group(const int32_t *I, uint32_t k0, unsigned mask, int32_t *dst, const LD4 &ld4) {
-    const int4 *p = reinterpret_cast<const int4 *>(I + k0);
+BXG_HD int32_t *emit_group(const int32_t *I, uint32_t k0, unsigned mask, int32_t *dst, const LD4 &ld4, int mul = 1) {
+    const int4 *p = reinterpret_cast<const int4 *>(group_ptr(I, k0, mul));
     const int4 a = ld4(p), b = ld4(p + 1), c = ld4(p + 2), d = ld4(p + 3);
     if (mask & 0x0001u) *dst++ = a.x;
     if (mask & 0x0002u) *dst++ = a.y;

@@ -86,13 +86,27 @@ int main(int argc, char **argv) {
         }
         std::vector<const int32_t *> Mp;
         for (auto &m : M) Mp.push_back(m.data());
+        // interleaved level-0 layouts, as the kernels use them: [S x16 | PM x16] and [E x16 | I x16] per 16-item group
+        std::vector<int32_t> SPi(2 * npad), EIi(2 * npad);
+        for (long g = 0; g < npad; g += 16)
+            for (int i = 0; i < 16; i++) {
+                SPi[2 * g + i] = S[g + i];
+                SPi[2 * g + 16 + i] = PM[g + i];
+                EIi[2 * g + i] = E[g + i];
+                EIi[2 * g + 16 + i] = (int32_t)(g + i) * 7 + 1;      // "item id" of position g+i
+            }
+        const int mul = (trial % 3 == 0) ? 1 : 2;
+        if (mul == 2) {
+            KS[0] = SPi.data();
+            KP[0] = SPi.data() + 16;
+        }
         for (int q = 0; q < 150; q++) {
             const int t = (int)(rnd() % (uint32_t)ntrees);
             const int32_t qs = (int)(rnd() % (uint32_t)(range + 40)) - 70;
             const int32_t qe = qs + (int)(rnd() % 60) - 5;
             uint32_t hi, lo;
             bxs::dual_search(KS.data(), KP.data(), nk, spS.data(), spPM.data(), shift, toff[t], toff[t + 1], qe, qs, ld4,
-                             ld, hi, lo);
+                             ld, hi, lo, bxs::NoPrefetch(), mul);
             const uint32_t ehi = (uint32_t)(std::lower_bound(S.begin() + toff[t], S.begin() + toff[t + 1], qe) - S.begin());
             const uint32_t elo = (uint32_t)(std::upper_bound(PM.begin() + toff[t], PM.begin() + toff[t + 1], qs) - PM.begin());
             if (hi != ehi || lo != elo) {
@@ -102,15 +116,26 @@ int main(int argc, char **argv) {
             }
             if (lo > hi) lo = hi;
             std::vector<uint32_t> got, want;
-            bxs::walk_hits(E.data(), Mp.data(), (int)Mp.size(), lo, hi, qs, ld4, ld, [&](uint32_t k0, unsigned mask) {
+            std::vector<int32_t> ids(hi - lo + 32), want_ids;
+            int32_t *dst = ids.data();
+            const int32_t *Eb = mul == 2 ? EIi.data() : E.data();
+            bxs::walk_hits(Eb, Mp.data(), (int)Mp.size(), lo, hi, qs, ld4, ld, [&](uint32_t k0, unsigned mask) {
+                if (mul == 2) dst = bxs::emit_group(EIi.data() + 16, k0, mask, dst, ld4, 2);
                 while (mask) {
                     int b = bxs::ffs32(mask) - 1;
                     mask &= mask - 1;
                     got.push_back(k0 + b);
                 }
-            });
+            }, bxs::NoPrefetch(), mul);
             for (uint32_t k = lo; k < hi; k++)
-                if (E[k] > qs) want.push_back(k);
+                if (E[k] > qs) {
+                    want.push_back(k);
+                    want_ids.push_back((int32_t)k * 7 + 1);
+                }
+            if (mul == 2 && std::vector<int32_t>(ids.data(), dst) != want_ids) {
+                printf("EMIT MISMATCH trial %d lo=%u hi=%u\n", trial, lo, hi);
+                return 1;
+            }
             if (got != want) {
                 printf("WALK MISMATCH trial %d n=%d lo=%u hi=%u qs=%d got=%zu want=%zu\n", trial, n, lo, hi, qs, got.size(),
                        want.size());
