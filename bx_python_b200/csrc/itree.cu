@@ -87,9 +87,14 @@ struct bxg_itree {
         for (int l = 0; l < MAX_LEVELS; l++) v.M[l] = M[l];
         for (int j = 0; j < MAX_KLEV; j++) { v.KS[j] = KS[j]; v.KP[j] = KP[j]; }
         v.nk = nk;
-        v.KS[0] = SP; v.KP[0] = SP ? SP + 16 : nullptr;
-        v.WE = EI; v.WI = EI ? EI + 16 : nullptr;
-        v.mul = 2;
+        // Interleaved level-0 arrays (SP/EI, mul = 2) were measured SLOWER than the plain ones on B200 (profiles/r01k:
+        // count 0.977 -> 1.046 ms, single-pass 1.62 -> 1.72 ms), so the plain arrays are used; build_interleaved()
+        // and the mul parameter stay for experiments.
+        if (SP && EI) {
+            v.KS[0] = SP; v.KP[0] = SP + 16; v.WE = EI; v.WI = EI + 16; v.mul = 2;
+        } else {
+            v.KS[0] = S; v.KP[0] = PM; v.WE = E; v.WI = I; v.mul = 1;
+        }
         v.toff = toff; v.spS = split; v.spPM = split + nsplit_pad;
         v.n = (uint32_t)n; v.ntrees = ntrees; v.nlev = nlev; v.nsplit = nsplit; v.nsplit_pad = nsplit_pad; v.shift = shift;
         return v;
@@ -697,10 +702,12 @@ int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, c
     // 16-ary sampled levels between the shared-memory splitters (stride 2^shift) and the arrays themselves
     t->KS[0] = t->S;
     t->KP[0] = t->PM;
-    BUILD_CUDA(cudaMalloc(&t->SP, (size_t)npad * 8));
-    BUILD_CUDA(cudaMalloc(&t->EI, (size_t)npad * 8));
-    BXG_LAUNCH(k_interleave, grid_for(cdiv(npad, 256), 8), 256, 0, t->S, t->PM, npad, t->SP);
-    BXG_LAUNCH(k_interleave, grid_for(cdiv(npad, 256), 8), 256, 0, t->E, t->I, npad, t->EI);
+    if (getenv("BXB200_INTERLEAVE")) {          // experiment switch, see IndexView::view()
+        BUILD_CUDA(cudaMalloc(&t->SP, (size_t)npad * 8));
+        BUILD_CUDA(cudaMalloc(&t->EI, (size_t)npad * 8));
+        BXG_LAUNCH(k_interleave, grid_for(cdiv(npad, 256), 8), 256, 0, t->S, t->PM, npad, t->SP);
+        BXG_LAUNCH(k_interleave, grid_for(cdiv(npad, 256), 8), 256, 0, t->E, t->I, npad, t->EI);
+    }
     t->nk = std::max(1, (t->shift + 3) / 4);
     for (int j = 1; j < t->nk; j++) {
         const int ss = 4 * j;
