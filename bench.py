@@ -462,6 +462,7 @@ def run_ours(args):
 
     # ---- bitset AND (configs[2]) -----------------------------------------------------------------------------------------
     extra["pcie"] = bench_pcie()
+    extra["scalar_api"] = bench_scalar_api(db)
     if not args.no_bitset:
         extra["bitset"] = bench_bitset(args, peak, peak_src)
         extra["bed_intersect"] = bench_bed_intersect(peak)
@@ -597,6 +598,31 @@ def bench_bitset(args, peak, peak_src):
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "bound": "hbm",
                 "l2_policy": "one pass streams 1.16 GB through 24 operand pairs (> 126 MB L2)"})
     return res
+
+
+def bench_scalar_api(db):
+    """Latency of the reference-shaped scalar calls (one kernel round trip each): the price of NOT batching."""
+    from bx_python_b200.bitset import BinnedBitSet
+    from bx_python_b200.intervals import IntervalTree
+    s, e = db[20]
+    t = IntervalTree()
+    t.insert_many(s, e)
+    t.find(1000, 2000)
+    n = 200
+    t0 = time.perf_counter()
+    for k in range(n):
+        t.find(100000 * k, 100000 * k + 1500)
+    find_us = (time.perf_counter() - t0) / n * 1e6
+    b = BinnedBitSet(int(synth.HG38_LENS[20]))
+    b.set_range(10, 1000)
+    b.count_range(0, 5000)
+    t0 = time.perf_counter()
+    for k in range(n):
+        b.count_range(1000 * k, 1500)
+    count_us = (time.perf_counter() - t0) / n * 1e6
+    return {"find_us_per_call": find_us, "count_range_us_per_call": count_us,
+            "note": "scalar IntervalTree.find / BinnedBitSet.count_range go through one kernel launch + copy each; "
+                    "the reference's Cython calls take ~1-4 us -- bulk callers must use the batched methods"}
 
 
 def bench_pcie():
