@@ -545,6 +545,24 @@ def test_bitset_genome_batch_vs_oracle(bx, orc):
         bx.bitset.iand_many([A[0]], [A[1]])
 
 
+def test_set_ranges_long_and_short_mixed(bx, orc):
+    """Chromosome-arm-long ranges (handed to the grid-wide fill) mixed with short ones, odd/even word alignments,
+    overlapping each other; scalar set_range of the whole bitmap."""
+    size = 60_000_000
+    rng = np.random.default_rng(602)
+    s = np.concatenate([[3, 100, 64 * 30001, 64 * 30001 + 1, 1_999_999], rng.integers(0, size - 3000, 500)])
+    c = np.concatenate([[40_000_000, 2_000_013, 64 * 20000, 64 * 20001 + 7, 30_000_001], rng.integers(0, 3000, 500)])
+    b, o = bx.bitset.BinnedBitSet(size), orc.OracleBinnedBitSet(size)
+    b.set_ranges(s, c); o.set_ranges(s, c)
+    assert np.array_equal(b.to_words(), o.words())
+    assert np.array_equal(b.bin_states(), o.states())
+    b2, o2 = bx.bitset.BinnedBitSet(size, 10), orc.OracleBinnedBitSet(size, 10)
+    b2.set_range(0, size); o2.set_range(0, size)
+    assert b2.count_range(0, size) == size == o2.count_range(0, size)
+    b2.invert()
+    assert b2.count_all() == 0 and b2.next_set(0) == size
+
+
 def test_count_ranges_many_vs_oracle(bx, orc):
     """bed_intersect's per-line `bitsets[chrom].count_range(...)` as one launch over several bit sets (strict mode incl.
     inverted sets), with lines naming a chromosome that has no bitset."""
