@@ -250,35 +250,20 @@ k_popcount(const ulonglong2 *__restrict__ a, int64_t nvec, unsigned long long *c
 // set_range x n  (binBits.c:98-128): one lane per range for the two edge words (64-bit atomicOr), the whole warp
 // sweeps each lane's interior words with coalesced stores of ~0.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int64_t LONG_WORDS = 1 << 14;          // interiors above 128 KB go to the grid-wide fill
-constexpr unsigned int LONG_QUEUE_CAP = 4096;
-
-// grid-wide fill of the queued long interiors with all-ones words (128-bit stores where aligned)
-__global__ void __launch_bounds__(256)
-k_fill_long(uint64_t *__restrict__ words, const int64_t *__restrict__ queue, const unsigned int *__restrict__ count) {
-    const unsigned int nq = min(*count, LONG_QUEUE_CAP);
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (unsigned int r = 0; r < nq; r++) {
-        const int64_t b = queue[2 * r], e = queue[2 * r + 1];
-        const int64_t b2 = (b + 1) & ~1ll, e2 = e & ~1ll;          // 16-byte aligned core
-        if (tid == 0 && b < b2 && b < e) words[b] = ~0ull;
-        if (tid == 1 && e2 < e && e2 >= b) words[e2] = ~0ull;
-        ulonglong2 *v = reinterpret_cast<ulonglong2 *>(words);
-        const ulonglong2 ones = make_ulonglong2(~0ull, ~0ull);
-        for (int64_t i = (b2 >> 1) + tid; i < (e2 >> 1); i += stride) st_stream(v + i, ones);
-    }
-}
+constexpr int64_t LONG_WORDS = 1 << 12;          // interiors above 32 KB are swept by the whole CTA instead of one warp
+constexpr int LONG_SLOTS = 64;                   // per-CTA queue of such interiors (per 256-range tile)
 
 __global__ void __launch_bounds__(256)
 k_set_ranges(uint64_t *__restrict__ words, uint8_t *__restrict__ state, int bin_size, int flat,
-             const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n,
-             int64_t *__restrict__ long_queue, unsigned int *__restrict__ long_count) {
+             const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n) {
+    __shared__ int64_t s_long[2 * LONG_SLOTS];
+    __shared__ unsigned int s_nlong;
     const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t base = warp0 * 32; base < n; base += nwarps * 32) {
-        int64_t i = base + lane;
+    // block-uniform tile loop (every warp of a CTA runs the same number of iterations: the tile ends with barriers)
+    for (int64_t tile = (int64_t)blockIdx.x * blockDim.x; tile < n; tile += (int64_t)gridDim.x * blockDim.x) {
+        if (threadIdx.x == 0) s_nlong = 0;
+        __syncthreads();
+        const int64_t i = tile + threadIdx.x;
         int64_t mb = 0, me = 0;
         if (i < n) {
             int32_t s = __ldg(start + i), c = __ldg(count + i);
@@ -301,35 +286,35 @@ k_set_ranges(uint64_t *__restrict__ words, uint8_t *__restrict__ state, int bin_
                 me = w1;
             }
         }
-        // very long interiors (a whole chromosome arm) are not worth one warp's time: queue them for k_fill_long, where
-        // the whole grid sweeps each of them at streaming rate
-        if (me - mb > LONG_WORDS && long_queue != nullptr) {
-            unsigned int slot = atomicAdd(long_count, 1u);
-            if (slot < LONG_QUEUE_CAP) {
-                long_queue[2 * slot] = mb;
-                long_queue[2 * slot + 1] = me;
-                me = mb;                                   // handed over
+        // a very long interior (a chromosome arm) is not worth one warp's time: hand it to the whole CTA
+        if (me - mb > LONG_WORDS) {
+            unsigned int slot = atomicAdd(&s_nlong, 1u);
+            if (slot < LONG_SLOTS) {
+                s_long[2 * slot] = mb;
+                s_long[2 * slot + 1] = me;
+                me = mb;
             }
         }
-        // interiors: four ranges at a time, eight lanes each (typical interiors are 10-30 words: a full warp per range
-        // would leave most lanes idle and serialise 32 sweeps)
+        // ordinary interiors (10-30 words): the warp sweeps them one after the other with coalesced stores of ~0
         unsigned has = __ballot_sync(0xffffffffu, me > mb);
-        const int grp = lane >> 3, sub = lane & 7;
         while (has) {
-            const unsigned pick = __fns(has, 0, grp + 1);            // the (grp+1)-th pending range, or 0xffffffff
-            const int src = pick < 32u ? (int)pick : 0;
-            const int64_t b = __shfl_sync(0xffffffffu, mb, src), e = __shfl_sync(0xffffffffu, me, src);
-            if (pick < 32u)
-                for (int64_t w = b + sub; w < e; w += 8) words[w] = ~0ull;
-            // drop the (up to) four ranges just served
-            unsigned served = 0;
-#pragma unroll
-            for (int k = 1; k <= 4; k++) {
-                const unsigned p = __fns(has, 0, k);
-                if (p < 32u) served |= 1u << p;
-            }
-            has &= ~served;
+            int src = __ffs(has) - 1;
+            has &= has - 1;
+            int64_t b = __shfl_sync(0xffffffffu, mb, src), e = __shfl_sync(0xffffffffu, me, src);
+            for (int64_t w = b + lane; w < e; w += 32) words[w] = ~0ull;
         }
+        __syncthreads();
+        const unsigned int nl = min(s_nlong, (unsigned int)LONG_SLOTS);
+        for (unsigned int r = 0; r < nl; r++) {
+            const int64_t b = s_long[2 * r], e = s_long[2 * r + 1];
+            const int64_t b2 = (b + 1) & ~1ll, e2 = e & ~1ll;      // 16-byte aligned core, 128-bit streaming stores
+            if (threadIdx.x == 0 && b < b2) words[b] = ~0ull;
+            if (threadIdx.x == 1 && e2 < e) words[e2] = ~0ull;
+            ulonglong2 *v = reinterpret_cast<ulonglong2 *>(words);
+            const ulonglong2 ones = make_ulonglong2(~0ull, ~0ull);
+            for (int64_t k = (b2 >> 1) + threadIdx.x; k < (e2 >> 1); k += blockDim.x) st_stream(v + k, ones);
+        }
+        __syncthreads();
     }
 }
 
@@ -618,14 +603,8 @@ int bxg_bits_set_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *coun
     const void *ds, *dc;
     BXG_TRY(stage_in(0, start, (size_t)n * 4, loc, &ds));
     BXG_TRY(stage_in(1, count, (size_t)n * 4, loc, &dc));
-    void *q;
-    BXG_TRY(scratch(6, (size_t)LONG_QUEUE_CAP * 16 + 16, &q));
-    int64_t *d_queue = (int64_t *)q;
-    unsigned int *d_qcount = (unsigned int *)(d_queue + 2 * LONG_QUEUE_CAP);
-    BXG_CUDA(cudaMemsetAsync(d_qcount, 0, sizeof(unsigned int), ctx().stream));
     BXG_LAUNCH(k_set_ranges, grid_for(cdiv(n, 256), 8), 256, 0, b->words, b->state, b->bin_size, b->flat,
-               (const int32_t *)ds, (const int32_t *)dc, n, d_queue, d_qcount);
-    BXG_LAUNCH(k_fill_long, grid_for(1 << 20, 4), 256, 0, b->words, (const int64_t *)d_queue, (const unsigned int *)d_qcount);
+               (const int32_t *)ds, (const int32_t *)dc, n);
     invalidate(b);
     if (loc == BXG_HOST) BXG_CUDA(cudaStreamSynchronize(ctx().stream));   // caller may reuse its arrays on return
     return BXG_OK;
