@@ -310,7 +310,7 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
                 bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(),
                                  hi, lo,           // hi: start < qe ends here; lo: running max end > qs starts here
-                                 bxs::NoPrefetch(), ix.mul);
+                                 bxs::NoPrefetch(), ix.mul, /*coarse_lo=*/true);
                 if (lo > hi) lo = hi;
                 bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
                                [&](uint32_t, unsigned mask) { c += __popc(mask); }, bxs::NoPrefetch(), ix.mul);
@@ -390,7 +390,7 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
                 bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo,
-                                 bxs::NoPrefetch(), ix.mul);
+                                 bxs::NoPrefetch(), ix.mul, /*coarse_lo=*/true);
                 if (lo > hi) lo = hi;
                 int32_t cc = 0;
                 bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t, unsigned mask) { cc += __popc(mask); },

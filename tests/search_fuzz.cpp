@@ -105,11 +105,13 @@ int main(int argc, char **argv) {
             const int32_t qs = (int)(rnd() % (uint32_t)(range + 40)) - 70;
             const int32_t qe = qs + (int)(rnd() % 60) - 5;
             uint32_t hi, lo;
+            const bool coarse = (q % 2) == 1;      // coarse_lo: lo may be up to 15 items early, never late
             bxs::dual_search(KS.data(), KP.data(), nk, spS.data(), spPM.data(), shift, toff[t], toff[t + 1], qe, qs, ld4,
-                             ld, hi, lo, bxs::NoPrefetch(), mul);
+                             ld, hi, lo, bxs::NoPrefetch(), mul, coarse);
             const uint32_t ehi = (uint32_t)(std::lower_bound(S.begin() + toff[t], S.begin() + toff[t + 1], qe) - S.begin());
             const uint32_t elo = (uint32_t)(std::upper_bound(PM.begin() + toff[t], PM.begin() + toff[t + 1], qs) - PM.begin());
-            if (hi != ehi || lo != elo) {
+            const bool lo_ok = coarse ? (lo <= elo && lo + 16 > elo && lo >= toff[t]) : (lo == elo);
+            if (hi != ehi || !lo_ok) {
                 printf("SEARCH MISMATCH trial %d n=%d shift=%d nk=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u\n", trial, n,
                        shift, nk, toff[t], toff[t + 1], qs, qe, hi, ehi, lo, elo);
                 return 1;
