@@ -63,6 +63,7 @@ struct bxg_itree {
     int32_t *es_end = nullptr, *es_k = nullptr;   // per-tree (end, in-order position) ordering for before(); lazy
     // query-side buffers (grow-only)
     int32_t *d_cnt = nullptr, *d_lo = nullptr, *d_hi = nullptr;
+    unsigned long long *d_mask = nullptr;         // hit masks of the first four groups of every query (count -> fill)
     int64_t *d_off = nullptr;
     int32_t *d_hits = nullptr;
     int64_t q_cap = 0, hits_cap = 0;
@@ -289,42 +290,75 @@ __device__ __forceinline__ const SmemIndex stage_index(const IndexView &ix, unsi
     return s;
 }
 
+// The count pass stashes the hit masks of a query's first four 16-item groups (64 bits per query): the fill pass then
+// emits straight from the masks -- it reads the aligned group of I, but never E, qs or hi again.  Queries whose walk
+// needs more than four groups, or skipped through the max hierarchy, set WALK_AGAIN in lo_ and are re-walked by the fill.
+constexpr uint32_t WALK_AGAIN = 0x80000000u;
+
+struct MaskStash {
+    uint32_t base;            // lo & ~15
+    unsigned long long m = 0;
+    bool overflow = false;
+    int32_t c = 0;
+    __device__ __forceinline__ void operator()(uint32_t k0, unsigned mask) {
+        c += __popc(mask);
+        const uint32_t j = (k0 - base) >> 4;
+        if (j < 4u) m |= (unsigned long long)mask << (16u * j); else overflow = true;
+    }
+};
+
 template <bool FILL>
 __global__ void __launch_bounds__(FIND_THREADS, FIND_MIN_CTAS)
 k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, const int32_t *__restrict__ qs_, const int32_t *__restrict__ qe_,
        int64_t nq, int32_t *__restrict__ cnt, int32_t *__restrict__ lo_, int32_t *__restrict__ hi_,
-       const int64_t *__restrict__ off, int32_t *__restrict__ hits, unsigned long long *total) {
+       unsigned long long *__restrict__ mask_, const int64_t *__restrict__ off, int32_t *__restrict__ hits,
+       unsigned long long *total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemIndex sm;
     if (!FILL) sm = stage_index(ix, smem_raw);
     unsigned long long local = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
-        const int32_t qs = __ldg(qs_ + q);
         if (!FILL) {
+            const int32_t qs = __ldg(qs_ + q);
             const int32_t qe = __ldg(qe_ + q);
             const int32_t t = qtree ? __ldg(qtree + q) : 0;
             uint32_t lo = 0, hi = 0;
-            int32_t c = 0;
+            MaskStash st;
+            st.base = 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
                 bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(),
                                  hi, lo,           // hi: start < qe ends here; lo: running max end > qs starts here
                                  bxs::NoPrefetch(), ix.mul, /*coarse_lo=*/true);
                 if (lo > hi) lo = hi;
-                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
-                               [&](uint32_t, unsigned mask) { c += __popc(mask); }, bxs::NoPrefetch(), ix.mul);
+                st.base = lo & ~15u;
+                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), st, bxs::NoPrefetch(), ix.mul);
             }
-            cnt[q] = c;
-            lo_[q] = (int32_t)lo;
+            cnt[q] = st.c;
+            lo_[q] = (int32_t)(lo | (st.overflow ? WALK_AGAIN : 0u));
             hi_[q] = (int32_t)hi;
-            local += (unsigned long long)c;
+            mask_[q] = st.m;
+            local += (unsigned long long)st.c;
         } else {
-            const uint32_t lo = (uint32_t)lo_[q], hi = (uint32_t)hi_[q];
+            const uint32_t lo_raw = (uint32_t)lo_[q];
             int32_t *dst = hits + off[q];
-            bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
-                           [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.WI, k0, mask, dst, Ld4(), ix.mul); },
-                           bxs::NoPrefetch(), ix.mul);
+            if (!(lo_raw & WALK_AGAIN)) {
+                unsigned long long m = mask_[q];
+                uint32_t k0 = lo_raw & ~15u;
+                while (m) {                                    // at most four groups
+                    const unsigned mk = (unsigned)(m & 0xffffull);
+                    if (mk) dst = bxs::emit_group(ix.WI, k0, mk, dst, Ld4(), ix.mul);
+                    m >>= 16;
+                    k0 += 16;
+                }
+            } else {
+                const uint32_t lo = lo_raw & ~WALK_AGAIN, hi = (uint32_t)hi_[q];
+                const int32_t qs = __ldg(qs_ + q);
+                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                               [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.WI, k0, mask, dst, Ld4(), ix.mul); },
+                               bxs::NoPrefetch(), ix.mul);
+            }
         }
     }
     if (!FILL && total) {
@@ -383,6 +417,8 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
         uint32_t lo = 0, hi = 0;
         int32_t qs = 0;
         long long c = 0;
+        MaskStash st;
+        st.base = 0;
         if (q < nq) {
             qs = __ldg(qs_ + q);
             const int32_t qe = __ldg(qe_ + q);
@@ -392,10 +428,9 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
                 bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo,
                                  bxs::NoPrefetch(), ix.mul, /*coarse_lo=*/true);
                 if (lo > hi) lo = hi;
-                int32_t cc = 0;
-                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t, unsigned mask) { cc += __popc(mask); },
-                               bxs::NoPrefetch(), ix.mul);
-                c = cc;
+                st.base = lo & ~15u;
+                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), st, bxs::NoPrefetch(), ix.mul);
+                c = st.c;
             }
         }
         long long excl, tile_total;
@@ -434,9 +469,20 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
             off[q] = base + excl;
             if (fits && c > 0) {
                 int32_t *dst = hits + base + excl;
-                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
-                               [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.WI, k0, mask, dst, Ld4(), ix.mul); },
-                               bxs::NoPrefetch(), ix.mul);
+                if (!st.overflow) {                            // emit from the masks kept in registers: E is not read again
+                    unsigned long long m = st.m;
+                    uint32_t k0 = st.base;
+                    while (m) {
+                        const unsigned mk = (unsigned)(m & 0xffffull);
+                        if (mk) dst = bxs::emit_group(ix.WI, k0, mk, dst, Ld4(), ix.mul);
+                        m >>= 16;
+                        k0 += 16;
+                    }
+                } else {
+                    bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                                   [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.WI, k0, mask, dst, Ld4(), ix.mul); },
+                                   bxs::NoPrefetch(), ix.mul);
+                }
             }
         }
         if (threadIdx.x == 0) {
@@ -479,14 +525,16 @@ static size_t find_smem_bytes(const bxg_itree *t) {
 static int ensure_query_buffers(bxg_itree *t, int64_t nq) {
     if (nq + 1 <= t->q_cap) return BXG_OK;
     BXG_CUDA(cudaStreamSynchronize(ctx().stream));
-    cudaFree(t->d_cnt); cudaFree(t->d_lo); cudaFree(t->d_hi); cudaFree(t->d_off);
+    cudaFree(t->d_cnt); cudaFree(t->d_lo); cudaFree(t->d_hi); cudaFree(t->d_off); cudaFree(t->d_mask);
     t->d_cnt = t->d_lo = t->d_hi = nullptr;
     t->d_off = nullptr;
+    t->d_mask = nullptr;
     int64_t cap = nq + 1 + nq / 8;
     BXG_CUDA(cudaMalloc(&t->d_cnt, (size_t)cap * 4));
     BXG_CUDA(cudaMalloc(&t->d_lo, (size_t)cap * 4));
     BXG_CUDA(cudaMalloc(&t->d_hi, (size_t)cap * 4));
     BXG_CUDA(cudaMalloc(&t->d_off, (size_t)cap * 8));
+    BXG_CUDA(cudaMalloc(&t->d_mask, (size_t)cap * 8));
     t->q_cap = cap;
     return BXG_OK;
 }
@@ -505,7 +553,8 @@ static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
     BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<false>, FIND_THREADS, smem));
     int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
     BXG_LAUNCH((k_find<false>), grid, FIND_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, nq,
-               t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, (const int64_t *)nullptr, (int32_t *)nullptr, d_total);
+               t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, t->d_mask + q0, (const int64_t *)nullptr, (int32_t *)nullptr,
+               d_total);
     return BXG_OK;
 }
 
@@ -515,8 +564,8 @@ static int launch_fill(bxg_itree *t, const int32_t *dqs, int64_t nq, int64_t q0 
     BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<true>, FIND_THREADS, 0));
     int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
     BXG_LAUNCH((k_find<true>), grid, FIND_THREADS, 0, t->view(), (const int32_t *)nullptr, dqs + q0,
-               (const int32_t *)nullptr, nq, t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, (const int64_t *)(t->d_off + q0),
-               t->d_hits, (unsigned long long *)nullptr);
+               (const int32_t *)nullptr, nq, t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, t->d_mask + q0,
+               (const int64_t *)(t->d_off + q0), t->d_hits, (unsigned long long *)nullptr);
     return BXG_OK;
 }
 
@@ -556,6 +605,7 @@ int bxg_itree_free(bxg_itree_t *t) {
     cudaStreamSynchronize(ctx().stream);
     free_index(t);
     cudaFree(t->d_cnt); cudaFree(t->d_lo); cudaFree(t->d_hi); cudaFree(t->d_off); cudaFree(t->d_hits);
+    cudaFree(t->d_mask);
     if (t->s_in) {
         cudaStreamSynchronize(t->s_in);
         cudaStreamSynchronize(t->s_out);
