@@ -439,13 +439,14 @@ def run_ours(args):
     n_items = len(s)
     alg = {
         # per launch, bytes that must move (DESIGN.md "algorithmic bytes"):
-        # count pass: read (chrom,start,end) 12 B/query, write (count,lo,hi) 12 B/query, read S,PM,E once 12 B/item
-        "k_find<false>": 24 * nq + 12 * n_items,
-        # fill pass: read start,lo,hi,offset 20 B/query, read E once 4 B/item, read I + write hit 8 B/hit
-        "k_find<true>": 20 * nq + 4 * n_items + 8 * hits_total,
-        # single-pass kernel: read (chrom,start,end) 12 B/query, write offset 8 B/query, S,PM,E once 12 B/item,
+        # count pass: read (chrom,start,end) 12 B/query, write (count,lo,hi,mask) 20 B/query, read S,E once 8 B/item
+        # (the PM array itself is no longer read: coarse lo)
+        "k_find<false>": 32 * nq + 8 * n_items,
+        # fill pass: read lo,mask,offset 20 B/query, read I + write hit 8 B/hit (E is not read again: mask stash)
+        "k_find<true>": 20 * nq + 8 * hits_total,
+        # single-pass kernel: read (chrom,start,end) 12 B/query, write offset 8 B/query, S,E once 8 B/item,
         # read I + write hit 8 B/hit
-        "k_find_fused": 20 * nq + 12 * n_items + 8 * hits_total,
+        "k_find_fused": 20 * nq + 8 * n_items + 8 * hits_total,
     }
     kern = {}
     for name, (n_l, tot_ms) in prof.items():
