@@ -91,11 +91,7 @@ struct bxg_itree {
         // Interleaved level-0 arrays (SP/EI, mul = 2) were measured SLOWER than the plain ones on B200 (profiles/r01k:
         // count 0.977 -> 1.046 ms, single-pass 1.62 -> 1.72 ms), so the plain arrays are used; build_interleaved()
         // and the mul parameter stay for experiments.
-        if (SP && EI) {
-            v.KS[0] = SP; v.KP[0] = SP + 16; v.WE = EI; v.WI = EI + 16; v.mul = 2;
-        } else {
-            v.KS[0] = S; v.KP[0] = PM; v.WE = E; v.WI = I; v.mul = 1;
-        }
+        v.KS[0] = S; v.KP[0] = PM; v.WE = E; v.WI = I; v.mul = 1;
         v.toff = toff; v.spS = split; v.spPM = split + nsplit_pad;
         v.n = (uint32_t)n; v.ntrees = ntrees; v.nlev = nlev; v.nsplit = nsplit; v.nsplit_pad = nsplit_pad; v.shift = shift;
         return v;
@@ -290,17 +286,19 @@ __device__ __forceinline__ const SmemIndex stage_index(const IndexView &ix, unsi
     return s;
 }
 
-// The count pass stashes the hit masks of a query's first four 16-item groups (64 bits per query): the fill pass then
-// emits straight from the masks -- it reads the aligned group of I, but never E, qs or hi again.  Queries whose walk
-// needs more than four groups, or skipped through the max hierarchy, set WALK_AGAIN in lo_ and are re-walked by the fill.
+// The count pass stashes the hit masks of four consecutive 16-item groups, starting at the first group that has a hit
+// (64 bits per query), and records that group's position in lo_: the fill pass then emits straight from the masks -- it
+// reads the aligned groups of I, but never E, qs or hi again.  Queries whose hits span more than four groups set
+// WALK_AGAIN in lo_ and are re-walked by the fill from that position (everything in front of the first hit has E <= qs).
 constexpr uint32_t WALK_AGAIN = 0x80000000u;
 
 struct MaskStash {
-    uint32_t base;            // lo & ~15
+    uint32_t base = 0;        // 16-aligned position of the first group that has a hit (valid once c > 0)
     unsigned long long m = 0;
     bool overflow = false;
     int32_t c = 0;
     __device__ __forceinline__ void operator()(uint32_t k0, unsigned mask) {
+        if (c == 0) base = k0;
         c += __popc(mask);
         const uint32_t j = (k0 - base) >> 4;
         if (j < 4u) m |= (unsigned long long)mask << (16u * j); else overflow = true;
@@ -325,18 +323,14 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             const int32_t t = qtree ? __ldg(qtree + q) : 0;
             uint32_t lo = 0, hi = 0;
             MaskStash st;
-            st.base = 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
-                bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(),
-                                 hi, lo,           // hi: start < qe ends here; lo: running max end > qs starts here
-                                 bxs::NoPrefetch(), ix.mul, /*coarse_lo=*/true);
-                if (lo > hi) lo = hi;
-                st.base = lo & ~15u;
-                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), st, bxs::NoPrefetch(), ix.mul);
+                // hi: candidates (start < qe) end here; lo: coarse start of the walk (running max end > qs from here on)
+                bxs::search_walk(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev,
+                                 Ld4(), Ld1(), hi, lo, st);
             }
             cnt[q] = st.c;
-            lo_[q] = (int32_t)(lo | (st.overflow ? WALK_AGAIN : 0u));
+            lo_[q] = (int32_t)((st.c ? st.base : lo) | (st.overflow ? WALK_AGAIN : 0u));
             hi_[q] = (int32_t)hi;
             mask_[q] = st.m;
             local += (unsigned long long)st.c;
@@ -345,7 +339,7 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             int32_t *dst = hits + off[q];
             if (!(lo_raw & WALK_AGAIN)) {
                 unsigned long long m = mask_[q];
-                uint32_t k0 = lo_raw & ~15u;
+                uint32_t k0 = lo_raw;                          // 16-aligned position of the first group with a hit
                 while (m) {                                    // at most four groups
                     const unsigned mk = (unsigned)(m & 0xffffull);
                     if (mk) dst = bxs::emit_group(ix.WI, k0, mk, dst, Ld4(), ix.mul);
@@ -418,18 +412,14 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
         int32_t qs = 0;
         long long c = 0;
         MaskStash st;
-        st.base = 0;
         if (q < nq) {
             qs = __ldg(qs_ + q);
             const int32_t qe = __ldg(qe_ + q);
             const int32_t t = qtree ? __ldg(qtree + q) : 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
-                bxs::dual_search(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo,
-                                 bxs::NoPrefetch(), ix.mul, /*coarse_lo=*/true);
-                if (lo > hi) lo = hi;
-                st.base = lo & ~15u;
-                bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), st, bxs::NoPrefetch(), ix.mul);
+                bxs::search_walk(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev,
+                                 Ld4(), Ld1(), hi, lo, st);
                 c = st.c;
             }
         }
@@ -479,7 +469,7 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
                         k0 += 16;
                     }
                 } else {
-                    bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                    bxs::walk_hits(ix.WE, ix.M, ix.nlev, st.base, hi, qs, Ld4(), Ld1(),
                                    [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.WI, k0, mask, dst, Ld4(), ix.mul); },
                                    bxs::NoPrefetch(), ix.mul);
                 }
@@ -752,12 +742,7 @@ int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, c
     // 16-ary sampled levels between the shared-memory splitters (stride 2^shift) and the arrays themselves
     t->KS[0] = t->S;
     t->KP[0] = t->PM;
-    if (getenv("BXB200_INTERLEAVE")) {          // experiment switch, see IndexView::view()
-        BUILD_CUDA(cudaMalloc(&t->SP, (size_t)npad * 8));
-        BUILD_CUDA(cudaMalloc(&t->EI, (size_t)npad * 8));
-        BXG_LAUNCH(k_interleave, grid_for(cdiv(npad, 256), 8), 256, 0, t->S, t->PM, npad, t->SP);
-        BXG_LAUNCH(k_interleave, grid_for(cdiv(npad, 256), 8), 256, 0, t->E, t->I, npad, t->EI);
-    }
+
     t->nk = std::max(1, (t->shift + 3) / 4);
     for (int j = 1; j < t->nk; j++) {
         const int ss = 4 * j;

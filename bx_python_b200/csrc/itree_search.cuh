@@ -188,10 +188,11 @@ BXG_HD void dual_search(const int32_t *const *KS, const int32_t *const *KP, int 
 // through the max hierarchy M[l] (M[l][b] = max E over 32^(l+1) items) -- O(32 log n) per hit in the worst case.
 template <typename LD4, typename LD, typename F, typename PF = NoPrefetch>
 BXG_HD void walk_hits(const int32_t *E, const int32_t *const *M, int nlev, uint32_t lo, uint32_t hi, int32_t qs,
-                      const LD4 &ld4, const LD &ld, F &&f, const PF &pf = PF(), int mul = 1) {
+                      const LD4 &ld4, const LD &ld, F &&f, const PF &pf = PF(), int mul = 1,
+                      uint32_t k_start = 0xffffffffu, bool prev_empty0 = false) {
     if (lo >= hi) return;
-    uint32_t k = lo & ~15u;
-    bool prev_empty = false;
+    uint32_t k = k_start == 0xffffffffu ? (lo & ~15u) : k_start;   // resume point of a walk whose first group is done
+    bool prev_empty = prev_empty0;
     while (k < hi) {
         if (prev_empty && (k & 31u) == 0 && k + 32u <= hi && ld(M[0] + (k >> 5)) <= qs) {
             uint32_t idx = k >> 5;
@@ -216,6 +217,74 @@ BXG_HD void walk_hits(const int32_t *E, const int32_t *const *M, int nlev, uint3
         if (mask) f(k, mask);
         k += 16;
     }
+}
+
+// Search + walk of one query with the LAST search round and the FIRST walk group overlapped.
+//
+// After the sampled levels (j >= 1) the PM search has its coarse `lo` (see dual_search: coarse_lo), i.e. the walk's
+// first E group is already known while the S search still needs its final round on S itself.  Both loads (two DRAM
+// lines) are issued together, so the dependent chain of a typical query is
+//     splitters (smem) -> level 2 -> level 1 -> { S group || E group } -> (second E group if the span needs it)
+// instead of ... -> S group -> E group -> E group.  Plain (non-interleaved) level-0 arrays only.
+template <typename SP, typename LD4, typename LD, typename F>
+BXG_HD void search_walk(const int32_t *const *KS, const int32_t *const *KP, int nk, const SP &spS, const SP &spPM,
+                        int shift, uint32_t seg_lo, uint32_t seg_hi, int32_t qe, int32_t qs, const int32_t *E,
+                        const int32_t *const *M, int nlev, const LD4 &ld4, const LD &ld, uint32_t &hi_out,
+                        uint32_t &lo_out, F &&f) {
+    hi_out = lo_out = seg_hi;
+    if (seg_lo >= seg_hi) return;
+    const uint32_t k0 = (seg_lo + (1u << shift) - 1) >> shift, k1 = ((seg_hi - 1) >> shift) + 1;
+    uint32_t a_s = k0, a_p = k0;
+    if (k0 < k1) {
+        uint32_t step = 1;
+        while (step * 2 <= k1 - k0) step *= 2;
+        for (; step > 0; step >>= 1) {
+            a_s = lift_step<false>(spS, a_s, step, k1, qe);
+            a_p = lift_step<true>(spPM, a_p, step, k1, qs);
+        }
+    }
+    Win ws = splitter_window(a_s, k0, k1, shift, seg_lo, seg_hi);
+    Win wp = splitter_window(a_p, k0, k1, shift, seg_lo, seg_hi);
+    for (int j = nk - 1; j >= 1; j--) {
+        const int ss = 4 * j;
+        const Round rs = round_prepare(ws, ss), rp = round_prepare(wp, ss);
+        int4 s0{}, s1{}, s2{}, s3{}, p0{}, p1{}, p2{}, p3{};
+        if (rs.active) {
+            const int4 *p = reinterpret_cast<const int4 *>(KS[j] + rs.g);
+            s0 = ld4(p); s1 = ld4(p + 1); s2 = ld4(p + 2); s3 = ld4(p + 3);
+        }
+        if (rp.active) {
+            const int4 *p = reinterpret_cast<const int4 *>(KP[j] + rp.g);
+            p0 = ld4(p); p1 = ld4(p + 1); p2 = ld4(p + 2); p3 = ld4(p + 3);
+        }
+        if (rs.active) round_apply(ws, rs, ss, group_mask<false>(s0, s1, s2, s3, qe));
+        if (rp.active) round_apply(wp, rp, ss, group_mask<true>(p0, p1, p2, p3, qs));
+    }
+    // final S round and first E group together
+    const uint32_t lo_c = wp.lo;                       // coarse lo: <= the true lo, possibly > the true hi
+    const uint32_t g0 = lo_c & ~15u;
+    const Round rs = round_prepare(ws, 0);
+    int4 s0{}, s1{}, s2{}, s3{}, e0{}, e1{}, e2{}, e3{};
+    if (rs.active) {
+        const int4 *p = reinterpret_cast<const int4 *>(KS[0] + rs.g);
+        s0 = ld4(p); s1 = ld4(p + 1); s2 = ld4(p + 2); s3 = ld4(p + 3);
+    }
+    const bool spec = lo_c < seg_hi;
+    if (spec) {
+        const int4 *p = reinterpret_cast<const int4 *>(E + g0);
+        e0 = ld4(p); e1 = ld4(p + 1); e2 = ld4(p + 2); e3 = ld4(p + 3);
+    }
+    if (rs.active) round_apply(ws, rs, 0, group_mask<false>(s0, s1, s2, s3, qe));
+    const uint32_t hi = finish_binary<false>(KS[0], ws, qe, ld);
+    const uint32_t lo = lo_c < hi ? lo_c : hi;
+    hi_out = hi;
+    lo_out = lo;
+    if (lo >= hi) return;                              // (then lo == lo_c and g0 == lo & ~15)
+    unsigned mask = 0xffffu & ~group_mask<true>(e0, e1, e2, e3, qs);
+    if (g0 < lo) mask &= ~0u << (lo - g0);
+    if (g0 + 16u > hi) mask &= (1u << (hi - g0)) - 1u;
+    if (mask) f(g0, mask);
+    if (g0 + 16u < hi) walk_hits(E, M, nlev, lo, hi, qs, ld4, ld, f, NoPrefetch(), 1, g0 + 16u, mask == 0);
 }
 
 // Write the item ids of the hits of one 16-item group: the whole aligned group of I is fetched with four 16-byte

@@ -138,6 +138,23 @@ int main(int argc, char **argv) {
                 printf("EMIT MISMATCH trial %d lo=%u hi=%u\n", trial, lo, hi);
                 return 1;
             }
+            if (mul == 1) {           // the overlapped search+walk the count kernels use (plain level-0 arrays)
+                std::vector<uint32_t> got2;
+                uint32_t hi2, lo2;
+                bxs::search_walk(KS.data(), KP.data(), nk, spS.data(), spPM.data(), shift, toff[t], toff[t + 1], qe, qs,
+                                 E.data(), Mp.data(), (int)Mp.size(), ld4, ld, hi2, lo2, [&](uint32_t k0, unsigned mask) {
+                                     while (mask) {
+                                         int b = bxs::ffs32(mask) - 1;
+                                         mask &= mask - 1;
+                                         got2.push_back(k0 + b);
+                                     }
+                                 });
+                if (hi2 != ehi || lo2 > std::min(elo, ehi) || got2 != want) {
+                    printf("SEARCH_WALK MISMATCH trial %d n=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u got=%zu want=%zu\n", trial,
+                           n, toff[t], toff[t + 1], qs, qe, hi2, ehi, lo2, elo, got2.size(), want.size());
+                    return 1;
+                }
+            }
             if (got != want) {
                 printf("WALK MISMATCH trial %d n=%d lo=%u hi=%u qs=%d got=%zu want=%zu\n", trial, n, lo, hi, qs, got.size(),
                        want.size());
