@@ -260,6 +260,7 @@ def run_ours(args):
     from bx_python_b200._lib import check, ptr
     from bx_python_b200.intervals import IntervalForest
     L = _lib.lib()
+    numa = _lib.bind_to_gpu_numa_node() if world > 1 else "single rank: not bound"
     comm = Comm("nccl")
     info = _lib.device_info()
     t_gen = time.perf_counter()
@@ -272,6 +273,7 @@ def run_ours(args):
     qt, qs, qe = qt[perm], qs[perm], qe[perm]
     nq = len(qs)
     if rank == 0:
+        log(f"numa: {numa}")
         log(f"device {info['name']} x{world}; rank0 owns chroms {mine}: {len(s)} intervals, {nq} queries "
             f"(gen {time.perf_counter() - t_gen:.1f}s)")
 

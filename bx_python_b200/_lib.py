@@ -24,6 +24,7 @@ SIGNATURES = {
     "bxg_init": [cint],
     "bxg_device_count": [C.POINTER(cint)],
     "bxg_device_info": [C.c_char_p, cint, C.POINTER(cint), pi64, C.POINTER(cint), C.POINTER(cint)],
+    "bxg_device_pci_bus_id": [C.c_char_p, cint],
     "bxg_last_error": [],
     "bxg_version": [],
     "bxg_sync": [],
@@ -189,6 +190,30 @@ def device_info() -> dict:
     sm, mem, maj, mnr = cint(), i64(), cint(), cint()
     check(lib().bxg_device_info(name, 256, C.byref(sm), C.byref(mem), C.byref(maj), C.byref(mnr)))
     return {"name": name.value.decode(), "sm_count": sm.value, "total_mem": mem.value, "cc": (maj.value, mnr.value)}
+
+
+def bind_to_gpu_numa_node() -> str:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers allocated afterwards
+    (first touch) and the copy threads are local to the GPU's PCIe root.  Matters when several ranks share a two-socket
+    host.  Returns a short description; never raises (a box without sysfs NUMA info is left alone)."""
+    try:
+        buf = C.create_string_buffer(64)
+        check(lib().bxg_device_pci_bus_id(buf, 64))
+        bus = buf.value.decode().lower()
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return f"{bus}: no NUMA affinity reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"{bus}: NUMA node {node} has no usable CPU"
+        os.sched_setaffinity(0, cpus)
+        return f"{bus}: bound to NUMA node {node} ({len(cpus)} CPUs)"
+    except (OSError, ValueError, RuntimeError) as e:
+        return f"not bound ({e})"
 
 
 class Timer:

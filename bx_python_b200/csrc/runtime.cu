@@ -149,6 +149,13 @@ int bxg_device_info(char *name, int name_cap, int *sm_count, int64_t *total_mem,
     return BXG_OK;
 }
 
+int bxg_device_pci_bus_id(char *out, int cap) {
+    BXG_TRY(ensure_init());
+    if (!out || cap < 16) return set_error(BXG_ERR_ARG, "buffer too small");
+    BXG_CUDA(cudaDeviceGetPCIBusId(out, cap, g_ctx.device));
+    return BXG_OK;
+}
+
 int bxg_sync(void) {
     BXG_TRY(ensure_init());
     BXG_CUDA(cudaStreamSynchronize(g_ctx.stream));

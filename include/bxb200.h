@@ -42,6 +42,7 @@ extern "C" {
 int         bxg_init(int device);                 /* bind this thread/process to `device`, create the stream       */
 int         bxg_device_count(int *n);
 int         bxg_device_info(char *name, int name_cap, int *sm_count, int64_t *total_mem, int *cc_major, int *cc_minor);
+int         bxg_device_pci_bus_id(char *out, int cap);   /* "0000:1b:00.0": lets the host pin itself to the GPU's NUMA node */
 const char *bxg_last_error(void);                 /* thread-local message of the last failing call                 */
 const char *bxg_version(void);
 int         bxg_sync(void);                       /* cudaStreamSynchronize(library stream)                          */
