@@ -33,11 +33,10 @@ constexpr int MAX_KLEV = 5;            // 16-ary sampled search levels: strides 
 struct IndexView {
     const int32_t *S, *E, *I, *PM;
     const int32_t *KS[MAX_KLEV], *KP[MAX_KLEV];   // KS[j][i] = S[i << 4j], KP likewise for PM; padded with INT32_MAX
-    int32_t nk;                                   // levels in use; K*[0] point into SP (see below)
-    // level-0 arrays of the find kernels, interleaved per 16-item group so that the lines one query touches are adjacent:
-    //   SP = [S x16 | PM x16] ...   (KS[0] = SP, KP[0] = SP + 16),   EI = [E x16 | I x16] ...   (WE = EI, WI = EI + 16)
-    const int32_t *WE, *WI;
-    int32_t mul;                                  // group pitch of those arrays in 16-int units (2)
+    int32_t nk;                                   // levels in use (K*[0] are S / PM themselves)
+    const int32_t *WE, *WI;                       // arrays the walk / the emitter read in 16-item groups (E, I)
+    int32_t mul;                                  // their group pitch in 16-int units: 1 (plain arrays; an interleaved
+                                                  // [a x16 | b x16] layout, pitch 2, measured slower -- profiles/r01k)
     const int32_t *M[MAX_LEVELS];
     const int64_t *toff;
     const int32_t *spS, *spPM;   // contiguous: spS[nsplit_pad] then spPM[nsplit_pad]
@@ -59,7 +58,6 @@ struct bxg_itree {
     int32_t *KS[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases S
     int32_t *KP[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases PM
     int nk = 1;
-    int32_t *SP = nullptr, *EI = nullptr;         // interleaved level-0 arrays (find kernels only)
     int32_t *es_end = nullptr, *es_k = nullptr;   // per-tree (end, in-order position) ordering for before(); lazy
     // query-side buffers (grow-only)
     int32_t *d_cnt = nullptr, *d_lo = nullptr, *d_hi = nullptr;
@@ -88,9 +86,6 @@ struct bxg_itree {
         for (int l = 0; l < MAX_LEVELS; l++) v.M[l] = M[l];
         for (int j = 0; j < MAX_KLEV; j++) { v.KS[j] = KS[j]; v.KP[j] = KP[j]; }
         v.nk = nk;
-        // Interleaved level-0 arrays (SP/EI, mul = 2) were measured SLOWER than the plain ones on B200 (profiles/r01k:
-        // count 0.977 -> 1.046 ms, single-pass 1.62 -> 1.72 ms), so the plain arrays are used; build_interleaved()
-        // and the mul parameter stay for experiments.
         v.KS[0] = S; v.KP[0] = PM; v.WE = E; v.WI = I; v.mul = 1;
         v.toff = toff; v.spS = split; v.spPM = split + nsplit_pad;
         v.n = (uint32_t)n; v.ntrees = ntrees; v.nlev = nlev; v.nsplit = nsplit; v.nsplit_pad = nsplit_pad; v.shift = shift;
@@ -175,16 +170,6 @@ __global__ void k_sample_level(const int32_t *__restrict__ A, int64_t n, int ss,
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nout_pad; i += stride)
         out[i] = (i < nout && (i << ss) < n) ? A[i << ss] : INT32_MAX;
 }
-// out = [a x16 | b x16] per 16-item group (npad is a multiple of 16)
-__global__ void k_interleave(const int32_t *__restrict__ a, const int32_t *__restrict__ b, int64_t npad,
-                             int32_t *__restrict__ out) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < npad; k += stride) {
-        const int64_t o = (k & ~15ll) * 2 + (k & 15);
-        out[o] = a[k];
-        out[o + 16] = b[k];
-    }
-}
 __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
@@ -245,22 +230,6 @@ struct Ld4 {
 struct Ld1 {
     __device__ __forceinline__ int32_t operator()(const int32_t *p) const { return __ldg(p); }
 };
-// prefetch the aligned 16-item (64-byte) group of up to two arrays into L1; no registers are tied up.
-// Measured (profiles/r01k): prefetching E at the final search round and I alongside the E loads of the fill made the
-// kernels SLOWER (count 0.977 -> 0.991 ms, fill 0.50 -> 0.60 ms: I lines of hit-less groups are fetched for nothing and
-// the extra requests queue in front of demand loads), so the kernels pass bxs::NoPrefetch; kept for experiments.
-struct PrefetchGroups {
-    const int32_t *a, *b;
-    __device__ __forceinline__ void operator()(uint32_t g) const {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(a + g));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(a + g + 8));
-        if (b) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(b + g));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(b + g + 8));
-        }
-    }
-};
-
 __device__ __forceinline__ const SmemIndex stage_index(const IndexView &ix, unsigned char *smem_raw) {
     // layout: [mbarrier 8 B][pad 8 B][spS nsplit_pad x 4][spPM nsplit_pad x 4][toff (ntrees+1) x 8]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -498,9 +467,6 @@ static void free_index(bxg_itree *t) {
     cudaFree(t->es_end);
     cudaFree(t->es_k);
     t->es_end = t->es_k = nullptr;
-    cudaFree(t->SP);
-    cudaFree(t->EI);
-    t->SP = t->EI = nullptr;
     t->S = t->E = t->I = t->PM = nullptr;
     t->toff = nullptr;
     t->split = nullptr;
