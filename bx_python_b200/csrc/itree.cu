@@ -224,8 +224,16 @@ struct SmemIndex {
 
 // The search (dual_search) and walk (walk_hits) arithmetic lives in itree_search.cuh so that the CPU fuzz harness
 // (tests/search_fuzz.cpp) compiles exactly the code the kernels run.
+// One aligned 64-byte group per thread as two 256-bit loads (LDG.E.256, new with sm_100).  The searches are divergent --
+// every lane reads its own line -- and the kernel is bound by L1 data-pipe wavefronts, one per lane-sector whatever the
+// access width: 4 x LDG.128 cost 4 wavefronts per lane and group (each 32-byte sector visited twice), 2 x LDG.256 cost 2.
 struct Ld4 {
-    __device__ __forceinline__ int4 operator()(const int4 *p) const { return __ldg(p); }
+    __device__ __forceinline__ void operator()(const int4 *p, int4 &a, int4 &b, int4 &c, int4 &d) const {
+        asm("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+        asm("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(p + 2));
+    }
 };
 struct Ld1 {
     __device__ __forceinline__ int32_t operator()(const int32_t *p) const { return __ldg(p); }

@@ -126,7 +126,7 @@ BXG_HD uint32_t finish_binary(const int32_t *A, Win w, int32_t key, const LD &ld
 }
 
 // Both searches of one query, in lock-step.  SP: shared-memory splitter arrays; KS/KP: sampled levels (K*[0] = S / PM,
-// padded to 16-entry groups with INT32_MAX); ld4(ptr) loads one 16-byte group quarter.
+// padded to 16-entry groups with INT32_MAX); ld4(ptr, a, b, c, d) loads one aligned 64-byte group (16 entries).
 struct NoPrefetch {
     BXG_HD void operator()(uint32_t) const {}
 };
@@ -170,11 +170,11 @@ BXG_HD void dual_search(const int32_t *const *KS, const int32_t *const *KP, int 
         }
         if (rs.active) {
             const int4 *p = reinterpret_cast<const int4 *>(j ? KS[j] + rs.g : group_ptr(KS[0], rs.g, mul0));
-            s0 = ld4(p); s1 = ld4(p + 1); s2 = ld4(p + 2); s3 = ld4(p + 3);
+            ld4(p, s0, s1, s2, s3);
         }
         if (rp.active) {
             const int4 *p = reinterpret_cast<const int4 *>(j ? KP[j] + rp.g : group_ptr(KP[0], rp.g, mul0));
-            p0 = ld4(p); p1 = ld4(p + 1); p2 = ld4(p + 2); p3 = ld4(p + 3);
+            ld4(p, p0, p1, p2, p3);
         }
         if (rs.active) round_apply(ws, rs, ss, group_mask<false>(s0, s1, s2, s3, qe));
         if (rp.active) round_apply(wp, rp, ss, group_mask<true>(p0, p1, p2, p3, qs));
@@ -209,7 +209,8 @@ BXG_HD void walk_hits(const int32_t *E, const int32_t *const *M, int nlev, uint3
         }
         pf(k);          // the emitter will read the same group of I: start that fetch together with the E loads
         const int4 *p = reinterpret_cast<const int4 *>(group_ptr(E, k, mul));
-        const int4 v0 = ld4(p), v1 = ld4(p + 1), v2 = ld4(p + 2), v3 = ld4(p + 3);
+        int4 v0, v1, v2, v3;
+        ld4(p, v0, v1, v2, v3);
         unsigned mask = 0xffffu & ~group_mask<true>(v0, v1, v2, v3, qs);      // E > qs
         if (k < lo) mask &= ~0u << (lo - k);
         if (k + 16u > hi) mask &= (1u << (hi - k)) - 1u;
@@ -251,11 +252,11 @@ BXG_HD void search_walk(const int32_t *const *KS, const int32_t *const *KP, int 
         int4 s0{}, s1{}, s2{}, s3{}, p0{}, p1{}, p2{}, p3{};
         if (rs.active) {
             const int4 *p = reinterpret_cast<const int4 *>(KS[j] + rs.g);
-            s0 = ld4(p); s1 = ld4(p + 1); s2 = ld4(p + 2); s3 = ld4(p + 3);
+            ld4(p, s0, s1, s2, s3);
         }
         if (rp.active) {
             const int4 *p = reinterpret_cast<const int4 *>(KP[j] + rp.g);
-            p0 = ld4(p); p1 = ld4(p + 1); p2 = ld4(p + 2); p3 = ld4(p + 3);
+            ld4(p, p0, p1, p2, p3);
         }
         if (rs.active) round_apply(ws, rs, ss, group_mask<false>(s0, s1, s2, s3, qe));
         if (rp.active) round_apply(wp, rp, ss, group_mask<true>(p0, p1, p2, p3, qs));
@@ -267,12 +268,12 @@ BXG_HD void search_walk(const int32_t *const *KS, const int32_t *const *KP, int 
     int4 s0{}, s1{}, s2{}, s3{}, e0{}, e1{}, e2{}, e3{};
     if (rs.active) {
         const int4 *p = reinterpret_cast<const int4 *>(KS[0] + rs.g);
-        s0 = ld4(p); s1 = ld4(p + 1); s2 = ld4(p + 2); s3 = ld4(p + 3);
+        ld4(p, s0, s1, s2, s3);
     }
     const bool spec = lo_c < seg_hi;
     if (spec) {
         const int4 *p = reinterpret_cast<const int4 *>(E + g0);
-        e0 = ld4(p); e1 = ld4(p + 1); e2 = ld4(p + 2); e3 = ld4(p + 3);
+        ld4(p, e0, e1, e2, e3);
     }
     if (rs.active) round_apply(ws, rs, 0, group_mask<false>(s0, s1, s2, s3, qe));
     const uint32_t hi = finish_binary<false>(KS[0], ws, qe, ld);
@@ -293,7 +294,8 @@ BXG_HD void search_walk(const int32_t *const *KS, const int32_t *const *KP, int 
 template <typename LD4>
 BXG_HD int32_t *emit_group(const int32_t *I, uint32_t k0, unsigned mask, int32_t *dst, const LD4 &ld4, int mul = 1) {
     const int4 *p = reinterpret_cast<const int4 *>(group_ptr(I, k0, mul));
-    const int4 a = ld4(p), b = ld4(p + 1), c = ld4(p + 2), d = ld4(p + 3);
+    int4 a, b, c, d;
+    ld4(p, a, b, c, d);
     if (mask & 0x0001u) *dst++ = a.x;
     if (mask & 0x0002u) *dst++ = a.y;
     if (mask & 0x0004u) *dst++ = a.z;

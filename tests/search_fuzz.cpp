@@ -17,7 +17,7 @@ static uint32_t rnd() {
 
 int main(int argc, char **argv) {
     const int trials = argc > 1 ? atoi(argv[1]) : 1500;
-    auto ld4 = [](const int4 *p) { return *p; };
+    auto ld4 = [](const int4 *p, int4 &a, int4 &b, int4 &c, int4 &d) { a = p[0]; b = p[1]; c = p[2]; d = p[3]; };
     auto ld = [](const int32_t *p) { return *p; };
     long checks = 0;
     for (int trial = 0; trial < trials; trial++) {
