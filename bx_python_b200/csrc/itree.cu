@@ -293,11 +293,20 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
     if (!FILL) sm = stage_index(ix, smem_raw);
     unsigned long long local = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+    // Fill only: the inputs of the next grid-stride iteration are loaded at the top of the current one (0.350 -> 0.338 ms).
+    // The same pipelining of qs/qe in the count kernel, by registers or by prefetch.global.L1, measured no gain.
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t n_lo = 0;
+    unsigned long long n_m = 0;
+    int64_t n_off = 0;
+    if (FILL && q < nq) { n_lo = lo_[q]; n_m = mask_[q]; n_off = off[q]; }
+    for (; q < nq; q += stride) {
+        const int32_t c_a = n_lo;
+        const unsigned long long c_m = n_m;
+        const int64_t c_off = n_off;
+        if (FILL && q + stride < nq) { n_lo = lo_[q + stride]; n_m = mask_[q + stride]; n_off = off[q + stride]; }
         if (!FILL) {
-            const int32_t qs = __ldg(qs_ + q);
-            const int32_t qe = __ldg(qe_ + q);
-            const int32_t t = qtree ? __ldg(qtree + q) : 0;
+            const int32_t qs = __ldg(qs_ + q), qe = __ldg(qe_ + q), t = qtree ? __ldg(qtree + q) : 0;
             uint32_t lo = 0, hi = 0;
             MaskStash st;
             if (t >= 0 && t < ix.ntrees) {
@@ -312,10 +321,10 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             mask_[q] = st.m;
             local += (unsigned long long)st.c;
         } else {
-            const uint32_t lo_raw = (uint32_t)lo_[q];
-            int32_t *dst = hits + off[q];
+            const uint32_t lo_raw = (uint32_t)c_a;
+            int32_t *dst = hits + c_off;
             if (!(lo_raw & WALK_AGAIN)) {
-                unsigned long long m = mask_[q];
+                unsigned long long m = c_m;
                 uint32_t k0 = lo_raw;                          // 16-aligned position of the first group with a hit
                 while (m) {                                    // at most four groups
                     const unsigned mk = (unsigned)(m & 0xffffull);
@@ -337,6 +346,81 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
         if ((threadIdx.x & 31) == 0 && local) atomicAdd(total, local);
+    }
+}
+
+// ---- fill, staged: the hits of the 32 consecutive queries of one warp form ONE contiguous span of the output
+// (off[] is monotone), on average 32 x hits/query ints.  Each lane drops its hits into a per-warp shared-memory window
+// at (off[q] - off[first query of the warp]) and the warp then writes the window out with coalesced stores: the
+// direct fill's ~27 scattered 4-byte store instructions per warp (7 partial sectors each -- LG-throttle stalls and
+// L2 tag traffic) become ~27 shared stores plus span/32 full-line stores.  Warps whose span exceeds the window
+// (FILL_STAGE ints) write directly, as k_find<true> does.
+constexpr int FILL_STAGE = 512;
+constexpr int FILL_MIN_CTAS = 5;
+
+struct SharedSink {
+    uint32_t a;                                           // shared-window byte address
+    __device__ __forceinline__ void put(int32_t v) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+        a += 4;
+    }
+};
+
+template <typename SINK>
+__device__ __forceinline__ void fill_query(const IndexView &ix, uint32_t lo_raw, unsigned long long m, int64_t q,
+                                           const int32_t *__restrict__ qs_, const int32_t *__restrict__ hi_, SINK &out) {
+    if (!(lo_raw & WALK_AGAIN)) {
+        uint32_t k0 = lo_raw;                                  // 16-aligned position of the first group with a hit
+        while (m) {                                            // at most four groups
+            const unsigned mk = (unsigned)(m & 0xffffull);
+            if (mk) bxs::emit_group_to(ix.WI, k0, mk, out, Ld4(), ix.mul);
+            m >>= 16;
+            k0 += 16;
+        }
+    } else {
+        const uint32_t lo = lo_raw & ~WALK_AGAIN, hi = (uint32_t)hi_[q];
+        const int32_t qs = __ldg(qs_ + q);
+        bxs::walk_hits(ix.WE, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                       [&](uint32_t k0, unsigned mask) { bxs::emit_group_to(ix.WI, k0, mask, out, Ld4(), ix.mul); },
+                       bxs::NoPrefetch(), ix.mul);
+    }
+}
+
+__global__ void __launch_bounds__(FIND_THREADS, FILL_MIN_CTAS)
+k_fill_staged(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qs_, int64_t nq, const int32_t *__restrict__ lo_,
+              const int32_t *__restrict__ hi_, const unsigned long long *__restrict__ mask_, const int64_t *__restrict__ off,
+              int32_t *__restrict__ hits) {
+    __shared__ int32_t stage[FIND_THREADS / 32][FILL_STAGE];
+    const int lane = threadIdx.x & 31;
+    int32_t *buf = stage[threadIdx.x >> 5];
+    const uint32_t buf_a = (uint32_t)__cvta_generic_to_shared(buf);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t off_end = off[nq];
+    for (int64_t qw = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); qw < nq; qw += stride) {   // warp-uniform
+        const int64_t q = qw + lane;
+        const bool valid = q < nq;
+        uint32_t lo_raw = 0;
+        unsigned long long m = 0;
+        int64_t o = off_end;
+        if (valid) { lo_raw = (uint32_t)lo_[q]; m = mask_[q]; o = off[q]; }
+        int64_t o_next = __shfl_down_sync(0xffffffffu, o, 1);
+        if (lane == 31) o_next = valid ? off[q + 1] : off_end;
+        const int64_t span0 = __shfl_sync(0xffffffffu, o, 0);
+        const int64_t span = __shfl_sync(0xffffffffu, o_next, 31) - span0;
+        if (span == 0) continue;
+        if (span <= FILL_STAGE) {
+            if (o_next > o) {
+                SharedSink out{buf_a + 4u * (uint32_t)(o - span0)};
+                fill_query(ix, lo_raw, m, q, qs_, hi_, out);
+            }
+            __syncwarp();
+            int32_t *dst = hits + span0;
+            for (int i = lane; i < (int)span; i += 32) dst[i] = buf[i];
+            __syncwarp();
+        } else if (o_next > o) {
+            bxs::PtrSink out{hits + o};
+            fill_query(ix, lo_raw, m, q, qs_, hi_, out);
+        }
     }
 }
 
@@ -525,6 +609,18 @@ static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
 // pass B over queries [q0, q0+nq): writes hits at the (global) CSR offsets d_off[q0..]
 static int launch_fill(bxg_itree *t, const int32_t *dqs, int64_t nq, int64_t q0 = 0) {
     int occ = 0;
+    static const bool staged = [] {
+        const char *e = getenv("BXB200_FILL_STAGED");     // 0: direct stores (k_find<true>), for A/B measurements
+        return !(e && e[0] == '0');
+    }();
+    if (staged) {
+        BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fill_staged, FIND_THREADS, 0));
+        int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
+        BXG_LAUNCH(k_fill_staged, grid, FIND_THREADS, 0, t->view(), dqs + q0, nq, (const int32_t *)(t->d_lo + q0),
+                   (const int32_t *)(t->d_hi + q0), (const unsigned long long *)(t->d_mask + q0),
+                   (const int64_t *)(t->d_off + q0), t->d_hits);
+        return BXG_OK;
+    }
     BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<true>, FIND_THREADS, 0));
     int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
     BXG_LAUNCH((k_find<true>), grid, FIND_THREADS, 0, t->view(), (const int32_t *)nullptr, dqs + q0,

@@ -291,28 +291,39 @@ BXG_HD void search_walk(const int32_t *const *KS, const int32_t *const *KP, int 
 // Write the item ids of the hits of one 16-item group: the whole aligned group of I is fetched with four 16-byte
 // loads issued back to back (one 64-byte line), THEN the selected ids are stored -- a load per hit interleaved with
 // the stores would serialise on every store (the compiler must assume hits[] may alias I[]).
-template <typename LD4>
-BXG_HD int32_t *emit_group(const int32_t *I, uint32_t k0, unsigned mask, int32_t *dst, const LD4 &ld4, int mul = 1) {
+template <typename LD4, typename SINK>
+BXG_HD void emit_group_to(const int32_t *I, uint32_t k0, unsigned mask, SINK &out, const LD4 &ld4, int mul = 1) {
     const int4 *p = reinterpret_cast<const int4 *>(group_ptr(I, k0, mul));
     int4 a, b, c, d;
     ld4(p, a, b, c, d);
-    if (mask & 0x0001u) *dst++ = a.x;
-    if (mask & 0x0002u) *dst++ = a.y;
-    if (mask & 0x0004u) *dst++ = a.z;
-    if (mask & 0x0008u) *dst++ = a.w;
-    if (mask & 0x0010u) *dst++ = b.x;
-    if (mask & 0x0020u) *dst++ = b.y;
-    if (mask & 0x0040u) *dst++ = b.z;
-    if (mask & 0x0080u) *dst++ = b.w;
-    if (mask & 0x0100u) *dst++ = c.x;
-    if (mask & 0x0200u) *dst++ = c.y;
-    if (mask & 0x0400u) *dst++ = c.z;
-    if (mask & 0x0800u) *dst++ = c.w;
-    if (mask & 0x1000u) *dst++ = d.x;
-    if (mask & 0x2000u) *dst++ = d.y;
-    if (mask & 0x4000u) *dst++ = d.z;
-    if (mask & 0x8000u) *dst++ = d.w;
-    return dst;
+    if (mask & 0x0001u) out.put(a.x);
+    if (mask & 0x0002u) out.put(a.y);
+    if (mask & 0x0004u) out.put(a.z);
+    if (mask & 0x0008u) out.put(a.w);
+    if (mask & 0x0010u) out.put(b.x);
+    if (mask & 0x0020u) out.put(b.y);
+    if (mask & 0x0040u) out.put(b.z);
+    if (mask & 0x0080u) out.put(b.w);
+    if (mask & 0x0100u) out.put(c.x);
+    if (mask & 0x0200u) out.put(c.y);
+    if (mask & 0x0400u) out.put(c.z);
+    if (mask & 0x0800u) out.put(c.w);
+    if (mask & 0x1000u) out.put(d.x);
+    if (mask & 0x2000u) out.put(d.y);
+    if (mask & 0x4000u) out.put(d.z);
+    if (mask & 0x8000u) out.put(d.w);
+}
+
+struct PtrSink {
+    int32_t *p;
+    BXG_HD void put(int32_t v) { *p++ = v; }
+};
+
+template <typename LD4>
+BXG_HD int32_t *emit_group(const int32_t *I, uint32_t k0, unsigned mask, int32_t *dst, const LD4 &ld4, int mul = 1) {
+    PtrSink out{dst};
+    emit_group_to(I, k0, mask, out, ld4, mul);
+    return out.p;
 }
 
 }  // namespace bxs
