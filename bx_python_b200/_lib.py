@@ -79,10 +79,21 @@ SIGNATURES = {
     "bxg_itree_result_dev": [vp, pvp, pvp, pi64, pi64],
     "bxg_itree_count": [vp, vp, vp, vp, i64, cint, vp, pi64],
     "bxg_itree_neighbors": [vp, vp, vp, vp, vp, i64, cint, cint, pi64],
+    "bxg_itree_join": [vp, vp, vp, vp, i64, vp, vp, i32, cint, pi64],
+    "bxg_itree_join_fetch": [vp, vp, vp],
     "bxg_scores_create": [vp, i64, i32, cint, pvp],
     "bxg_scores_free": [vp],
     "bxg_aggregate": [vp, vp, vp, vp, i64, cint, vp, vp, vp, vp, vp],
     "bxg_aggregate_multi": [pvp, pvp, i32, vp, vp, vp, i64, cint, vp, vp, vp, vp, vp],
+    "bxg_scores_alloc": [i64, i32, C.c_float, pvp],
+    "bxg_scores_info": [vp, pi64, pi32, C.POINTER(C.c_float)],
+    "bxg_scores_reserve": [vp, i64],
+    "bxg_scores_set_spans": [vp, vp, vp, vp, i64, cint],
+    "bxg_scores_write": [vp, i64, vp, i64, cint],
+    "bxg_scores_get": [vp, vp, i64, vp, cint],
+    "bxg_scores_get_range": [vp, i64, i64, vp],
+    "bxg_scores_device": [vp, pvp, pi64],
+    "bxg_summarize": [vp, vp, vp, i64, cint, C.c_uint32, C.c_uint32, i32, vp, vp, vp, vp, vp],
     "bxg_comm_unique_id": [C.c_char_p],
     "bxg_comm_init": [C.c_char_p, cint, cint],
     "bxg_comm_allreduce_i64": [vp, i64],

@@ -59,6 +59,9 @@ def aggregate_genome(tracks, track_ids, starts, ends, masks=None):
     nw, nt = len(ws), len(tracks)
     out = dict(sum=np.empty(nw, np.float32), avg=np.empty(nw, np.float32), count=np.empty(nw, np.int32),
                min=np.empty(nw, np.float32), max=np.empty(nw, np.float32))
+    for t in tracks:
+        if hasattr(t, "_flush"):                       # device BinnedArray: apply queued scalar sets first
+            t._flush()
     ht = (C.c_void_p * nt)(*[t._h for t in tracks])
     hm = None
     if masks is not None:
@@ -76,3 +79,39 @@ def format_line(res, w):
     if res["count"][w] == 0:
         return ["nan", "nan", "nan"]
     return [str(np.float32(res[k][w])) for k in ("avg", "min", "max")]
+
+
+def aggregate_scores_in_intervals(scores_by_chrom, interval_lines, out_file, masks=None):
+    """The main loop of scripts/aggregate_scores_in_intervals.py:105-134 as one launch: for every line
+    ``chrom start stop ...`` of ``interval_lines`` write ``chrom, start, stop, avg, min, max`` (tab separated;
+    ``nan`` columns when nothing was counted) to ``out_file``.  ``scores_by_chrom`` maps chromosome ->
+    ``ScoreTrack`` / device ``BinnedArray`` / ``FileBinnedArray`` (``wiggle.load_scores_wiggle`` builds one);
+    ``masks`` maps chromosome -> bit set (``bitset_builders.binned_bitsets_from_file``) or is None."""
+    chroms, starts, stops = [], [], []
+    for line in interval_lines:
+        fields = line.split()
+        chroms.append(fields[0])
+        starts.append(int(fields[1]))
+        stops.append(int(fields[2]))
+    names = list(scores_by_chrom.keys()) if hasattr(scores_by_chrom, "keys") else None
+    if names is None:                                  # a dict-like without iteration (FileBinnedArrayDir, :30-57)
+        names = []
+        for c in dict.fromkeys(chroms):
+            try:
+                scores_by_chrom[c]
+                names.append(c)
+            except KeyError:
+                pass
+    tid = {c: i for i, c in enumerate(names)}
+    if not chroms:
+        return
+    if not names:
+        res = None
+    else:
+        tracks = [scores_by_chrom[c] for c in names]
+        mlist = None if not masks else [masks[c] if c in masks else None for c in names]
+        wt = np.asarray([tid.get(c, -1) for c in chroms], np.int32)
+        res = aggregate_genome(tracks, wt, starts, stops, mlist)
+    for w, (c, a, b) in enumerate(zip(chroms, starts, stops)):
+        cols = ["nan", "nan", "nan"] if res is None else format_line(res, w)
+        print("\t".join([c, str(a), str(b)] + cols), file=out_file)

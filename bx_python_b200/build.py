@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbxb200.so")
-SOURCES = ["runtime.cu", "bits.cu", "itree.cu", "aggregate.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "itree_search.cuh"),
+SOURCES = ["runtime.cu", "bits.cu", "itree.cu", "aggregate.cu", "scores.cu", "join.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "itree_search.cuh"), os.path.join(CSRC, "scores.cuh"),
            os.path.join(HERE, "..", "include", "bxb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -6,20 +6,13 @@
 // LSB-first bitmap (bits.cu).
 #include <math.h>
 
-#include "common.cuh"
+#include "scores.cuh"
 
 using namespace bxg;
 
 struct bxg_bits;
 const uint64_t *bxg_bits_words_internal(const bxg_bits *b);
 int32_t bxg_bits_size_internal(const bxg_bits *b);
-
-struct bxg_scores {
-    float *v = nullptr;
-    int64_t n = 0;
-    int32_t origin = 0;
-    bool owned = true;
-};
 
 // one window: strict left-to-right float32 accumulation over positions [ws,we) of one track
 __device__ __forceinline__ void aggregate_window(const float *__restrict__ v, int64_t n, int64_t origin,
@@ -98,8 +91,10 @@ int bxg_scores_create(const float *scores, int64_t n, int32_t origin, int loc, b
     if (!out || n < 0) return set_error(BXG_ERR_ARG, "bad arguments");
     bxg_scores *s = new bxg_scores();
     s->n = n;
+    s->cap = n > 0 ? n : 1;
     s->origin = origin;
-    BXG_CUDA(cudaMalloc(&s->v, (size_t)(n > 0 ? n : 1) * 4));
+    s->fill = __builtin_nanf("");
+    BXG_CUDA(cudaMalloc(&s->v, (size_t)s->cap * 4));
     if (n)
         BXG_CUDA(cudaMemcpyAsync(s->v, scores, (size_t)n * 4,
                                  loc == BXG_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx().stream));

@@ -201,3 +201,70 @@ def exon_lists(seed):
         s = np.sort(rng.integers(0, 5000, int(rng.integers(1, 30))))
         return [(int(a), int(a + rng.integers(1, 120))) for a in s]
     return one(), one()
+
+
+# ---- score sources / summary / join -------------------------------------------------------------------
+def wiggle_text(seed, n=6000, chroms=("chr1", "chr2")):
+    """A wiggle file mixing fixedStep / variableStep blocks (with and without span), a leading bedGraph-style
+    section, comments and blank lines; blocks overlap on purpose so that file order decides the final score."""
+    rng = np.random.default_rng(7000 + seed)
+    lines = ["track type=wiggle_0 name=synthetic", "# comment"]
+    if seed % 2:                                     # bed mode comes first (before any declaration)
+        for _ in range(int(rng.integers(1, 30))):
+            s = int(rng.integers(0, n - 50))
+            lines.append(f"{chroms[int(rng.integers(0, len(chroms)))]}\t{s}\t{s + int(rng.integers(0, 40))}\t{rng.normal():.4f}")
+        lines.append("chr1\t5\t9")                   # too few fields: ignored by the reader
+    for _ in range(int(rng.integers(2, 8))):
+        chrom = chroms[int(rng.integers(0, len(chroms)))]
+        kind = int(rng.integers(0, 3))
+        span = int(rng.integers(1, 7))
+        if kind == 0:
+            step = int(rng.integers(1, 6))
+            cnt = int(rng.integers(0, 150))
+            start = int(rng.integers(1, n - cnt * step - span - 1))
+            lines.append(f"fixedStep chrom={chrom} start={start} step={step}" + (f" span={span}" if span > 1 else ""))
+            for _ in range(cnt):
+                r = rng.random()
+                lines.append("nan" if r < 0.03 else "0" if r < 0.06 else repr(float(np.float32(rng.normal()))))
+            if rng.random() < 0.5:
+                lines.append("")
+        else:
+            lines.append(f"variableStep chrom={chrom}" + (f" span={span}" if kind == 1 else ""))
+            for p in rng.integers(1, n - 10, int(rng.integers(0, 150))).tolist():
+                lines.append(f"{p} {rng.normal():.5f}")
+    return "\n".join(lines) + "\n"
+
+
+def summarize_case(seed):
+    """(start, end, val, region start, region end, size): sorted disjoint batches (what a bigWig holds) for even
+    seeds, arbitrary overlapping / unsorted / empty / clipped ones for odd seeds."""
+    rng = np.random.default_rng(8000 + seed)
+    n = int(rng.integers(0, 400))
+    rs = int(rng.integers(0, 1000))
+    re_ = rs + int(rng.integers(1, 5000))
+    size = int(rng.integers(1, 64))
+    if seed % 2 == 0:
+        gaps, lens = rng.integers(0, 40, n), rng.integers(1, 90, n)
+        s = np.maximum(rs - 150 + np.cumsum(gaps + np.concatenate([[0], lens[:-1]])), 0)
+        e = s + lens
+    else:
+        s = rng.integers(max(rs - 200, 0), re_ + 200, n)
+        e = np.maximum(s + rng.integers(-2, 150, n), 0)
+    return s.astype(np.int32), e.astype(np.int32), rng.normal(0, 3, n).astype(np.float32), rs, re_, size
+
+
+def join_case(seed, nl=120, nr=100):
+    """Two BED line lists (4 columns) over three chromosomes, with zero-length intervals, duplicates and a comment."""
+    rng = np.random.default_rng(9000 + seed)
+
+    def bed(n, tag):
+        out = []
+        for i in range(n):
+            s = int(rng.integers(0, 800))
+            out.append(f"chr{int(rng.integers(1, 4))}\t{s}\t{s + int(rng.integers(0, 70))}\t{tag}{i}")
+        return out
+    left, right = bed(nl, "L"), bed(nr, "R")
+    left.insert(3, "# a comment in the left file")
+    right.append("chr9\t10\t20\tRlonely")
+    left.append("chr8\t10\t20\tLlonely")
+    return left, right, int(rng.integers(1, 12))

@@ -185,6 +185,16 @@ int bxg_itree_count(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, con
 int bxg_itree_neighbors(bxg_itree_t *t, const int32_t *qtree, const int32_t *pos, const int32_t *n,
                         const int32_t *max_dist, int64_t nq, int dir, int loc, int64_t *total);
 
+/* Overlap join (lib/bx/intervals/operations/join.py:14-75 over operations/quicksect.py:11-125): for every left
+ * interval q the items of the index with start < item.end && end > item.start (quicksect.py:115-121) whose `overlap`
+ * by the case analysis of join.py:35-50 is >= mincols.  istart/iend are the index's items in INSERTION order (the ids
+ * `find` returns index them).  Results stay on the device until bxg_itree_join_fetch: CSR pair_offsets[nq+1] /
+ * pair_items[total] (item ids, index order within a left interval -- the reference's own order is a random treap
+ * walk) and visited[n] = 1 for every item kept at least once (join.py:54, drives the left-fill pass :62-75). */
+int bxg_itree_join(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
+                   const int32_t *istart, const int32_t *iend, int32_t mincols, int loc, int64_t *total_pairs);
+int bxg_itree_join_fetch(int64_t *pair_offsets, int32_t *pair_items, uint8_t *visited);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * aggregate_scores_in_intervals inner loop (scripts/aggregate_scores_in_intervals.py:107-134 over
  * BinnedArray.get, lib/bx/binned_array.py:89-94).  scores: dense float32, position origin+i, NaN = unset.
@@ -202,6 +212,38 @@ int bxg_aggregate(const bxg_scores_t *s, const bxg_bits_t *mask /* or NULL */,
 int bxg_aggregate_multi(const bxg_scores_t *const *tracks, const bxg_bits_t *const *masks, int32_t ntracks,
                         const int32_t *wtrack, const int32_t *ws, const int32_t *we, int64_t nw, int loc,
                         float *sum, float *avg, int32_t *count, float *mn, float *mx);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Score sources.
+ *
+ * BinnedArray (lib/bx/binned_array.py:72-136: get :89-94, set :96-100, get_range :102-127) as a dense device track:
+ * a bin that was never written reads as `default`, so a track pre-filled with `fill` is observably identical.
+ * bxg_scores_set_spans replaces the per-base assignment loop of load_scores_wiggle
+ * (scripts/aggregate_scores_in_intervals.py:60-70 over wiggle.Reader, lib/bx/wiggle.py:71-85): span i assigns val[i]
+ * to every position of [start[i], end[i]) (end == NULL: single positions), spans are applied IN ORDER, i.e. where
+ * spans overlap the last one wins; empty spans (end <= start) assign nothing.  Spans must lie inside the track
+ * (bxg_scores_reserve first).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int bxg_scores_alloc(int64_t n, int32_t origin, float fill, bxg_scores_t **out);       /* BinnedArray.__init__        */
+int bxg_scores_info(const bxg_scores_t *s, int64_t *n, int32_t *origin, float *fill);
+int bxg_scores_reserve(bxg_scores_t *s, int64_t n);            /* grow to n cells; new cells = fill (init_bin, :84-87) */
+int bxg_scores_set_spans(bxg_scores_t *s, const int32_t *start, const int32_t *end /* or NULL */, const float *val,
+                         int64_t n, int loc);
+int bxg_scores_write(bxg_scores_t *s, int64_t start, const float *vals, int64_t n, int loc);     /* contiguous cells  */
+int bxg_scores_get(const bxg_scores_t *s, const int32_t *pos, int64_t n, float *out, int loc);   /* get, batched      */
+int bxg_scores_get_range(const bxg_scores_t *s, int64_t start, int64_t end, float *out /* host, end-start floats */);
+int bxg_scores_device(const bxg_scores_t *s, const float **dptr, int64_t *n);
+
+/* bigWig summary (lib/bx/bbi/bbi_file.pyx:66-111, SummarizedData.accumulate_interval_value applied to every interval
+ * of the batch in order; lib/bx/bbi/bigwig_file.pyx:93-108,176-185 is the caller that feeds it the file's intervals):
+ * `size` bins of (rend - rstart) / size bases over [rstart, rend); per bin float64 valid_count, sum, sum of squares
+ * (weights and products in the reference's expression order), min and max.  The five arrays are IN/OUT: the batch
+ * is accumulated into the state they hold (zeros from SummarizedData.__init__, :70-78; +inf / -inf min / max from
+ * SummarizingBlockHandler, bigwig_file.pyx:98-105), so several calls continue one summary exactly like repeated
+ * accumulate_interval_value calls.  Coordinates are bits32 in the reference; values < 2^31 here. */
+int bxg_summarize(const int32_t *start, const int32_t *end, const float *val, int64_t n, int loc, uint32_t rstart,
+                  uint32_t rend, int32_t size, double *valid_count, double *min_val, double *max_val, double *sum_data,
+                  double *sum_squares);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Multi-GPU: one process per GPU; chromosomes are sharded with no data-path exchange; only the final per-chromosome

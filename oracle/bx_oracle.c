@@ -18,6 +18,10 @@
  *   orc_bits_* (flat BitSet)            <- src/kent/bits.c:51-263 via lib/bx/bitset.pyx:107-173
  *   orc_aggregate                       <- scripts/aggregate_scores_in_intervals.py:107-134 with
  *                                          lib/bx/binned_array.py:89-94 float32 semantics
+ *   orc_scores_set_spans                <- scripts/aggregate_scores_in_intervals.py:60-70 over lib/bx/wiggle.py:71-85
+ *                                          (per-base BinnedArray assignment in file order)
+ *   orc_summarize                       <- lib/bx/bbi/bbi_file.pyx:80-111 (SummarizedData.accumulate_interval_value)
+ *   orc_join                            <- lib/bx/intervals/operations/join.py:30-61 over quicksect.py:115-121
  *
  * Written as a closed-form restatement, not a transliteration: the treap is replaced by the total order its
  * in-order traversal realises; the sentinel pointers are replaced by a per-bin state byte.
@@ -464,4 +468,98 @@ void orc_aggregate(const float *scores, int64_t n, const uint64_t *mask,
         if (c > 0) { avg[w] = total / (float)c; mn[w] = (float)lo; mx[w] = (float)hi; }
         else { avg[w] = NAN; mn[w] = NAN; mx[w] = NAN; }
     }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Score sources
+ * ------------------------------------------------------------------------------------------------------------
+ * load_scores_wiggle: `scores_by_chrom[chrom][pos] = val` for every base of every record, in file order; a later
+ * record overwrites an earlier one.  track[] is the dense array (position p at index p - origin), pre-filled by the
+ * caller with the BinnedArray default.  end == NULL means single positions.  Returns -1 if a base falls outside.
+ */
+int orc_scores_set_spans(float *track, int64_t n, int64_t origin, const int32_t *start, const int32_t *end,
+                         const float *val, int64_t nspans)
+{
+    for (int64_t i = 0; i < nspans; i++) {
+        int64_t a = start[i], b = end ? end[i] : a + 1;
+        for (int64_t p = a; p < b; p++) {
+            if (p - origin < 0 || p - origin >= n) return -1;
+            track[p - origin] = val[i];
+        }
+    }
+    return 0;
+}
+
+/*
+ * SummarizedData.accumulate_interval_value for every interval in order.  The caller initialises the five arrays
+ * (zeros in SummarizedData.__init__, +inf/-inf min/max in SummarizingBlockHandler).  Types follow the Cython
+ * declarations: s, e are bits32 arguments clipped against the region; base_*, overlap, interval_size are C ints;
+ * overlap_factor / interval_weight doubles; val a C float (val * val is a float product, then widened).
+ * volatile keeps gcc from contracting a*b+c into an fma.
+ */
+void orc_summarize(const int32_t *start, const int32_t *end, const float *val, int64_t n,
+                   uint32_t rstart, uint32_t rend, int32_t size,
+                   double *valid_count, double *min_val, double *max_val, double *sum_data, double *sum_squares)
+{
+    for (int64_t i = 0; i < n; i++) {
+        uint32_t s = (uint32_t)start[i], e = (uint32_t)end[i];
+        if (s < rstart) s = rstart;
+        if (e > rend) e = rend;
+        if (s >= e) continue;
+        int base_step = (int)((rend - rstart) / (uint32_t)size);
+        float v = val[i];
+        for (int j = 0; j < size; j++) {
+            int base_start = (int)(rstart + (uint32_t)(base_step * j));
+            int base_end = base_start + base_step;
+            int lo = base_start > (int)s ? base_start : (int)s, hi = base_end < (int)e ? base_end : (int)e;
+            int overlap = hi - lo;
+            if (overlap > 0) {
+                int interval_size = (int)(e - s);
+                volatile double overlap_factor = (double)overlap / interval_size;
+                volatile double interval_weight = interval_size * overlap_factor;
+                volatile double t1 = v * interval_weight;
+                volatile float vv = v * v;
+                volatile double t2 = vv * interval_weight;
+                valid_count[j] += interval_weight;
+                sum_data[j] += t1;
+                sum_squares[j] += t2;
+                if (max_val[j] < v) max_val[j] = v;
+                if (min_val[j] > v) min_val[j] = v;
+            }
+        }
+    }
+}
+
+/*
+ * join.py:30-61: for left interval q, the right items (same tree) with qs < item.end && qe > item.start
+ * (quicksect.py:115-121) whose overlap (:35-50, inclusive membership tests) is >= mincols.  Emits, per left interval,
+ * the kept item ids in ascending id order (the reference's own order is a random treap pre-order) and visited[].
+ * pair_items may be NULL to only count.  Returns the number of kept pairs.
+ */
+int64_t orc_join(const int32_t *itree, const int32_t *istart, const int32_t *iend, int64_t n,
+                 const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq, int32_t mincols,
+                 int64_t *pair_offsets, int32_t *pair_items, uint8_t *visited)
+{
+    int64_t w = 0;
+    for (int64_t q = 0; q < nq; q++) {
+        pair_offsets[q] = w;
+        int64_t ls = qs[q], le = qe[q];
+        for (int64_t i = 0; i < n; i++) {
+            if (itree[i] != qtree[q]) continue;
+            int64_t s = istart[i], e = iend[i];
+            if (!(ls < e && le > s)) continue;
+            int in_s = s >= ls && s <= le, in_e = e >= ls && e <= le;
+            int64_t ov;
+            if (in_s && !in_e) ov = le - s;
+            else if (in_e && !in_s) ov = e - ls;
+            else if (in_s && in_e) ov = e - s;
+            else ov = le - ls;
+            if (ov < mincols) continue;
+            if (pair_items) pair_items[w] = (int32_t)i;
+            if (visited) visited[i] = 1;
+            w++;
+        }
+    }
+    pair_offsets[nq] = w;
+    return w;
 }

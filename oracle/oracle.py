@@ -23,6 +23,7 @@ _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 _u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 
 
 def build_port() -> None:
@@ -57,6 +58,9 @@ def lib():
         "orc_itree_find": (C.c_int, [vp, _i32p, _i32p, i64, _i64p, C.c_void_p]),
         "orc_itree_before": (i64, [vp, i32, i32, i32, _i32p, i64]),
         "orc_itree_after": (i64, [vp, i32, i32, i32, _i32p, i64]),
+        "orc_scores_set_spans": (C.c_int, [_f32p, i64, i64, _i32p, C.c_void_p, _f32p, i64]),
+        "orc_summarize": (None, [_i32p, _i32p, _f32p, i64, C.c_uint32, C.c_uint32, i32, _f64p, _f64p, _f64p, _f64p, _f64p]),
+        "orc_join": (i64, [_i32p, _i32p, _i32p, i64, _i32p, _i32p, _i32p, i64, i32, _i64p, C.c_void_p, _u8p]),
         "orc_bb_geometry": (None, [i32, i32, C.POINTER(i32), C.POINTER(i32)]),
         "orc_bb_new": (vp, [i32, i32]),
         "orc_bb_free": (None, [vp]),
@@ -242,6 +246,47 @@ def aggregate(scores, ws, we, mask_words=None):
         mp = mask_words.ctypes.data_as(C.c_void_p)
     lib().orc_aggregate(scores, len(scores), mp, ws, we, nw, out["sum"], out["avg"], out["count"], out["min"], out["max"])
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# score sources, bigWig summary, join
+# ---------------------------------------------------------------------------------------------------------------
+def scores_set_spans(track, origin, start, end, val):
+    """In place: the sequential per-base assignment loop (last record wins); see orc_scores_set_spans."""
+    assert track.dtype == np.float32 and track.flags.c_contiguous
+    start, val = _a32(start), np.ascontiguousarray(val, np.float32)
+    ep = None
+    if end is not None:
+        end = _a32(end)
+        ep = end.ctypes.data_as(C.c_void_p)
+    rc = lib().orc_scores_set_spans(track, len(track), origin, start, ep, val, len(start))
+    if rc != 0:
+        raise IndexError("span outside the track")
+    return track
+
+
+def summarize(start, end, val, rstart, rend, size, init_min=np.inf, init_max=-np.inf):
+    """-> dict(valid_count, min_val, max_val, sum_data, sum_squares) float64[size]; see orc_summarize."""
+    start, end, val = _a32(start), _a32(end), np.ascontiguousarray(val, np.float32)
+    out = dict(valid_count=np.zeros(size), min_val=np.full(size, float(init_min)), max_val=np.full(size, float(init_max)),
+               sum_data=np.zeros(size), sum_squares=np.zeros(size))
+    lib().orc_summarize(start, end, val, len(start), rstart, rend, size, out["valid_count"], out["min_val"],
+                        out["max_val"], out["sum_data"], out["sum_squares"])
+    return out
+
+
+def join(itree, istart, iend, qtree, qs, qe, mincols=1):
+    """-> (pair_offsets, pair_items, visited); see orc_join."""
+    itree, istart, iend = _a32(itree), _a32(istart), _a32(iend)
+    qtree, qs, qe = _a32(qtree), _a32(qs), _a32(qe)
+    nq, n = len(qs), len(istart)
+    off = np.zeros(nq + 1, np.int64)
+    vis = np.zeros(max(n, 1), np.uint8)
+    total = lib().orc_join(itree, istart, iend, n, qtree, qs, qe, nq, mincols, off, None, vis)
+    items = np.empty(max(total, 1), np.int32)
+    vis[:] = 0
+    lib().orc_join(itree, istart, iend, n, qtree, qs, qe, nq, mincols, off, items.ctypes.data_as(C.c_void_p), vis)
+    return off, items[:total], vis[:n].astype(bool)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -207,6 +207,115 @@ def golden_builders():
     print("builders.json:", len(cases), "cases")
 
 
+def _ref_pure_python():
+    """Make the reference's pure-Python modules importable next to the compiled ones in oracle/_ref."""
+    import bx
+    import bx.bbi
+    import bx.intervals
+    for pkg, sub in ((bx, ""), (bx.intervals, "intervals"), (bx.bbi, "bbi")):
+        d = os.path.join(REFERENCE, "lib", "bx", sub)
+        if d not in pkg.__path__:
+            pkg.__path__.append(d)
+    if os.path.join(REFERENCE, "lib") not in sys.path:
+        sys.path.append(os.path.join(REFERENCE, "lib"))           # bx_extras
+
+
+def golden_scores():
+    """Reference wiggle.Reader -> BinnedArray per-base loop (load_scores_wiggle), BinnedArray.to_file bytes, and the
+    aggregate script run on the same wiggle text."""
+    _ref_pure_python()
+    import hashlib
+    import bx.wiggle
+    from bx.binned_array import BinnedArray
+    out = {}
+    for seed in range(8):
+        text = synth.wiggle_text(seed)
+        recs = [(c, s, e, st, float(v)) for c, s, e, st, v in bx.wiggle.IntervalReader(io.StringIO(text))]
+        arrays = {}
+        for chrom, pos, val in bx.wiggle.Reader(io.StringIO(text)):
+            if chrom not in arrays:
+                arrays[chrom] = BinnedArray(bin_size=1024, max_size=8192)
+            arrays[chrom][pos] = val
+        for chrom, ba in arrays.items():
+            out[f"s{seed}_{chrom}_dense"] = ba.get_range(0, 8192)
+            buf = io.BytesIO()
+            ba.to_file(buf)
+            out[f"s{seed}_{chrom}_file_sha256"] = np.frombuffer(hashlib.sha256(buf.getvalue()).digest(), np.uint8)
+        out[f"s{seed}_chroms"] = np.array(list(arrays.keys()))
+        out[f"s{seed}_nrecords"] = np.int64(len(recs))
+        out[f"s{seed}_rec_checksum"] = np.int64(sum((s * 31 + e * 17) % 1000003 for _, s, e, _, _ in recs))
+    np.savez_compressed(os.path.join(HERE, "scores.npz"), **out)
+    print("scores.npz:", len(out), "arrays")
+
+
+def golden_summarize():
+    """SummarizedData.accumulate_interval_value of the compiled reference (through oracle/bbi_shim) on synthetic
+    batches, and BigWigFile.get / summarize_from_full on the reference's own test.bw."""
+    _ref_pure_python()
+    import bbi_shim
+    from bx.bbi.bbi_file import SummarizedData
+    from bx.bbi.bigwig_file import BigWigFile
+    out = {}
+    keys = ("valid_count", "min_val", "max_val", "sum_data", "sum_squares")
+    for seed in range(24):
+        s, e, v, rs, re_, size = synth.summarize_case(seed)
+        sd = SummarizedData(rs, re_, size)
+        if seed % 4 < 2:
+            sd.min_val[:] = np.inf
+            sd.max_val[:] = -np.inf
+        bbi_shim.accumulate(sd, s.tolist(), e.tolist(), v.tolist())
+        out[f"c{seed}"] = np.stack([getattr(sd, k) for k in keys])
+    bw = BigWigFile(file=open(os.path.join(REFERENCE, "test_data", "bbi_tests", "test.bw"), "rb"))
+    iv = bw.get(b"chr1", 10000, 20000)
+    out["bw_start"] = np.array([x[0] for x in iv], np.int32)
+    out["bw_end"] = np.array([x[1] for x in iv], np.int32)
+    out["bw_val"] = np.array([x[2] for x in iv], np.float32)
+    regions = [(10000, 20000, 10), (10000, 20000, 7), (10917, 11500, 33), (12345, 19999, 100), (10000, 10920, 4)]
+    out["bw_regions"] = np.array(regions, np.int64)
+    for k, (a, b, size) in enumerate(regions):
+        sd = bw.summarize_from_full(b"chr1", a, b, size)
+        out[f"bw{k}"] = np.stack([getattr(sd, key) for key in keys])      # valid_count is rounded by the caller (:182-184)
+    np.savez_compressed(os.path.join(HERE, "summarize.npz"), **out)
+    print("summarize.npz:", len(out), "arrays;", len(iv), "bigWig intervals")
+
+
+def canonical_join_rows(rows, leftlen):
+    """Rows of one left interval are contiguous but in treap pre-order (random): sort inside each such group."""
+    out, group, key = [], [], None
+    for r in rows:
+        if not isinstance(r, list):
+            r = ["<passthrough>"]
+        k = tuple(r[:leftlen])
+        if k != key or all(x == "." for x in k):
+            out.extend(sorted(group))
+            group, key = [], k
+        if all(x == "." for x in k):
+            out.append(r)                              # left-fill tail: order is deterministic, keep it
+        else:
+            group.append(r)
+    out.extend(sorted(group))
+    return out
+
+
+def golden_join():
+    _ref_pure_python()
+    from bx.intervals.io import NiceReaderWrapper
+    from bx.intervals.operations.join import join
+    cases = []
+    for seed in range(6):
+        left, right, mincols = synth.join_case(seed)
+
+        def rd(lines):
+            return NiceReaderWrapper(io.StringIO("\n".join(lines) + "\n"), chrom_col=0, start_col=1, end_col=2,
+                                     fix_strand=True)
+        for lf, rf in ((True, True), (False, True), (True, False)):
+            rows = list(join(rd(left), rd(right), mincols=mincols, leftfill=lf, rightfill=rf))
+            cases.append({"seed": seed, "mincols": mincols, "leftfill": lf, "rightfill": rf,
+                          "rows": canonical_join_rows(rows, 4)})
+    json.dump(cases, open(os.path.join(HERE, "join.json"), "w"))
+    print("join.json:", len(cases), "cases;", sum(len(c["rows"]) for c in cases), "rows")
+
+
 if __name__ == "__main__":
     orc.build_ref(REFERENCE)
     bs, ix = orc.ref_modules()
@@ -215,3 +324,6 @@ if __name__ == "__main__":
     golden_bitset(bs)
     golden_aggregate()
     golden_builders()
+    golden_scores()
+    golden_summarize()
+    golden_join()

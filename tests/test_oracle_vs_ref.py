@@ -173,3 +173,88 @@ def test_runs_idiom():
             runs.append((st, end))
         rs, re = o.runs()
         assert runs == list(zip(rs.tolist(), re.tolist()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# score sources, bigWig summary, join -- against the live reference (needs /root/reference for its
+# pure-Python modules, so these also skip on a box that only carries the compiled oracle/_ref)
+# ---------------------------------------------------------------------------------------------------------------
+import io  # noqa: E402
+import os  # noqa: E402
+import sys  # noqa: E402
+
+REFERENCE = "/root/reference"
+needs_reference = pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="/root/reference not present")
+
+
+def _ref_pure_python():
+    orc.ref_modules()
+    import bx
+    import bx.intervals
+    import bx.bbi
+    for pkg, sub in ((bx, ""), (bx.intervals, "intervals"), (bx.bbi, "bbi")):
+        d = os.path.join(REFERENCE, "lib", "bx", sub)
+        if d not in pkg.__path__:
+            pkg.__path__.append(d)
+    if os.path.join(REFERENCE, "lib") not in sys.path:
+        sys.path.append(os.path.join(REFERENCE, "lib"))
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(100, 140))
+def test_summarize_vs_compiled_accumulate(seed):
+    from bx_python_b200 import synth
+    _ref_pure_python()                                 # bx.bbi.bbi_file imports the pure-Python bx.misc.binary_file
+    try:
+        import bbi_shim
+        from bx.bbi.bbi_file import SummarizedData
+    except ImportError:
+        pytest.skip("bbi modules not built in oracle/_ref")
+    s, e, v, rs, re_, size = synth.summarize_case(seed)
+    sd = SummarizedData(rs, re_, size)
+    bbi_shim.accumulate(sd, s.tolist(), e.tolist(), v.tolist())
+    o = orc.summarize(s, e, v, rs, re_, size, 0.0, 0.0)
+    for k in o:
+        assert np.array_equal(o[k].view(np.uint64), getattr(sd, k).view(np.uint64)), k
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_span_loop_vs_reference_binned_array(seed):
+    from bx_python_b200 import synth, wiggle
+    _ref_pure_python()
+    import bx.wiggle
+    from bx.binned_array import BinnedArray
+    text = synth.wiggle_text(seed)
+    arrays = {}
+    for chrom, pos, val in bx.wiggle.Reader(io.StringIO(text)):
+        arrays.setdefault(chrom, BinnedArray(bin_size=1024, max_size=8192))[pos] = val
+    assert repr(list(wiggle.IntervalReader(io.StringIO(text)))) == repr(list(bx.wiggle.IntervalReader(io.StringIO(text))))
+    spans = wiggle.read_spans(io.StringIO(text))
+    for chrom, ba in arrays.items():
+        t = np.full(8192, np.nan, np.float32)
+        orc.scores_set_spans(t, 0, *spans[chrom])
+        assert np.array_equal(t.view(np.uint32), ba.get_range(0, 8192).view(np.uint32))
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(100, 106))
+def test_join_vs_reference(seed):
+    from bx_python_b200 import synth
+    _ref_pure_python()
+    from bx.intervals.io import NiceReaderWrapper
+    from bx.intervals.operations.join import join
+    left, right, mincols = synth.join_case(seed, nl=60, nr=70)
+
+    def rd(lines):
+        return NiceReaderWrapper(io.StringIO("\n".join(lines) + "\n"), chrom_col=0, start_col=1, end_col=2, fix_strand=True)
+    rows = [r for r in join(rd(left), rd(right), mincols=mincols, leftfill=False, rightfill=False) if isinstance(r, list)]
+    lf = [ln.split("\t") for ln in left if not ln.startswith("#")]
+    rf = [ln.split("\t") for ln in right]
+    cid = {}
+    it = [cid.setdefault(r[0], len(cid)) for r in rf]
+    qt = [cid.get(r[0], -1) for r in lf]
+    off, items, _ = orc.join(it, [int(r[1]) for r in rf], [int(r[2]) for r in rf], qt, [int(r[1]) for r in lf],
+                             [int(r[2]) for r in lf], mincols)
+    mine = sorted(lf[q] + rf[i] for q in range(len(lf)) for i in items[off[q]:off[q + 1]].tolist())
+    assert mine == sorted(rows)
