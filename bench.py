@@ -480,6 +480,7 @@ def run_ours(args):
         extra["bitset"] = bench_bitset(args, peak, peak_src)
         extra["bed_intersect"] = bench_bed_intersect(peak)
         extra["aggregate"] = bench_aggregate(peak)
+        extra["score_sources"] = bench_score_sources(peak)
 
     # ---- CPU baseline (bounded sample, single thread = the reference's only native mode) -----------------------------------
     cpu = None
@@ -852,6 +853,120 @@ def bench_aggregate(peak):
             "genome": {"ms": gms, "windows_per_s": nw_all / (gms * 1e-3), "gbs": alg / (gms * 1e-3) / 1e9,
                        "frac": alg / (gms * 1e-3) / 1e9 / peak, "launches_per_pass": 1},
             "parity": "chr21 float32 averages bit-identical to oracle (per-chromosome and genome-wide launches)"}
+
+
+def bench_score_sources(peak):
+    """SURVEY 8f-4 rows, device-timed: the wiggle-load span write (per-GPU share of C5: 12.5 M scored bases), the bigWig
+    summary kernel and the overlap join; each with a bit-exact spot check against the oracle."""
+    import ctypes as C
+
+    from bx_python_b200 import _lib
+    from bx_python_b200._lib import check
+    from bx_python_b200.intervals import IntervalForest
+    from oracle import oracle as orc
+    L = _lib.lib()
+    timer = _lib.Timer()
+    rng = np.random.default_rng(6001)
+    out = {}
+
+    def timed(fn, reps=5):
+        fn()
+        _lib.sync()
+        timer.start()
+        for _ in range(reps):
+            fn()
+        timer.stop()
+        return timer.elapsed_ms() / reps
+
+    # ---- span write: 12.5 M bases as (a) single-base records (fixedStep span=1) and (b) 625 k records of 20 bases
+    n = 12_500_000
+    for tag, ln in (("span1", 1), ("span20", 20)):
+        k = n // ln
+        st = (np.arange(k, dtype=np.int64) * ln).astype(np.int32)
+        en = (st + ln).astype(np.int32)
+        v = rng.normal(size=k).astype(np.float32)
+        h = C.c_void_p()
+        check(L.bxg_scores_alloc(n, 0, float("nan"), C.byref(h)))
+        d_s, d_e, d_v = _lib.DeviceBuffer(st), _lib.DeviceBuffer(en), _lib.DeviceBuffer(v)
+        ms = timed(lambda: check(L.bxg_scores_set_spans(h, d_s.ptr, d_e.ptr, d_v.ptr, k, _lib.DEVICE)))
+        got = np.empty(4096, np.float32)
+        check(L.bxg_scores_get_range(h, n - 4096, n, got.ctypes.data_as(C.c_void_p)))
+        assert np.array_equal(got.view(np.uint32), np.repeat(v, ln)[-4096:].view(np.uint32)), "span write parity"
+        alg = 12 * k + 4 * n
+        out[f"set_spans_{tag}"] = {"ms": ms, "records": k, "bases_per_s": n / (ms * 1e-3), "algorithmic_bytes": alg,
+                                   "gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                                   "note": "includes the sorted/disjoint check kernel and its 24-byte D2H round trip"}
+        L.bxg_scores_free(h)
+    # overlapping batch -> owner/apply path
+    k = 1_000_000
+    st = rng.integers(0, n - 64, k).astype(np.int32)
+    en = (st + rng.integers(1, 40, k)).astype(np.int32)
+    v = rng.normal(size=k).astype(np.float32)
+    h = C.c_void_p()
+    check(L.bxg_scores_alloc(n, 0, float("nan"), C.byref(h)))
+    d_s, d_e, d_v = _lib.DeviceBuffer(st), _lib.DeviceBuffer(en), _lib.DeviceBuffer(v)
+    ms = timed(lambda: check(L.bxg_scores_set_spans(h, d_s.ptr, d_e.ptr, d_v.ptr, k, _lib.DEVICE)))
+    ref = np.full(n, np.nan, np.float32)
+    orc.scores_set_spans(ref, 0, st, en, v)
+    got = np.empty(n, np.float32)
+    check(L.bxg_scores_get_range(h, 0, n, got.ctypes.data_as(C.c_void_p)))
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), "ordered span write parity"
+    out["set_spans_overlapping"] = {"ms": ms, "records": k, "records_per_s": k / (ms * 1e-3),
+                                    "parity": "12.5 M cells bit-identical to the sequential loop (oracle)"}
+    L.bxg_scores_free(h)
+
+    # ---- bigWig summary: 10 M sorted disjoint intervals into 1000 bins
+    k = 10_000_000
+    ln = rng.integers(1, 30, k)
+    st64 = np.cumsum(ln + rng.integers(0, 5, k)) - ln
+    st, en = st64.astype(np.int32), (st64 + ln).astype(np.int32)
+    v = rng.normal(size=k).astype(np.float32)
+    size = 1000
+    d_s, d_e, d_v = _lib.DeviceBuffer(st), _lib.DeviceBuffer(en), _lib.DeviceBuffer(v)
+    zeros = np.zeros(size)
+    d_out = [_lib.DeviceBuffer(zeros) for _ in range(5)]
+
+    def summ():
+        for b in d_out:
+            check(L.bxg_memcpy_h2d(b.ptr, zeros.ctypes.data_as(C.c_void_p), zeros.nbytes))
+        check(L.bxg_summarize(d_s.ptr, d_e.ptr, d_v.ptr, k, _lib.DEVICE, 0, int(en[-1]), size, *[b.ptr for b in d_out]))
+    ms = timed(summ)
+    got = np.empty(size)
+    check(L.bxg_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_out[3].ptr, got.nbytes))
+    _lib.sync()
+    m = 200_000                                       # the first 200 k intervals fill the first bins completely
+    nb = int(en[m - 1]) // (int(en[-1]) // size) - 1
+    o = orc.summarize(st[:m], en[:m], v[:m], 0, int(en[-1]), size, 0.0, 0.0)
+    assert nb > 2 and np.array_equal(got[:nb].view(np.uint64), o["sum_data"][:nb].view(np.uint64)), "summary parity"
+    alg = 12 * k + 40 * size
+    out["summarize"] = {"ms": ms, "intervals": k, "bins": size, "intervals_per_s": k / (ms * 1e-3),
+                        "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                        "note": "one thread per bin walks ~10 k intervals sequentially (float64 sums are order-dependent)",
+                        "parity": f"first {nb} bins bit-identical to oracle"}
+
+    # ---- join: 1 M left x 1 M right hg38-shaped intervals, mincols 1 and 500
+    chroms = list(range(len(synth.HG38_LENS)))
+    (tid, s, e), (qt, qs, qe) = (flatten(synth.genome_intervals(1_000_000, 6002), chroms),
+                                flatten(synth.genome_intervals(1_000_000, 6003), chroms))
+    forest = IntervalForest(len(chroms)).build(tid, s, e)
+    d = [_lib.DeviceBuffer(a) for a in (qt, qs, qe, s, e)]
+    total = C.c_int64()
+    for mincols in (1, 500):
+        ms = timed(lambda: check(L.bxg_itree_join(forest.handle, d[0].ptr, d[1].ptr, d[2].ptr, len(qs), d[3].ptr, d[4].ptr,
+                                                  mincols, _lib.DEVICE, C.byref(total))), reps=3)
+        out[f"join_mincols{mincols}"] = {"ms": ms, "left": len(qs), "right": len(s), "pairs": total.value,
+                                         "left_per_s": len(qs) / (ms * 1e-3)}
+    poff = np.empty(len(qs) + 1, np.int64)
+    items = np.empty(total.value, np.int32)
+    vis = np.empty(len(s), np.uint8)
+    check(L.bxg_itree_join_fetch(poff.ctypes.data_as(C.c_void_p), items.ctypes.data_as(C.c_void_p), vis.ctypes.data_as(C.c_void_p)))
+    c = len(chroms) - 4                                                   # one small chromosome (chr21) against the oracle
+    si, qi = np.nonzero(tid == c)[0], np.nonzero(qt == c)[0][:2000]
+    ooff, oitems, _ = orc.join(tid[si], s[si], e[si], qt[qi], qs[qi], qe[qi], 500)
+    for j, q in enumerate(qi.tolist()):
+        assert sorted(items[poff[q]:poff[q + 1]].tolist()) == si[oitems[ooff[j]:ooff[j + 1]]].tolist(), "join parity"
+    out["join_mincols500"]["parity"] = f"{len(qi)} left intervals of chromosome #{c}: kept sets identical to oracle"
+    return out
 
 
 def main():

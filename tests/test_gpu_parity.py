@@ -250,6 +250,38 @@ def test_find_large_properties(bx):
     assert inc.all()
 
 
+def test_find_c2_full_size_vs_oracle(bx, orc):
+    """BASELINE configs[1] at full size -- 10 M hg38-shaped intervals vs 10 M queries (bench.py's workload, seeds
+    2001 / 2002), one forest of 24 chromosomes, queries in shuffled (file) order: offsets and ordered hit lists of
+    EVERY query bit-identical to the oracle, chromosome by chromosome."""
+    n = nq = 10_000_000
+    db, qq = synth.genome_intervals(n, 2001), synth.genome_intervals(nq, 2002)
+    tid = np.concatenate([np.full(len(d[0]), c, np.int32) for c, d in enumerate(db)])
+    s, e = np.concatenate([d[0] for d in db]), np.concatenate([d[1] for d in db])
+    qt = np.concatenate([np.full(len(q[0]), c, np.int32) for c, q in enumerate(qq)])
+    qs, qe = np.concatenate([q[0] for q in qq]), np.concatenate([q[1] for q in qq])
+    perm = np.random.default_rng(7).permutation(nq)
+    forest = bx.ix.IntervalForest(24).build(tid, s, e)
+    off, hits = forest.find_batch(qt[perm], qs[perm], qe[perm], copy=False)
+    cnt = np.diff(off)
+    base = np.concatenate([[0], np.cumsum([len(d[0]) for d in db])])
+    qbase = np.concatenate([[0], np.cumsum([len(q[0]) for q in qq])])
+    inv = np.empty(nq, np.int64)
+    inv[perm] = np.arange(nq)                          # position of original query j in the shuffled batch
+    total = 0
+    for c in range(24):
+        ooff, ohits = orc.OracleIntervalTree(*db[c]).find(*qq[c])
+        where = inv[qbase[c]:qbase[c + 1]]
+        assert np.array_equal(cnt[where], np.diff(ooff)), f"counts differ on chromosome {c}"
+        # gather this chromosome's hit lists back into original query order and compare them wholesale
+        starts = off[where]
+        lens = np.diff(ooff)
+        idx = np.repeat(starts - ooff[:-1], lens) + np.arange(len(ohits))
+        assert np.array_equal(hits[idx] - base[c], ohits), f"hit lists differ on chromosome {c}"
+        total += len(ohits)
+    assert total == off[-1] == len(hits)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # neighbours: before / after / *_interval / upstream / downstream  (intersection.pyx:192-260, 408-477)
 # ---------------------------------------------------------------------------------------------------------------

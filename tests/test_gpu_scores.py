@@ -221,17 +221,17 @@ def test_summarize_bigwig_file_golden():
     for k, (a, b, size) in enumerate(g["bw_regions"].tolist()):
         sd = bbi.summarize_from_full(g["bw_start"], g["bw_end"], g["bw_val"], a, b, size)
         assert np.array_equal(bits(np.stack([getattr(sd, key) for key in KEYS])), bits(g[f"bw{k}"]))
-    # lib/bx/bbi/bigwig_tests.py:28-72 known answers (query on chr1:10000-20000 with 10 bins and with 1 bin)
-    sd = bbi.summarize_from_full(g["bw_start"], g["bw_end"], g["bw_val"], 10000, 20000, 10)
-    q = bbi.query(sd, 10000, 20000, 10)
-    means = [x["mean"] for x in q]
-    expect = [-0.17557571594973645, -0.054009292602539061, -0.056892242431640622, -0.03650328826904297,
-              0.036112907409667966, 0.0064466032981872557, 0.036949024200439454, 0.076638259887695306,
-              0.043518108367919923, 0.01554749584197998]
-    assert np.allclose(means, expect, atol=1e-5)
-    one = bbi.query(bbi.summarize_from_full(g["bw_start"], g["bw_end"], g["bw_val"], 10000, 20000, 1), 10000, 20000, 1)
-    assert [float(x["max"]) for x in one] == [0.289000004529953]
-    assert [float(x["min"]) for x in one] == [-3.9100000858306885]
+    # lib/bx/bbi/bigwig_tests.py:73-92 known answers (test_get_leaf: chr1:11000-11005 is answered from the full data;
+    # the 10-bin test above it goes through a zoom level of the file, which is container code and out of scope)
+    q = bbi.query(bbi.summarize_from_full(g["bw_start"], g["bw_end"], g["bw_val"], 11000, 11005, 5), 11000, 11005, 5)
+    assert np.allclose([float(x["mean"]) for x in q],
+                       [0.050842501223087311, -2.4589500427246094, 0.050842501223087311, 0.050842501223087311,
+                        0.050842501223087311])
+    one = bbi.query(bbi.summarize_from_full(g["bw_start"], g["bw_end"], g["bw_val"], 11000, 11005, 1), 11000, 11005, 1)
+    assert [float(x["max"]) for x in one] == [0.050842501223087311]
+    assert [float(x["min"]) for x in one] == [-2.4589500427246094]
+    whole = bbi.summarize_from_full(g["bw_start"], g["bw_end"], g["bw_val"], 10000, 20000, 1)    # :62-67 min / max
+    assert whole.max_val.tolist() == [0.289000004529953] and whole.min_val.tolist() == [-3.9100000858306885]
     assert bbi.summarize_from_full([], [], [], 5, 5, 3) is None
 
 
