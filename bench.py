@@ -660,8 +660,9 @@ def bench_scalar_api(db):
         b.count_range(1000 * k, 1500)
     count_us = (time.perf_counter() - t0) / n * 1e6
     return {"find_us_per_call": find_us, "count_range_us_per_call": count_us,
-            "note": "scalar IntervalTree.find / BinnedBitSet.count_range go through one kernel launch + copy each; "
-                    "the reference's Cython calls take ~1-4 us -- bulk callers must use the batched methods"}
+            "note": "scalar IntervalTree.find / BinnedBitSet.count_range = one launch + one synchronise each (arguments by value / "
+                    "mapped pinned memory, results written by the kernel into mapped pinned memory: no copies); the reference's "
+                    "Cython calls take ~1-4 us -- bulk callers should still use the batched methods"}
 
 
 def bench_pcie():
@@ -941,7 +942,7 @@ def bench_score_sources(peak):
     alg = 12 * k + 40 * size
     out["summarize"] = {"ms": ms, "intervals": k, "bins": size, "intervals_per_s": k / (ms * 1e-3),
                         "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
-                        "note": "one thread per bin walks ~10 k intervals sequentially (float64 sums are order-dependent)",
+                        "note": "one warp per bin: 32 intervals weighed in parallel, folded in file order by one lane (float64 sums are order-dependent)",
                         "parity": f"first {nb} bins bit-identical to oracle"}
 
     # ---- join: 1 M left x 1 M right hg38-shaped intervals, mincols 1 and 500

@@ -127,7 +127,25 @@ class _DeviceBits:
 
     def _get(self, index):
         self._check_index(index)
-        return int(self.get_many(np.array([index], np.int32))[0])
+        self._flush()
+        a = self._scalar_io()
+        a[0][0] = index
+        check(a[3].bxg_bits_read(self._h, a[0], 1, a[4], _lib.HOST))
+        return a[4][0]
+
+    def _scalar_io(self):
+        """Reusable ctypes cells for the one-element calls (no numpy arrays on the scalar path)."""
+        a = getattr(self, "_sio", None)
+        if a is None:
+            a = self._sio = ((C.c_int32 * 1)(), (C.c_int32 * 1)(), (C.c_int32 * 1)(), _lib.lib(), (C.c_uint8 * 1)())
+        return a
+
+    def _count_one(self, start, count, strict):
+        self._flush()
+        a = self._scalar_io()
+        a[0][0], a[1][0] = start, count
+        check(a[3].bxg_bits_count_ranges(self._h, a[0], a[1], 1, a[2], 1 if strict else 0, _lib.HOST))
+        return a[2][0]
 
     def __getitem__(self, index):
         return self._get(index)
@@ -293,7 +311,7 @@ class BitSet(_DeviceBits):
         if count is None:
             count = self._size - start
         self._check_range_count(start, count)
-        return int(self.count_ranges(np.array([start], np.int32), np.array([count], np.int32))[0])
+        return self._count_one(start, count, True)
 
     def _check_range(self, start, end):
         self._check_index(start)
@@ -347,7 +365,7 @@ class BinnedBitSet(_DeviceBits):
 
     def count_range(self, start, count):
         self._check_range_count(start, count)
-        return int(self.count_ranges(np.array([start], np.int32), np.array([count], np.int32), self._strict)[0])
+        return self._count_one(start, count, self._strict)
 
     def count_ranges(self, starts, counts, strict=None):
         return super().count_ranges(starts, counts, self._strict if strict is None else strict)

@@ -625,6 +625,13 @@ int bxg_bits_set_bits(bxg_bits_t *b, const int32_t *pos, int64_t n, int value, i
 int bxg_bits_read(const bxg_bits_t *b, const int32_t *pos, int64_t n, uint8_t *out, int loc) {
     if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
     if (n <= 0) return BXG_OK;
+    if (zc_small(loc, n)) {                 // __getitem__ of one position: no staging copies (common.cuh)
+        memcpy(zc_host(0), pos, (size_t)n * 4);
+        BXG_LAUNCH(k_read_bits, 1, 64, 0, b->words, (const int32_t *)zc_device(0), n, (uint8_t *)zc_device(1));
+        BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+        memcpy(out, zc_host(1), (size_t)n);
+        return BXG_OK;
+    }
     const void *dp;
     BXG_TRY(stage_in(0, pos, (size_t)n * 4, loc, &dp));
     uint8_t *dout = out;
@@ -771,6 +778,15 @@ int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *co
     if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
     if (n <= 0) return BXG_OK;
     BXG_TRY(build_rank(b));
+    if (zc_small(loc, n)) {                 // the scalar count_range(start, count): no staging copies (common.cuh)
+        memcpy(zc_host(0), start, (size_t)n * 4);
+        memcpy(zc_host(1), count, (size_t)n * 4);
+        BXG_LAUNCH(k_count_ranges, 1, 256, 0, b->words, b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0,
+                   (const int32_t *)zc_device(0), (const int32_t *)zc_device(1), n, (int32_t *)zc_device(2));
+        BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+        memcpy(out, zc_host(2), (size_t)n * 4);
+        return BXG_OK;
+    }
     const void *ds, *dc;
     BXG_TRY(stage_in(0, start, (size_t)n * 4, loc, &ds));
     BXG_TRY(stage_in(1, count, (size_t)n * 4, loc, &dc));

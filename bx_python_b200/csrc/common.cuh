@@ -21,6 +21,9 @@ struct Context {
     // small pinned host mailbox for scalar results
     int64_t *mailbox = nullptr;     // 64 x int64, pinned
     int64_t *d_mailbox = nullptr;   // 64 x int64, device
+    // 4 KB of mapped pinned memory: tiny host arrays of scalar-style calls are read / written by the kernel in place
+    // (no staging copies) -- see zc_small()
+    char *zc = nullptr, *zc_dev = nullptr;
     void *l2_flush_buf = nullptr;
     size_t l2_flush_bytes = 0;
 };
@@ -67,6 +70,13 @@ static inline int grid_for(int64_t ctas_needed, int ctas_per_sm) {
     if (ctas_needed < 1) ctas_needed = 1;
     return (int)(ctas_needed < cap ? ctas_needed : cap);
 }
+
+// Scalar-style calls (a handful of positions in host memory, answer needed at once) skip the staging copies: inputs
+// are memcpy'd into the mapped pinned page, the kernel reads and writes it over PCIe, one synchronise ends the call.
+constexpr int64_t ZC_MAX_ITEMS = 64;          // per array; the page holds 4 arrays of 64 x 8 bytes + slack
+static inline bool zc_small(int loc, int64_t n) { return loc == BXG_HOST && n <= ZC_MAX_ITEMS && ctx().zc != nullptr; }
+static inline void *zc_host(int k) { return ctx().zc + (size_t)k * 512; }
+static inline void *zc_device(int k) { return ctx().zc_dev + (size_t)k * 512; }
 
 // Stage a caller array onto the device if it lives on the host; returns the device pointer to use.
 int stage_in(int slot, const void *src, size_t bytes, int loc, const void **dptr);

@@ -79,6 +79,9 @@ struct bxg_itree {
     unsigned int *d_ticket = nullptr;       // MAX_CHUNKS + 1
     long long *d_result = nullptr;          // 2 x (MAX_CHUNKS + 1)
     long long *h_result = nullptr;          // pinned mirror
+    // small-batch path (bxg_itree_find_small): results land in mapped pinned memory, written by the kernel itself
+    long long *m_off = nullptr;             // SMALL_Q + 1 offsets, then an overflow flag
+    int32_t *m_hits = nullptr;              // SMALL_CAP hit ids
     // the staged query arrays of the last find (device pointers valid until the next call)
     IndexView view() const {
         IndexView v;
@@ -684,6 +687,8 @@ int bxg_itree_free(bxg_itree_t *t) {
     cudaFree(t->d_ticket);
     cudaFree(t->d_result);
     if (t->h_result) cudaFreeHost(t->h_result);
+    if (t->m_off) cudaFreeHost(t->m_off);
+    if (t->m_hits) cudaFreeHost(t->m_hits);
     delete t;
     return BXG_OK;
 }
@@ -1210,6 +1215,85 @@ static int find_mode() {
 int bxg_set_find_mode(int mode) {
     if (mode < -1 || mode > 1) return set_error(BXG_ERR_ARG, "find mode must be -1 (auto), 0 (three-pass) or 1 (single-pass)");
     g_find_mode = mode;
+    return BXG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Small batches (the scalar IntervalTree.find of the reference API, one Python call per query): the general path costs
+// two staged uploads, three launches and two downloads over three streams -- ~70 us for ONE query.  Here the queries
+// travel as kernel arguments, one warp answers up to 32 of them (one lane each: count walk, warp scan, emit walk) and
+// writes the CSR straight into mapped pinned host memory: one launch, one stream synchronise, no copies.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SMALL_Q = 32;
+constexpr int SMALL_CAP = 1 << 16;
+struct SmallQueries {
+    int32_t t[SMALL_Q], qs[SMALL_Q], qe[SMALL_Q];
+};
+
+__global__ void __launch_bounds__(32)
+k_find_small(IndexView ix, SmallQueries a, int nq, long long *__restrict__ out_off, int32_t *__restrict__ out_hits) {
+    const int q = threadIdx.x;
+    uint32_t lo = 0, hi = 0;
+    int32_t qs = 0;
+    int c = 0;
+    if (q < nq) {
+        const int32_t t = a.t[q], qe = a.qe[q];
+        qs = a.qs[q];
+        if (t >= 0 && t < ix.ntrees) {
+            const uint32_t seg_lo = (uint32_t)ix.toff[t], seg_hi = (uint32_t)ix.toff[t + 1];
+            bxs::dual_search(ix.KS, ix.KP, ix.nk, ix.spS, ix.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo,
+                             bxs::NoPrefetch(), 1, true);
+            bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t, unsigned m) { c += __popc(m); });
+        }
+    }
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (q >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (q < nq) out_off[q] = incl - c;
+    if (q == 0) {
+        out_off[nq] = total;
+        out_off[SMALL_Q + 1] = total > SMALL_CAP;             // overflow: the host re-runs the general path
+    }
+    if (total > SMALL_CAP || c == 0) return;
+    int32_t *dst = out_hits + (incl - c);
+    bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
+                   [&](uint32_t k0, unsigned m) { dst = bxs::emit_group(ix.I, k0, m, dst, Ld4()); });
+}
+
+int bxg_itree_find_small(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int32_t nq,
+                         const int64_t **offsets, const int32_t **hits, int64_t *total) {
+    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
+    if (nq < 0 || nq > SMALL_Q) return set_error(BXG_ERR_ARG, "bxg_itree_find_small takes 0..%d queries", SMALL_Q);
+    Context &c = ctx();
+    if (!t->m_off) {
+        BXG_CUDA(cudaHostAlloc((void **)&t->m_off, (SMALL_Q + 2) * sizeof(long long), cudaHostAllocMapped));
+        BXG_CUDA(cudaHostAlloc((void **)&t->m_hits, (size_t)SMALL_CAP * 4, cudaHostAllocMapped));
+    }
+    if (nq == 0 || t->n == 0) {
+        for (int q = 0; q <= nq; q++) t->m_off[q] = 0;
+    } else {
+        SmallQueries a;
+        for (int q = 0; q < nq; q++) {
+            a.t[q] = qtree ? qtree[q] : 0;
+            a.qs[q] = qs[q];
+            a.qe[q] = qe[q];
+        }
+        long long *d_off;
+        int32_t *d_hits;
+        BXG_CUDA(cudaHostGetDevicePointer((void **)&d_off, t->m_off, 0));
+        BXG_CUDA(cudaHostGetDevicePointer((void **)&d_hits, t->m_hits, 0));
+        BXG_LAUNCH(k_find_small, 1, 32, 0, t->view(), a, (int)nq, d_off, d_hits);
+        BXG_CUDA(cudaStreamSynchronize(c.stream));
+        if (t->m_off[SMALL_Q + 1])                   // more than SMALL_CAP hits: the general path has no such limit
+            return bxg_itree_find_host(t, qtree, qs, qe, nq, offsets, hits, total);
+    }
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+    if (offsets) *offsets = (const int64_t *)t->m_off;
+    if (hits) *hits = t->m_hits;
+    if (total) *total = t->m_off[nq];
     return BXG_OK;
 }
 

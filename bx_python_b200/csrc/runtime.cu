@@ -129,6 +129,11 @@ int bxg_init(int device) {
     BXG_CUDA(cudaMallocHost(&c.mailbox, 64 * sizeof(int64_t)));
     BXG_CUDA(cudaMalloc(&c.d_mailbox, 64 * sizeof(int64_t)));
     BXG_CUDA(cudaMemset(c.d_mailbox, 0, 64 * sizeof(int64_t)));
+    if (cudaHostAlloc((void **)&c.zc, 4096, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&c.zc_dev, c.zc, 0) != cudaSuccess) {
+        cudaGetLastError();                    // no mapped memory on this platform: scalar calls use the staged path
+        c.zc = c.zc_dev = nullptr;
+    }
     c.device = device;
     c.launches = 0;
     return BXG_OK;

@@ -9,9 +9,10 @@
 //   the spans are written directly.  Otherwise an `owner` array over the batch's bounding range takes
 //   atomicMax(span index + 1) per base and a second sweep copies the winner's value: same result as the sequential
 //   loop, no dependence on thread order.
-// * bigWig summaries (lib/bx/bbi/bbi_file.pyx:66-111, SummarizedData.accumulate_interval_value): one thread per
-//   summary bin walks the intervals that reach it in file order with the reference's exact float64 expression
-//   sequence (no fma contraction), so valid_count / sum / sum_squares / min / max are bit-identical.
+// * bigWig summaries (lib/bx/bbi/bbi_file.pyx:66-111, SummarizedData.accumulate_interval_value): one warp per
+//   summary bin weighs the intervals that reach it 32 at a time and folds them into the bin in file order with the
+//   reference's exact float64 expression sequence (no fma contraction), so valid_count / sum / sum_squares / min /
+//   max are bit-identical.
 #include <math.h>
 
 #include "scores.cuh"
@@ -28,13 +29,16 @@ __global__ void __launch_bounds__(256) k_scores_fill(float *__restrict__ v, int6
 // over the non-empty spans (as offsets from `origin`, biased so that 0 means "no span")
 __global__ void __launch_bounds__(256)
 k_spans_check(const int32_t *__restrict__ start, const int32_t *__restrict__ end, int64_t n, int64_t origin, int64_t len,
-              unsigned long long *__restrict__ flags) {
+              int no_empty, unsigned long long *__restrict__ flags) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int bad = 0, oob = 0;
     long long lo = INT64_MAX, hi = INT64_MIN;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int64_t s = __ldg(start + i), e = end ? (int64_t)__ldg(end + i) : s + 1;
-        if (e <= s) continue;                          // range(start, end) is empty: nothing is assigned
+        if (e <= s) {                                  // range(start, end) is empty: nothing is assigned
+            if (no_empty) bad = 1;                     // ... but a caller that bisects on `end` cannot have it
+            continue;
+        }
         if (s - origin < 0 || e - origin > len) oob = 1;
         lo = s < lo ? s : lo;
         hi = e > hi ? e : hi;
@@ -140,17 +144,26 @@ k_scores_gather(const float *__restrict__ v, int64_t n, int64_t origin, float fi
 // in file order.  All arithmetic in the reference's order and types: `overlap` int, overlap_factor = overlap /
 // interval_size (double), interval_weight = interval_size * overlap_factor, val a C float (so val * val is rounded to
 // float before it is widened).  SORTED: the batch is sorted by start and disjoint (what a bigWig file holds), so
-// the intervals reaching a bin are one contiguous run found by binary search; otherwise every thread scans the batch.
+// the intervals reaching a bin are one contiguous run found by binary search; otherwise every bin scans the batch.
+//
+// One WARP per bin: the 32 lanes load and weigh 32 consecutive intervals at a time (coalesced loads, the divisions and
+// products in parallel -- they do not depend on the running sums), park the three terms in shared memory, and lane 0
+// then folds them into the bin's state strictly in file order (the float64 sums and the `<` / `>` updates of min / max
+// are order-dependent, down to the sign of a zero).  The next batch's loads are issued before the fold.
+constexpr int SUMM_WARPS = 4;
 template <bool SORTED>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * SUMM_WARPS)
 k_summarize(const int32_t *__restrict__ start, const int32_t *__restrict__ end, const float *__restrict__ val, int64_t n,
             int64_t rs, int64_t re, int32_t size, double *__restrict__ valid, double *__restrict__ mn,
             double *__restrict__ mx, double *__restrict__ sum, double *__restrict__ sq) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= size) return;
+    __shared__ double s_w[SUMM_WARPS][32], s_t1[SUMM_WARPS][32], s_t2[SUMM_WARPS][32], s_v[SUMM_WARPS][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int j = blockIdx.x * SUMM_WARPS + wib;
+    if (j >= size) return;                          // whole warp leaves together
     const int64_t step = (re - rs) / size;
     const int64_t b0 = rs + step * j, b1 = b0 + step;
-    double vc = valid[j], lo = mn[j], hi = mx[j], sm = sum[j], ss = sq[j];     // accumulate INTO the caller's state
+    double vc = 0.0, lo = 0.0, hi = 0.0, sm = 0.0, ss = 0.0;
+    if (lane == 0) { vc = valid[j]; lo = mn[j]; hi = mx[j]; sm = sum[j]; ss = sq[j]; }   // accumulate INTO the caller's state
     int64_t i0 = 0;
     if (SORTED) {                                   // first interval with end > b0 (ends ascend too)
         int64_t a = 0, b = n;
@@ -158,27 +171,54 @@ k_summarize(const int32_t *__restrict__ start, const int32_t *__restrict__ end, 
             const int64_t m = (a + b) >> 1;
             if ((int64_t)(uint32_t)__ldg(end + m) > b0) b = m; else a = m + 1;
         }
-        i0 = a;
+        i0 = a & ~31ll;                             // aligned batches: 128-byte coalesced loads
     }
-    for (int64_t i = i0; i < n; i++) {
-        int64_t s = (uint32_t)__ldg(start + i), e = (uint32_t)__ldg(end + i);      // bits32 in the reference
-        if (SORTED && s >= b1) break;
-        if (s < rs) s = rs;
-        if (e > re) e = re;
-        if (s >= e) continue;
-        const int64_t ov = (e < b1 ? e : b1) - (s > b0 ? s : b0);
-        if (ov <= 0) continue;
-        const float vf = __ldg(val + i);
-        const double v = (double)vf;
-        const double isz = (double)(int32_t)(e - s);
-        const double w = __dmul_rn(isz, __ddiv_rn((double)(int32_t)ov, isz));
-        vc = __dadd_rn(vc, w);
-        sm = __dadd_rn(sm, __dmul_rn(v, w));
-        ss = __dadd_rn(ss, __dmul_rn((double)__fmul_rn(vf, vf), w));
-        if (hi < v) hi = v;
-        if (lo > v) lo = v;
+    int64_t ns = 0, ne = 0;
+    float nv = 0.0f;
+    if (i0 + lane < n) { ns = (uint32_t)__ldg(start + i0 + lane); ne = (uint32_t)__ldg(end + i0 + lane); nv = __ldg(val + i0 + lane); }
+    for (int64_t base = i0; base < n; base += 32) {
+        int64_t s = ns, e = ne;                     // bits32 in the reference
+        const float vf = nv;
+        const bool live = base + lane < n;
+        if (SORTED && __shfl_sync(0xffffffffu, s, 0) >= b1) break;      // every later interval starts past the bin
+        if (base + 32 + lane < n) {                 // prefetch the next batch
+            ns = (uint32_t)__ldg(start + base + 32 + lane); ne = (uint32_t)__ldg(end + base + 32 + lane); nv = __ldg(val + base + 32 + lane);
+        }
+        bool has = false;
+        if (live) {
+            if (s < rs) s = rs;
+            if (e > re) e = re;
+            if (s < e) {
+                const int64_t ov = (e < b1 ? e : b1) - (s > b0 ? s : b0);
+                if (ov > 0) {
+                    has = true;
+                    const double v = (double)vf;
+                    const double isz = (double)(int32_t)(e - s);
+                    const double w = __dmul_rn(isz, __ddiv_rn((double)(int32_t)ov, isz));
+                    s_w[wib][lane] = w;
+                    s_t1[wib][lane] = __dmul_rn(v, w);
+                    s_t2[wib][lane] = __dmul_rn((double)__fmul_rn(vf, vf), w);
+                    s_v[wib][lane] = v;
+                }
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, has);
+        __syncwarp();
+        if (lane == 0) {
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                const double v = s_v[wib][k];
+                vc = __dadd_rn(vc, s_w[wib][k]);
+                sm = __dadd_rn(sm, s_t1[wib][k]);
+                ss = __dadd_rn(ss, s_t2[wib][k]);
+                if (hi < v) hi = v;
+                if (lo > v) lo = v;
+            }
+        }
+        __syncwarp();
     }
-    valid[j] = vc; mn[j] = lo; mx[j] = hi; sum[j] = sm; sq[j] = ss;
+    if (lane == 0) { valid[j] = vc; mn[j] = lo; mx[j] = hi; sum[j] = sm; sq[j] = ss; }
 }
 
 static int fill_range(bxg_scores *s, int64_t a, int64_t b) {
@@ -259,7 +299,7 @@ int bxg_scores_set_spans(bxg_scores_t *s, const int32_t *start, const int32_t *e
     c.mailbox[18] = INT64_MIN;
     BXG_CUDA(cudaMemcpyAsync(flags, c.mailbox + 16, 24, cudaMemcpyHostToDevice, c.stream));
     const int g = grid_for(cdiv(n, 256), 8);
-    BXG_LAUNCH(k_spans_check, g, 256, 0, (const int32_t *)ds, (const int32_t *)de, n, (int64_t)s->origin, s->n, flags);
+    BXG_LAUNCH(k_spans_check, g, 256, 0, (const int32_t *)ds, (const int32_t *)de, n, (int64_t)s->origin, s->n, 0, flags);
     BXG_CUDA(cudaMemcpyAsync(c.mailbox + 16, flags, 24, cudaMemcpyDeviceToHost, c.stream));
     BXG_CUDA(cudaStreamSynchronize(c.stream));
     const int64_t fl = c.mailbox[16], lo = c.mailbox[17], hi = c.mailbox[18];
@@ -354,7 +394,7 @@ int bxg_summarize(const int32_t *start, const int32_t *end, const float *val, in
         c.mailbox[18] = INT64_MIN;
         BXG_CUDA(cudaMemcpyAsync(flags, c.mailbox + 16, 24, cudaMemcpyHostToDevice, c.stream));
         BXG_LAUNCH(k_spans_check, grid_for(cdiv(n, 256), 8), 256, 0, (const int32_t *)ds, (const int32_t *)de, n,
-                   (int64_t)INT32_MIN, (int64_t)1 << 33, flags);
+                   (int64_t)INT32_MIN, (int64_t)1 << 33, 1, flags);
         BXG_CUDA(cudaMemcpyAsync(c.mailbox + 16, flags, 8, cudaMemcpyDeviceToHost, c.stream));
         BXG_CUDA(cudaStreamSynchronize(c.stream));
         sorted = (c.mailbox[16] & 1) == 0;
@@ -374,10 +414,10 @@ int bxg_summarize(const int32_t *start, const int32_t *end, const float *val, in
         BXG_CUDA(cudaMemcpyAsync(dsq, sum_squares, (size_t)size * 8, cudaMemcpyHostToDevice, st));
     }
     if (sorted)
-        BXG_LAUNCH(k_summarize<true>, (int)cdiv(size, 128), 128, 0, (const int32_t *)ds, (const int32_t *)de,
+        BXG_LAUNCH(k_summarize<true>, (int)cdiv(size, SUMM_WARPS), 32 * SUMM_WARPS, 0, (const int32_t *)ds, (const int32_t *)de,
                    (const float *)dv, n, (int64_t)rstart, (int64_t)rend, size, d, dmn, dmx, dsm, dsq);
     else
-        BXG_LAUNCH(k_summarize<false>, (int)cdiv(size, 128), 128, 0, (const int32_t *)ds, (const int32_t *)de,
+        BXG_LAUNCH(k_summarize<false>, (int)cdiv(size, SUMM_WARPS), 32 * SUMM_WARPS, 0, (const int32_t *)ds, (const int32_t *)de,
                    (const float *)dv, n, (int64_t)rstart, (int64_t)rend, size, d, dmn, dmx, dsm, dsq);
     if (loc == BXG_HOST) {
         cudaStream_t st = c.stream;

@@ -98,6 +98,7 @@ class _DeviceIndex:
 
     def __init__(self):
         self._h = C.c_void_p()
+        self._one = None
         check(_lib.lib().bxg_itree_create(C.byref(self._h)))
 
     def __del__(self):
@@ -123,6 +124,17 @@ class _DeviceIndex:
         if copy:
             return off.copy(), hits.copy()
         return off, hits
+
+    def find_one(self, start, end, tree=0):
+        """One query through the low-latency path (bxg_itree_find_small): -> list of item indices."""
+        a = self._one
+        if a is None:
+            a = self._one = ((C.c_int32 * 1)(), (C.c_int32 * 1)(), (C.c_int32 * 1)(), C.c_void_p(), C.c_void_p(), C.c_int64())
+            self._one_fn = _lib.lib().bxg_itree_find_small
+        a[0][0], a[1][0], a[2][0] = tree, start, end
+        check(self._one_fn(self._h, a[0], a[1], a[2], 1, C.byref(a[3]), C.byref(a[4]), C.byref(a[5])))
+        n = a[5].value
+        return (C.c_int32 * n).from_address(a[4].value)[:] if n else []
 
     def count(self, qtree, qs, qe):
         out = np.empty(len(qs), np.int32)
@@ -188,10 +200,9 @@ class IntervalTree:
         """Return a sorted list of all intervals overlapping [start,end)."""
         if not self._starts:
             return []
-        qs, qe = np.array([_c_int(start)], np.int32), np.array([_c_int(end)], np.int32)
-        _, hits = self._ensure().find(None, qs, qe)
+        hits = self._ensure().find_one(_c_int(start), _c_int(end))
         v = self._values
-        return [v[i] for i in hits.tolist()]
+        return [v[i] for i in hits]
 
     def find_batch(self, starts, ends):
         """-> (offsets int64[nq+1], hits int32[total]): item indices (insertion order) per query, reference order."""

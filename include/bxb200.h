@@ -172,6 +172,12 @@ int bxg_set_find_mode(int mode);
  * host buffers owned by the index and stay valid until its next find or bxg_itree_free. */
 int bxg_itree_find_host(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
                         const int64_t **offsets, const int32_t **hits, int64_t *total);
+/* Up to 32 queries with the latency of one launch and one synchronise: the scalar `IntervalTree.find(start, end)`
+ * (intersection.pyx:400-406) called once per line by scripts such as bed_count_overlapping.py:27-33.  Host arrays only;
+ * the CSR is written by the kernel into mapped pinned memory owned by the index (valid until its next find).  Falls
+ * back to bxg_itree_find_host when the queries have more than 65536 hits in total. */
+int bxg_itree_find_small(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int32_t nq,
+                         const int64_t **offsets, const int32_t **hits, int64_t *total);
 int bxg_itree_result_dev(const bxg_itree_t *t, const int64_t **d_offsets, const int32_t **d_hits, int64_t *nq,
                          int64_t *total);
 /* len(find(...)) only (scripts/bed_count_overlapping.py:27-33): int32 counts[nq] written to `counts` (host or device

@@ -250,6 +250,37 @@ def test_find_large_properties(bx):
     assert inc.all()
 
 
+def test_find_small_path(bx, orc):
+    """bxg_itree_find_small (the scalar IntervalTree.find route): up to 32 queries answered by one warp into mapped
+    pinned memory; identical CSR to the batched path, incl. the fallback when more than 65536 hits come back."""
+    import ctypes as C
+    L = bx.lib.lib()
+    rng = np.random.default_rng(21)
+    s, e = synth.uniform_intervals(rng, 50_000, 2_000_000)
+    tid = (np.arange(len(s)) % 3).astype(np.int32)
+    forest = bx.ix.IntervalForest(3).build(tid, s, e)
+    for nq in (0, 1, 2, 31, 32):
+        qs, qe = synth.uniform_intervals(rng, max(nq, 1), 2_000_000)
+        qs, qe = qs[:nq].copy(), qe[:nq].copy()
+        qt = rng.integers(-1, 4, nq).astype(np.int32)                 # -1 and 3 are not trees: no hits
+        p_off, p_hits, total = C.c_void_p(), C.c_void_p(), C.c_int64()
+        bx.lib.check(L.bxg_itree_find_small(forest.handle, bx.lib.ptr(qt), bx.lib.ptr(qs), bx.lib.ptr(qe), nq,
+                                            C.byref(p_off), C.byref(p_hits), C.byref(total)))
+        off = np.frombuffer((C.c_int64 * (nq + 1)).from_address(p_off.value), np.int64).copy()
+        hits = np.frombuffer((C.c_int32 * max(total.value, 1)).from_address(p_hits.value), np.int32)[:total.value].copy()
+        eoff, ehits = forest.find_batch(qt, qs, qe)
+        assert np.array_equal(off, eoff) and np.array_equal(hits, ehits)
+    # scalar API on a single tree against the oracle, incl. an answer too large for the mapped buffer
+    t = tree_of(bx, s, e)
+    o = orc.OracleIntervalTree(s, e)
+    for a, b in ((0, 2_000_000), (1000, 1001), (5, 5), (1_999_999, 3_000_000), (-10, 0)):
+        assert t.find(a, b) == o.find([a], [b])[1].tolist()
+    big = bx.ix.IntervalTree()
+    big.insert_many(np.zeros(70_000, np.int32), np.full(70_000, 10, np.int32))
+    assert big.find(0, 5) == list(range(70_000))                     # > 65536 hits: falls back to the general path
+    assert big.find(10, 20) == []
+
+
 def test_find_c2_full_size_vs_oracle(bx, orc):
     """BASELINE configs[1] at full size -- 10 M hg38-shaped intervals vs 10 M queries (bench.py's workload, seeds
     2001 / 2002), one forest of 24 chromosomes, queries in shuffled (file) order: offsets and ordered hit lists of
