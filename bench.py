@@ -443,13 +443,15 @@ def run_ours(args):
         # per launch, bytes that must move (DESIGN.md "algorithmic bytes"):
         # count pass: read (chrom,start,end) 12 B/query, write (count,lo,hi,mask) 20 B/query, read S,E once 8 B/item
         # (the PM array itself is no longer read: coarse lo)
-        "k_find<false>": 32 * nq + 8 * n_items,
+        "k_find<false, true>": 32 * nq + 8 * n_items,     # probe search (default)
+        "k_find<false, false>": 32 * nq + 8 * n_items,    # two lock-step searches (BXB200_FIND_PROBE=0)
         # fill pass: read lo,mask,offset 20 B/query, read I + write hit 8 B/hit (E is not read again: mask stash)
-        "k_find<true>": 20 * nq + 8 * hits_total,
+        "k_find<true, false>": 20 * nq + 8 * hits_total,
         "k_fill_staged": 20 * nq + 8 * hits_total,         # same bytes; stores staged through shared memory
         # single-pass kernel: read (chrom,start,end) 12 B/query, write offset 8 B/query, S,E once 8 B/item,
         # read I + write hit 8 B/hit
-        "k_find_fused": 20 * nq + 8 * n_items + 8 * hits_total,
+        "k_find_fused<true>": 20 * nq + 8 * n_items + 8 * hits_total,
+        "k_find_fused<false>": 20 * nq + 8 * n_items + 8 * hits_total,
     }
     kern = {}
     for name, (n_l, tot_ms) in prof.items():

@@ -241,6 +241,72 @@ struct Ld4 {
 struct Ld1 {
     __device__ __forceinline__ int32_t operator()(const int32_t *p) const { return __ldg(p); }
 };
+// one aligned 32-byte sector (8 entries): a single LDG.E.256
+struct Ld8 {
+    __device__ __forceinline__ void operator()(const int4 *p, int4 &a, int4 &b) const {
+        asm("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+    }
+};
+// L2 residency.  The count pass streams 12 B/query in and 20 B/query out (320 MB per 10 M queries) past an index of
+// ~85 MB (S, E, the sampled levels) that every query reads at random; with default caching the streams keep pushing
+// index lines out of the 126 MB L2 and the kernel re-reads them from HBM (r01q: 854 MB of DRAM reads against ~205 MB
+// of distinct data).  So index loads carry an evict_last policy, and the per-query streams use .cs (evict-first)
+// accesses.  -DFIND_L2_HINTS=0 restores plain accesses for A/B runs.
+#ifndef FIND_L2_HINTS
+#define FIND_L2_HINTS 1
+#endif
+#if FIND_L2_HINTS
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+struct LdK4 {
+    uint64_t pol;
+    __device__ __forceinline__ LdK4() : pol(l2_keep_policy()) {}
+    __device__ __forceinline__ void operator()(const int4 *p, int4 &a, int4 &b, int4 &c, int4 &d) const {
+        asm("ld.global.nc.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+            : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p), "l"(pol));
+        asm("ld.global.nc.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+            : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(p + 2), "l"(pol));
+    }
+};
+struct LdK8 {
+    uint64_t pol;
+    __device__ __forceinline__ LdK8() : pol(l2_keep_policy()) {}
+    __device__ __forceinline__ void operator()(const int4 *p, int4 &a, int4 &b) const {
+        asm("ld.global.nc.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+            : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p), "l"(pol));
+    }
+};
+__device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldcs(p); }
+__device__ __forceinline__ unsigned long long ld_stream(const unsigned long long *p) { return __ldcs(p); }
+__device__ __forceinline__ long long ld_stream(const long long *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream_q(int32_t *p, int32_t v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream_q(unsigned long long *p, unsigned long long v) { __stcs(p, v); }
+#else
+typedef Ld4 LdK4;
+typedef Ld8 LdK8;
+__device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldg(p); }
+__device__ __forceinline__ unsigned long long ld_stream(const unsigned long long *p) { return *p; }
+__device__ __forceinline__ long long ld_stream(const long long *p) { return *p; }
+__device__ __forceinline__ void st_stream_q(int32_t *p, int32_t v) { *p = v; }
+__device__ __forceinline__ void st_stream_q(unsigned long long *p, unsigned long long v) { *p = v; }
+#endif
+
+// PROBE selects search_walk_probe (one search + backward probe of KP[1], half-group walk: ~10 sectors per query)
+// over search_walk (two lock-step searches: ~13); identical results, kept switchable (BXB200_FIND_PROBE=0) for A/B runs
+template <bool PROBE, typename SP, typename F>
+__device__ __forceinline__ void query_search_walk(const IndexView &ix, const SP &spS, const SP &spPM, uint32_t seg_lo,
+                                                  uint32_t seg_hi, int32_t qe, int32_t qs, uint32_t &hi, uint32_t &lo, F &&f) {
+    if (PROBE)
+        bxs::search_walk_probe(ix.KS, ix.KP, ix.nk, spS, spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdK4(),
+                               LdK8(), Ld1(), hi, lo, f);
+    else
+        bxs::search_walk(ix.KS, ix.KP, ix.nk, spS, spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdK4(), Ld1(),
+                         hi, lo, f);
+}
 __device__ __forceinline__ const SmemIndex stage_index(const IndexView &ix, unsigned char *smem_raw) {
     // layout: [mbarrier 8 B][pad 8 B][spS nsplit_pad x 4][spPM nsplit_pad x 4][toff (ntrees+1) x 8]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -285,7 +351,7 @@ struct MaskStash {
     }
 };
 
-template <bool FILL>
+template <bool FILL, bool PROBE>
 __global__ void __launch_bounds__(FIND_THREADS, FIND_MIN_CTAS)
 k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, const int32_t *__restrict__ qs_, const int32_t *__restrict__ qe_,
        int64_t nq, int32_t *__restrict__ cnt, int32_t *__restrict__ lo_, int32_t *__restrict__ hi_,
@@ -309,19 +375,18 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
         const int64_t c_off = n_off;
         if (FILL && q + stride < nq) { n_lo = lo_[q + stride]; n_m = mask_[q + stride]; n_off = off[q + stride]; }
         if (!FILL) {
-            const int32_t qs = __ldg(qs_ + q), qe = __ldg(qe_ + q), t = qtree ? __ldg(qtree + q) : 0;
+            const int32_t qs = ld_stream(qs_ + q), qe = ld_stream(qe_ + q), t = qtree ? ld_stream(qtree + q) : 0;
             uint32_t lo = 0, hi = 0;
             MaskStash st;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
                 // hi: candidates (start < qe) end here; lo: coarse start of the walk (running max end > qs from here on)
-                bxs::search_walk(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev,
-                                 Ld4(), Ld1(), hi, lo, st);
+                query_search_walk<PROBE>(ix, sm.spS, sm.spPM, seg_lo, seg_hi, qe, qs, hi, lo, st);
             }
-            cnt[q] = st.c;
-            lo_[q] = (int32_t)((st.c ? st.base : lo) | (st.overflow ? WALK_AGAIN : 0u));
-            hi_[q] = (int32_t)hi;
-            mask_[q] = st.m;
+            cnt[q] = st.c;                                 // read again right away by the scan: keep it cached
+            st_stream_q(lo_ + q, (int32_t)((st.c ? st.base : lo) | (st.overflow ? WALK_AGAIN : 0u)));
+            st_stream_q(hi_ + q, (int32_t)hi);
+            st_stream_q(mask_ + q, st.m);
             local += (unsigned long long)st.c;
         } else {
             const uint32_t lo_raw = (uint32_t)c_a;
@@ -405,7 +470,7 @@ k_fill_staged(const __grid_constant__ IndexView ix, const int32_t *__restrict__ 
         uint32_t lo_raw = 0;
         unsigned long long m = 0;
         int64_t o = off_end;
-        if (valid) { lo_raw = (uint32_t)lo_[q]; m = mask_[q]; o = off[q]; }
+        if (valid) { lo_raw = (uint32_t)ld_stream(lo_ + q); m = ld_stream(mask_ + q); o = ld_stream((const long long *)off + q); }
         int64_t o_next = __shfl_down_sync(0xffffffffu, o, 1);
         if (lane == 31) o_next = valid ? off[q + 1] : off_end;
         const int64_t span0 = __shfl_sync(0xffffffffu, o, 0);
@@ -418,7 +483,7 @@ k_fill_staged(const __grid_constant__ IndexView ix, const int32_t *__restrict__ 
             }
             __syncwarp();
             int32_t *dst = hits + span0;
-            for (int i = lane; i < (int)span; i += 32) dst[i] = buf[i];
+            for (int i = lane; i < (int)span; i += 32) st_stream_q(dst + i, buf[i]);
             __syncwarp();
         } else if (o_next > o) {
             bxs::PtrSink out{hits + o};
@@ -453,6 +518,7 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 
+template <bool PROBE>
 __global__ void __launch_bounds__(FUSED_THREADS, FIND_MIN_CTAS)
 k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, const int32_t *__restrict__ qs_,
              const int32_t *__restrict__ qe_, int64_t nq, int64_t *__restrict__ off, int32_t *__restrict__ hits,
@@ -482,8 +548,7 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
             const int32_t t = qtree ? __ldg(qtree + q) : 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
-                bxs::search_walk(ix.KS, ix.KP, ix.nk, sm.spS, sm.spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev,
-                                 Ld4(), Ld1(), hi, lo, st);
+                query_search_walk<PROBE>(ix, sm.spS, sm.spPM, seg_lo, seg_hi, qe, qs, hi, lo, st);
                 c = st.c;
             }
         }
@@ -590,22 +655,40 @@ static int ensure_query_buffers(bxg_itree *t, int64_t nq) {
     return BXG_OK;
 }
 
+static bool find_probe() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BXB200_FIND_PROBE");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // pass A over queries [q0, q0+nq): searches + per-query hit counts into d_cnt/d_lo/d_hi[q0..]
 static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t nq,
                         unsigned long long *d_total, int64_t q0 = 0) {
     size_t smem = find_smem_bytes(t);
     static bool attr_set = false;
     if (!attr_set) {
-        BXG_CUDA(cudaFuncSetAttribute(k_find<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        BXG_CUDA(cudaFuncSetAttribute(k_find<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        BXG_CUDA(cudaFuncSetAttribute(k_find<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set = true;
     }
     // persistent grid: exactly the CTAs that are co-resident (whole waves only), grid-stride over the queries
     int occ = 0;
-    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<false>, FIND_THREADS, smem));
-    int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
-    BXG_LAUNCH((k_find<false>), grid, FIND_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, nq,
-               t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, t->d_mask + q0, (const int64_t *)nullptr, (int32_t *)nullptr,
-               d_total);
+    if (find_probe()) {
+        BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<false, true>, FIND_THREADS, smem));
+        int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
+        BXG_LAUNCH((k_find<false, true>), grid, FIND_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0,
+                   nq, t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, t->d_mask + q0, (const int64_t *)nullptr,
+                   (int32_t *)nullptr, d_total);
+    } else {
+        BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<false, false>, FIND_THREADS, smem));
+        int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
+        BXG_LAUNCH((k_find<false, false>), grid, FIND_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0,
+                   nq, t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, t->d_mask + q0, (const int64_t *)nullptr,
+                   (int32_t *)nullptr, d_total);
+    }
     return BXG_OK;
 }
 
@@ -624,9 +707,9 @@ static int launch_fill(bxg_itree *t, const int32_t *dqs, int64_t nq, int64_t q0 
                    (const int64_t *)(t->d_off + q0), t->d_hits);
         return BXG_OK;
     }
-    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<true>, FIND_THREADS, 0));
+    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<true, false>, FIND_THREADS, 0));
     int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
-    BXG_LAUNCH((k_find<true>), grid, FIND_THREADS, 0, t->view(), (const int32_t *)nullptr, dqs + q0,
+    BXG_LAUNCH((k_find<true, false>), grid, FIND_THREADS, 0, t->view(), (const int32_t *)nullptr, dqs + q0,
                (const int32_t *)nullptr, nq, t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, t->d_mask + q0,
                (const int64_t *)(t->d_off + q0), t->d_hits, (unsigned long long *)nullptr);
     return BXG_OK;
@@ -1059,15 +1142,24 @@ static int launch_fused(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
     size_t smem = find_smem_bytes(t);
     static bool attr_set = false;
     if (!attr_set) {
-        BXG_CUDA(cudaFuncSetAttribute(k_find_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        BXG_CUDA(cudaFuncSetAttribute(k_find_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        BXG_CUDA(cudaFuncSetAttribute(k_find_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set = true;
     }
     int occ = 0;
-    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_fused, FUSED_THREADS, smem));
-    int grid = grid_for(ntiles, occ > 0 ? occ : 1);     // every CTA is resident: the look-back cannot starve
-    BXG_LAUNCH(k_find_fused, grid, FUSED_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, n,
-               t->d_off + q0, t->d_hits, t->hits_cap, (const int64_t *)(t->d_off + q0), t->d_tiles + tile0,
-               t->d_ticket + slot, t->d_result + 2 * slot);
+    if (find_probe()) {
+        BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_fused<true>, FUSED_THREADS, smem));
+        int grid = grid_for(ntiles, occ > 0 ? occ : 1);     // every CTA is resident: the look-back cannot starve
+        BXG_LAUNCH(k_find_fused<true>, grid, FUSED_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, n,
+                   t->d_off + q0, t->d_hits, t->hits_cap, (const int64_t *)(t->d_off + q0), t->d_tiles + tile0,
+                   t->d_ticket + slot, t->d_result + 2 * slot);
+    } else {
+        BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_fused<false>, FUSED_THREADS, smem));
+        int grid = grid_for(ntiles, occ > 0 ? occ : 1);
+        BXG_LAUNCH(k_find_fused<false>, grid, FUSED_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, n,
+                   t->d_off + q0, t->d_hits, t->hits_cap, (const int64_t *)(t->d_off + q0), t->d_tiles + tile0,
+                   t->d_ticket + slot, t->d_result + 2 * slot);
+    }
     return BXG_OK;
 }
 

@@ -288,6 +288,156 @@ BXG_HD void search_walk(const int32_t *const *KS, const int32_t *const *KP, int 
     if (g0 + 16u < hi) walk_hits(E, M, nlev, lo, hi, qs, ld4, ld, f, NoPrefetch(), 1, g0 + 16u, mask == 0);
 }
 
+// ---- search + walk, second form: ONE search, then a backward probe for the walk's start ---------------------------
+//
+// The count kernels are bound by L1 data-pipe wavefronts -- one per 32-byte sector a lane touches (ncu, profiles/).
+// search_walk spends 13.3 sectors per query: three 64-byte rounds for `hi` (6), two for the coarse `lo` (4), and the E
+// groups of the walk (~3.3).  But `lo` is almost always within a few groups of `hi`: a query reaches back at most by
+// the length of the longest interval still "open" there.  So instead of searching PM from the top, look at the sampled
+// running maxima right in front of hi: KP[1][j] = PM[16 j].  If PM[16 j] <= qs, every item up to 16 j ends at or
+// before qs, i.e. the true lo is beyond 16 j and 16 j is a valid (coarse, aligned) start for the walk.  One 32-byte
+// sector of KP[1] holds 8 such samples = 128 items of reach, and its address is known BEFORE the last S round
+// resolves (hi - 1 lies in the <= 16-item window that round looks at), so the probe is issued together with the
+// final S group.  If no sample of the sector qualifies the probe steps back one sector at a time (twice), then falls
+// back to the full PM search -- long intervals in front pay that, short-interval data never does.
+// Sectors per query: 6 (S) + 1 (probe) + the walk; the walk itself loads only the 32-byte halves of an E group that
+// intersect [lo, hi) (walk_hits_halves).
+template <typename LD8>
+BXG_HD unsigned sector_mask_le(const int32_t *p, int32_t key, const LD8 &ld8) {
+    int4 a, b;
+    ld8(reinterpret_cast<const int4 *>(p), a, b);
+    return (unsigned)(a.x <= key) | (unsigned)(a.y <= key) << 1 | (unsigned)(a.z <= key) << 2 | (unsigned)(a.w <= key) << 3 |
+           (unsigned)(b.x <= key) << 4 | (unsigned)(b.y <= key) << 5 | (unsigned)(b.z <= key) << 6 | (unsigned)(b.w <= key) << 7;
+}
+
+BXG_HD int fls8(unsigned x) {   // 0-based index of the highest set bit of a non-zero 8-bit mask
+    int i = 0;
+    if (x & 0xf0u) { i += 4; x >>= 4; }
+    if (x & 0x0cu) { i += 2; x >>= 2; }
+    if (x & 0x02u) i += 1;
+    return i;
+}
+
+// walk_hits with half-group loads: of each aligned 16-item group only the 8-item halves that intersect [lo, hi) are
+// read (one 32-byte sector each); a half that is not read contributes no hits.
+template <typename LD8, typename LD, typename F>
+BXG_HD void walk_hits_halves(const int32_t *E, const int32_t *const *M, int nlev, uint32_t lo, uint32_t hi, int32_t qs,
+                             const LD8 &ld8, const LD &ld, F &&f) {
+    if (lo >= hi) return;
+    uint32_t k = lo & ~15u;
+    bool prev_empty = false;
+    while (k < hi) {
+        if (prev_empty && (k & 31u) == 0 && k + 32u <= hi && ld(M[0] + (k >> 5)) <= qs) {
+            uint32_t idx = k >> 5;
+            int lvl = 0;
+            while (lvl + 1 < nlev && (idx & 31u) == 0) {
+                const uint32_t up = idx >> 5;
+                const uint64_t span_end = ((uint64_t)up + 1) << (5 * (lvl + 2));
+                if (span_end > hi || ld(M[lvl + 1] + up) > qs) break;
+                idx = up;
+                lvl++;
+            }
+            k = (idx + 1u) << (5 * (lvl + 1));
+            continue;
+        }
+        unsigned mask = 0;
+        if (lo < k + 8u) mask |= 0xffu & ~sector_mask_le(E + k, qs, ld8);                         // E > qs, items k..k+7
+        if (hi > k + 8u && lo < k + 16u) mask |= (0xffu & ~sector_mask_le(E + k + 8, qs, ld8)) << 8;
+        if (k < lo) mask &= ~0u << (lo - k);
+        if (k + 16u > hi) mask &= (1u << (hi - k)) - 1u;
+        prev_empty = mask == 0;
+        if (mask) f(k, mask);
+        k += 16;
+    }
+}
+
+template <typename SP, typename LD4, typename LD8, typename LD, typename F>
+BXG_HD void search_walk_probe(const int32_t *const *KS, const int32_t *const *KP, int nk, const SP &spS, const SP &spPM,
+                              int shift, uint32_t seg_lo, uint32_t seg_hi, int32_t qe, int32_t qs, const int32_t *E,
+                              const int32_t *const *M, int nlev, const LD4 &ld4, const LD8 &ld8, const LD &ld,
+                              uint32_t &hi_out, uint32_t &lo_out, F &&f) {
+    if (nk < 2) {                                      // small index: no sampled level to probe
+        search_walk(KS, KP, nk, spS, spPM, shift, seg_lo, seg_hi, qe, qs, E, M, nlev, ld4, ld, hi_out, lo_out, f);
+        return;
+    }
+    hi_out = lo_out = seg_hi;
+    if (seg_lo >= seg_hi) return;
+    const uint32_t k0 = (seg_lo + (1u << shift) - 1) >> shift, k1 = ((seg_hi - 1) >> shift) + 1;
+    uint32_t a_s = k0;
+    uint32_t step0 = 0;
+    if (k0 < k1) {
+        step0 = 1;
+        while (step0 * 2 <= k1 - k0) step0 *= 2;
+        for (uint32_t step = step0; step > 0; step >>= 1) a_s = lift_step<false>(spS, a_s, step, k1, qe);
+    }
+    Win ws = splitter_window(a_s, k0, k1, shift, seg_lo, seg_hi);
+    for (int j = nk - 1; j >= 1; j--) {
+        const int ss = 4 * j;
+        const Round rs = round_prepare(ws, ss);
+        if (rs.active) {
+            int4 s0, s1, s2, s3;
+            ld4(reinterpret_cast<const int4 *>(KS[j] + rs.g), s0, s1, s2, s3);
+            round_apply(ws, rs, ss, group_mask<false>(s0, s1, s2, s3, qe));
+        }
+    }
+    // final S round; the probe sector is chosen from the window's upper end (hi - 1 <= ws.hi - 1) and loaded with it
+    const Round rs = round_prepare(ws, 0);
+    uint32_t sb = ((ws.hi ? ws.hi - 1u : 0u) >> 4) & ~7u;
+    int4 s0{}, s1{}, s2{}, s3{};
+    if (rs.active) ld4(reinterpret_cast<const int4 *>(KS[0] + rs.g), s0, s1, s2, s3);
+    unsigned pm_le = sector_mask_le(KP[1] + sb, qs, ld8);
+    if (rs.active) round_apply(ws, rs, 0, group_mask<false>(s0, s1, s2, s3, qe));
+    const uint32_t hi = finish_binary<false>(KS[0], ws, qe, ld);
+    hi_out = lo_out = hi;
+    if (hi <= seg_lo) return;                          // no item starts before qe
+    const uint32_t m_hi = (hi - 1u) >> 4;              // group of the last candidate
+    if (m_hi < sb) {                                   // hi resolved into the group in front of the probed sector
+        sb = m_hi & ~7u;
+        pm_le = sector_mask_le(KP[1] + sb, qs, ld8);
+    }
+    uint32_t lo_c = 0;
+    bool found = false;
+    for (int tries = 0; tries < 3; tries++) {
+        // samples of this sector that belong to this tree (16 j >= seg_lo) and are not past the last candidate
+        unsigned valid = 0xffu;
+        if (m_hi < sb + 7u) valid &= (2u << (m_hi - sb)) - 1u;
+        const uint32_t jmin = (seg_lo + 15u) >> 4;     // first sample position inside the segment
+        if (jmin > sb) valid &= (jmin - sb >= 8u) ? 0u : (~0u << (jmin - sb));
+        const unsigned ok = pm_le & valid;
+        if (ok) {
+            lo_c = (sb + (uint32_t)fls8(ok)) << 4;
+            found = true;
+            break;
+        }
+        if (jmin >= sb) {                              // ran off the front of the tree: everything before is another tree
+            lo_c = seg_lo;
+            found = true;
+            break;
+        }
+        if (tries == 2) break;
+        sb -= 8u;
+        pm_le = sector_mask_le(KP[1] + sb, qs, ld8);
+    }
+    if (!found) {                                      // something long is open in front: the full PM search (coarse)
+        uint32_t a_p = k0;
+        for (uint32_t step = step0; step > 0; step >>= 1) a_p = lift_step<true>(spPM, a_p, step, k1, qs);
+        Win wp = splitter_window(a_p, k0, k1, shift, seg_lo, seg_hi);
+        for (int j = nk - 1; j >= 1; j--) {
+            const int ss = 4 * j;
+            const Round rp = round_prepare(wp, ss);
+            if (rp.active) {
+                int4 p0, p1, p2, p3;
+                ld4(reinterpret_cast<const int4 *>(KP[j] + rp.g), p0, p1, p2, p3);
+                round_apply(wp, rp, ss, group_mask<true>(p0, p1, p2, p3, qs));
+            }
+        }
+        lo_c = wp.lo;
+    }
+    const uint32_t lo = lo_c < hi ? lo_c : hi;
+    lo_out = lo;
+    walk_hits_halves(E, M, nlev, lo, hi, qs, ld8, ld, f);
+}
+
 // Write the item ids of the hits of one 16-item group: the whole aligned group of I is fetched with four 16-byte
 // loads issued back to back (one 64-byte line), THEN the selected ids are stored -- a load per hit interleaved with
 // the stores would serialise on every store (the compiler must assume hits[] may alias I[]).

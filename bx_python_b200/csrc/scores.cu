@@ -5,10 +5,10 @@
 //   host shim (it only shows through get_bin_offset / nbins).
 // * Wiggle load (scripts/aggregate_scores_in_intervals.py:60-70 over lib/bx/wiggle.py:16-85): the reference assigns
 //   `scores[chrom][pos] = val` one base at a time in file order, so when spans overlap the LAST one in the file wins.
-//   k_spans_check decides on the device whether the batch is sorted and disjoint (every real wiggle file is); then
-//   the spans are written directly.  Otherwise an `owner` array over the batch's bounding range takes
-//   atomicMax(span index + 1) per base and a second sweep copies the winner's value: same result as the sequential
-//   loop, no dependence on thread order.
+//   k_spans_write stores every span directly and checks in the same pass whether the batch is sorted and disjoint
+//   (every real wiggle file is) -- then each cell was written once and the job is done.  Otherwise an `owner` array
+//   over the batch's bounding range takes atomicMax(span index + 1) per base and a second sweep copies the winner's
+//   value over the speculative stores: same result as the sequential loop, no dependence on thread order.
 // * bigWig summaries (lib/bx/bbi/bbi_file.pyx:66-111, SummarizedData.accumulate_interval_value): one warp per
 //   summary bin weighs the intervals that reach it 32 at a time and folds them into the bin in file order with the
 //   reference's exact float64 expression sequence (no fma contraction), so valid_count / sum / sum_squares / min /
@@ -64,23 +64,42 @@ k_spans_check(const int32_t *__restrict__ start, const int32_t *__restrict__ end
     }
 }
 
-// sorted + disjoint batch: each span is written exactly once, no ordering question.  One lane per span for the
-// first 8 bases; longer spans are finished by the whole warp with coalesced stores.
+// The common case in one pass: write every span as if the batch were sorted and disjoint (then each cell is written
+// exactly once and order is moot) WHILE checking that it is -- same flags as k_spans_check.  If the check fails the
+// host runs the owner / apply passes afterwards: they rewrite exactly the cells touched here with the correct winner,
+// so the speculative stores do no harm.  Spans outside the track are flagged and not written.
+// One lane per span for the first 8 bases; longer spans are finished by the whole warp with coalesced stores.
 __global__ void __launch_bounds__(256)
-k_spans_write(float *__restrict__ v, int64_t origin, const int32_t *__restrict__ start, const int32_t *__restrict__ end,
-              const float *__restrict__ val, int64_t n) {
+k_spans_write(float *__restrict__ v, int64_t origin, int64_t len, const int32_t *__restrict__ start,
+              const int32_t *__restrict__ end, const float *__restrict__ val, int64_t n,
+              unsigned long long *__restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int bad = 0, oob = 0;
+    long long lo = INT64_MAX, hi = INT64_MIN;
     for (int64_t base = ((((int64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5) << 5; base < n; base += nwarps << 5) {
         const int64_t i = base + lane;
         int64_t a = 0, b = 0;
         float x = 0.0f;
         if (i < n) {
-            a = (int64_t)__ldg(start + i) - origin;
-            b = end ? (int64_t)__ldg(end + i) - origin : a + 1;
-            x = __ldg(val + i);
+            const int64_t s = __ldg(start + i), e = end ? (int64_t)__ldg(end + i) : s + 1;
+            if (e > s) {
+                if (s - origin < 0 || e - origin > len) {
+                    oob = 1;
+                } else {
+                    a = s - origin;
+                    b = e - origin;
+                    x = __ldg(val + i);
+                    lo = s < lo ? s : lo;
+                    hi = e > hi ? e : hi;
+                }
+                if (i > 0) {                       // previous span empty or reaching into this one: not the easy case
+                    const int64_t ps = __ldg(start + i - 1), pe = end ? (int64_t)__ldg(end + i - 1) : ps + 1;
+                    if (pe <= ps || s < pe) bad = 1;
+                }
+            }
         }
-        int64_t head = b - a < 8 ? b : a + 8;
+        const int64_t head = b - a < 8 ? b : a + 8;
         for (int64_t p = a; p < head; p++) v[p] = x;
         unsigned longm = __ballot_sync(0xffffffffu, b - a > 8);
         while (longm) {
@@ -89,6 +108,20 @@ k_spans_write(float *__restrict__ v, int64_t origin, const int32_t *__restrict__
             const int64_t la = __shfl_sync(0xffffffffu, a, src) + 8, lb = __shfl_sync(0xffffffffu, b, src);
             const float lx = __shfl_sync(0xffffffffu, x, src);
             for (int64_t p = la + lane; p < lb; p += 32) v[p] = lx;
+        }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    oob = __any_sync(0xffffffffu, oob);
+    for (int o = 16; o; o >>= 1) {
+        const long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if (lane == 0) {
+        if (bad | oob) atomicOr(flags, (unsigned long long)(bad | (oob << 1)));
+        if (lo != INT64_MAX) {
+            atomicMin((long long *)flags + 1, lo);
+            atomicMax((long long *)flags + 2, hi);
         }
     }
 }
@@ -299,18 +332,14 @@ int bxg_scores_set_spans(bxg_scores_t *s, const int32_t *start, const int32_t *e
     c.mailbox[18] = INT64_MIN;
     BXG_CUDA(cudaMemcpyAsync(flags, c.mailbox + 16, 24, cudaMemcpyHostToDevice, c.stream));
     const int g = grid_for(cdiv(n, 256), 8);
-    BXG_LAUNCH(k_spans_check, g, 256, 0, (const int32_t *)ds, (const int32_t *)de, n, (int64_t)s->origin, s->n, 0, flags);
+    BXG_LAUNCH(k_spans_write, g, 256, 0, s->v, (int64_t)s->origin, s->n, (const int32_t *)ds, (const int32_t *)de,
+               (const float *)dv, n, flags);
     BXG_CUDA(cudaMemcpyAsync(c.mailbox + 16, flags, 24, cudaMemcpyDeviceToHost, c.stream));
     BXG_CUDA(cudaStreamSynchronize(c.stream));
     const int64_t fl = c.mailbox[16], lo = c.mailbox[17], hi = c.mailbox[18];
-    if (fl & 2) return set_error(BXG_ERR_ARG, "span outside the track [%lld, %lld)", (long long)s->origin,
-                                 (long long)(s->origin + s->n));
-    if (lo == INT64_MAX) return BXG_OK;                 // every span empty
-    if (!(fl & 1)) {
-        BXG_LAUNCH(k_spans_write, g, 256, 0, s->v, (int64_t)s->origin, (const int32_t *)ds, (const int32_t *)de,
-                   (const float *)dv, n);
-        return BXG_OK;
-    }
+    if (fl & 2) return set_error(BXG_ERR_ARG, "span outside the track [%lld, %lld) (spans inside it were written)",
+                                 (long long)s->origin, (long long)(s->origin + s->n));
+    if (lo == INT64_MAX || !(fl & 1)) return BXG_OK;    // nothing to write, or sorted and disjoint: done in one pass
     const int64_t m = hi - lo;
     void *owner;
     BXG_TRY(scratch(2, (size_t)m * 4, &owner));

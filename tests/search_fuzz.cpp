@@ -19,6 +19,7 @@ int main(int argc, char **argv) {
     const int trials = argc > 1 ? atoi(argv[1]) : 1500;
     auto ld4 = [](const int4 *p, int4 &a, int4 &b, int4 &c, int4 &d) { a = p[0]; b = p[1]; c = p[2]; d = p[3]; };
     auto ld = [](const int32_t *p) { return *p; };
+    auto ld8 = [](const int4 *p, int4 &a, int4 &b) { a = p[0]; b = p[1]; };
     long checks = 0;
     for (int trial = 0; trial < trials; trial++) {
         const int n = 1 + (int)(rnd() % (trial % 4 == 0 ? 200000 : 3000));
@@ -149,6 +150,27 @@ int main(int argc, char **argv) {
                                          got2.push_back(k0 + b);
                                      }
                                  });
+                // the single-search form with the backward probe for the walk start (what the count kernels run)
+                std::vector<uint32_t> got3;
+                uint32_t hi3, lo3;
+                bxs::search_walk_probe(KS.data(), KP.data(), nk, spS.data(), spPM.data(), shift, toff[t], toff[t + 1], qe,
+                                       qs, E.data(), Mp.data(), (int)Mp.size(), ld4, ld8, ld, hi3, lo3,
+                                       [&](uint32_t k0, unsigned mask) {
+                                           while (mask) {
+                                               int b = bxs::ffs32(mask) - 1;
+                                               mask &= mask - 1;
+                                               got3.push_back(k0 + b);
+                                           }
+                                       });
+                // the naive expectation over the whole candidate range (the probe may start earlier than dual_search's lo)
+                std::vector<uint32_t> want3;
+                for (uint32_t k = toff[t]; k < ehi; k++)
+                    if (E[k] > qs) want3.push_back(k);
+                if (hi3 != ehi || lo3 > std::min(elo, ehi) || lo3 < toff[t] || got3 != want3) {
+                    printf("SEARCH_WALK_PROBE MISMATCH trial %d n=%d nk=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u got=%zu want=%zu\n",
+                           trial, n, nk, toff[t], toff[t + 1], qs, qe, hi3, ehi, lo3, elo, got3.size(), want3.size());
+                    return 1;
+                }
                 if (hi2 != ehi || lo2 > std::min(elo, ehi) || got2 != want) {
                     printf("SEARCH_WALK MISMATCH trial %d n=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u got=%zu want=%zu\n", trial,
                            n, toff[t], toff[t + 1], qs, qe, hi2, ehi, lo2, elo, got2.size(), want.size());
