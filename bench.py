@@ -443,15 +443,14 @@ def run_ours(args):
         # per launch, bytes that must move (DESIGN.md "algorithmic bytes"):
         # count pass: read (chrom,start,end) 12 B/query, write (count,lo,hi,mask) 20 B/query, read S,E once 8 B/item
         # (the PM array itself is no longer read: coarse lo)
-        "k_find<false, true>": 32 * nq + 8 * n_items,     # probe search (default)
-        "k_find<false, false>": 32 * nq + 8 * n_items,    # two lock-step searches (BXB200_FIND_PROBE=0)
+        # (the library's profiler reports the launch macro's text: PROBE is the search variant, BXB200_FIND_PROBE)
+        "k_find<false, PROBE>": 32 * nq + 8 * n_items,
         # fill pass: read lo,mask,offset 20 B/query, read I + write hit 8 B/hit (E is not read again: mask stash)
-        "k_find<true, false>": 20 * nq + 8 * hits_total,
+        "k_find<true, 0>": 20 * nq + 8 * hits_total,
         "k_fill_staged": 20 * nq + 8 * hits_total,         # same bytes; stores staged through shared memory
         # single-pass kernel: read (chrom,start,end) 12 B/query, write offset 8 B/query, S,E once 8 B/item,
         # read I + write hit 8 B/hit
-        "k_find_fused<true>": 20 * nq + 8 * n_items + 8 * hits_total,
-        "k_find_fused<false>": 20 * nq + 8 * n_items + 8 * hits_total,
+        "k_find_fused<PROBE>": 20 * nq + 8 * n_items + 8 * hits_total,
     }
     kern = {}
     for name, (n_l, tot_ms) in prof.items():
@@ -462,7 +461,8 @@ def run_ours(args):
     achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(dom, tj.get(dom.replace("PROBE", os.environ.get("BXB200_FIND_PROBE", "2"))))
     except (OSError, ValueError):
         pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -25,15 +25,22 @@ constexpr int MAX_SPLIT = 4096;        // splitter entries per array (16 KB each
 constexpr int SMEM_TREES = 256;        // toff entries cached in shared memory
 constexpr int FIND_THREADS = 256;
 #ifndef FIND_MIN_CTAS
-#define FIND_MIN_CTAS 4            // co-resident CTAs per SM the find kernels are compiled for (register budget 64)
+#define FIND_MIN_CTAS 6            // co-resident CTAs per SM the find kernels are compiled for (register budget 40):
+                                   // since the 8-ary probe search (7.4 sectors per query) the count kernel is bound by
+                                   // latency, not by L1 wavefronts, and occupancy pays even with a few spills:
+                                   // 4 / 5 / 6 CTAs -> 0.507 / 0.457 / 0.431 ms (profiles/r01s, r01t); shared memory
+                                   // (19.8 KB per CTA) allows no more than 6.  4 was right for the 16-ary searches
 #endif
 
 constexpr int MAX_KLEV = 5;            // 16-ary sampled search levels: strides 1, 16, 256, 4096, 65536
+constexpr int MAX_QLEV = 8;            // 8-ary sampled search levels: strides 1, 8, 64, 512, ... (one 32-byte sector per round)
 
 struct IndexView {
     const int32_t *S, *E, *I, *PM;
     const int32_t *KS[MAX_KLEV], *KP[MAX_KLEV];   // KS[j][i] = S[i << 4j], KP likewise for PM; padded with INT32_MAX
     int32_t nk;                                   // levels in use (K*[0] are S / PM themselves)
+    const int32_t *QS[MAX_QLEV], *QP[MAX_QLEV];   // QS[j][i] = S[i << 3j], QP likewise for PM (8-ary levels)
+    int32_t n8;
     const int32_t *WE, *WI;                       // arrays the walk / the emitter read in 16-item groups (E, I)
     int32_t mul;                                  // their group pitch in 16-int units: 1 (plain arrays; an interleaved
                                                   // [a x16 | b x16] layout, pitch 2, measured slower -- profiles/r01k)
@@ -58,6 +65,9 @@ struct bxg_itree {
     int32_t *KS[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases S
     int32_t *KP[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases PM
     int nk = 1;
+    int32_t *QS[MAX_QLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases S
+    int32_t *QP[MAX_QLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases PM
+    int n8 = 1;
     int32_t *es_end = nullptr, *es_k = nullptr;   // per-tree (end, in-order position) ordering for before(); lazy
     // query-side buffers (grow-only)
     int32_t *d_cnt = nullptr, *d_lo = nullptr, *d_hi = nullptr;
@@ -89,6 +99,8 @@ struct bxg_itree {
         for (int l = 0; l < MAX_LEVELS; l++) v.M[l] = M[l];
         for (int j = 0; j < MAX_KLEV; j++) { v.KS[j] = KS[j]; v.KP[j] = KP[j]; }
         v.nk = nk;
+        for (int j = 0; j < MAX_QLEV; j++) { v.QS[j] = QS[j]; v.QP[j] = QP[j]; }
+        v.QS[0] = S; v.QP[0] = PM; v.n8 = n8;
         v.KS[0] = S; v.KP[0] = PM; v.WE = E; v.WI = I; v.mul = 1;
         v.toff = toff; v.spS = split; v.spPM = split + nsplit_pad;
         v.n = (uint32_t)n; v.ntrees = ntrees; v.nlev = nlev; v.nsplit = nsplit; v.nsplit_pad = nsplit_pad; v.shift = shift;
@@ -295,12 +307,16 @@ __device__ __forceinline__ void st_stream_q(int32_t *p, int32_t v) { *p = v; }
 __device__ __forceinline__ void st_stream_q(unsigned long long *p, unsigned long long v) { *p = v; }
 #endif
 
-// PROBE selects search_walk_probe (one search + backward probe of KP[1], half-group walk: ~10 sectors per query)
-// over search_walk (two lock-step searches: ~13); identical results, kept switchable (BXB200_FIND_PROBE=0) for A/B runs
-template <bool PROBE, typename SP, typename F>
+// PROBE selects the search: 2 = search_walk_probe8 (one search over 8-ary levels + backward probe of QP[1], half-group
+// walk: ~8 sectors per query), 1 = search_walk_probe (the same over the 16-ary levels: ~10), 0 = search_walk (two
+// lock-step searches: ~13); identical results, kept switchable (BXB200_FIND_PROBE) for A/B runs
+template <int PROBE, typename SP, typename F>
 __device__ __forceinline__ void query_search_walk(const IndexView &ix, const SP &spS, const SP &spPM, uint32_t seg_lo,
                                                   uint32_t seg_hi, int32_t qe, int32_t qs, uint32_t &hi, uint32_t &lo, F &&f) {
-    if (PROBE)
+    if (PROBE == 2)
+        bxs::search_walk_probe8(ix.QS, ix.QP, ix.n8, spS, spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdK8(),
+                                Ld1(), hi, lo, f);
+    else if (PROBE == 1)
         bxs::search_walk_probe(ix.KS, ix.KP, ix.nk, spS, spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdK4(),
                                LdK8(), Ld1(), hi, lo, f);
     else
@@ -351,7 +367,7 @@ struct MaskStash {
     }
 };
 
-template <bool FILL, bool PROBE>
+template <bool FILL, int PROBE>
 __global__ void __launch_bounds__(FIND_THREADS, FIND_MIN_CTAS)
 k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, const int32_t *__restrict__ qs_, const int32_t *__restrict__ qe_,
        int64_t nq, int32_t *__restrict__ cnt, int32_t *__restrict__ lo_, int32_t *__restrict__ hi_,
@@ -424,7 +440,9 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
 // L2 tag traffic) become ~27 shared stores plus span/32 full-line stores.  Warps whose span exceeds the window
 // (FILL_STAGE ints) write directly, as k_find<true> does.
 constexpr int FILL_STAGE = 512;
-constexpr int FILL_MIN_CTAS = 5;
+#ifndef FILL_MIN_CTAS
+#define FILL_MIN_CTAS 6            // 4 / 5 / 6 CTAs per SM -> 0.208 / 0.202 / 0.198 ms (profiles/r01t)
+#endif
 
 struct SharedSink {
     uint32_t a;                                           // shared-window byte address
@@ -441,7 +459,7 @@ __device__ __forceinline__ void fill_query(const IndexView &ix, uint32_t lo_raw,
         uint32_t k0 = lo_raw;                                  // 16-aligned position of the first group with a hit
         while (m) {                                            // at most four groups
             const unsigned mk = (unsigned)(m & 0xffffull);
-            if (mk) bxs::emit_group_to(ix.WI, k0, mk, out, Ld4(), ix.mul);
+            if (mk) bxs::emit_group_halves_to(ix.WI, k0, mk, out, Ld8());
             m >>= 16;
             k0 += 16;
         }
@@ -518,7 +536,7 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 
-template <bool PROBE>
+template <int PROBE>
 __global__ void __launch_bounds__(FUSED_THREADS, FIND_MIN_CTAS)
 k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, const int32_t *__restrict__ qs_,
              const int32_t *__restrict__ qe_, int64_t nq, int64_t *__restrict__ off, int32_t *__restrict__ hits,
@@ -624,6 +642,9 @@ static void free_index(bxg_itree *t) {
     for (int j = 1; j < MAX_KLEV; j++) { cudaFree(t->KS[j]); cudaFree(t->KP[j]); }
     for (int j = 0; j < MAX_KLEV; j++) t->KS[j] = t->KP[j] = nullptr;
     t->nk = 1;
+    for (int j = 1; j < MAX_QLEV; j++) { cudaFree(t->QS[j]); cudaFree(t->QP[j]); }
+    for (int j = 0; j < MAX_QLEV; j++) t->QS[j] = t->QP[j] = nullptr;
+    t->n8 = 1;
     cudaFree(t->es_end);
     cudaFree(t->es_k);
     t->es_end = t->es_k = nullptr;
@@ -655,41 +676,42 @@ static int ensure_query_buffers(bxg_itree *t, int64_t nq) {
     return BXG_OK;
 }
 
-static bool find_probe() {
+static int find_probe() {      // 2 (default): 8-ary levels + probe; 1: 16-ary levels + probe; 0: two lock-step searches
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("BXB200_FIND_PROBE");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
     }
-    return v == 1;
+    return v;
 }
 
 // pass A over queries [q0, q0+nq): searches + per-query hit counts into d_cnt/d_lo/d_hi[q0..]
-static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t nq,
-                        unsigned long long *d_total, int64_t q0 = 0) {
+template <int PROBE>
+static int launch_count_as(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t nq,
+                           unsigned long long *d_total, int64_t q0) {
     size_t smem = find_smem_bytes(t);
     static bool attr_set = false;
     if (!attr_set) {
-        BXG_CUDA(cudaFuncSetAttribute(k_find<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        BXG_CUDA(cudaFuncSetAttribute(k_find<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        BXG_CUDA(cudaFuncSetAttribute(k_find<false, PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set = true;
     }
     // persistent grid: exactly the CTAs that are co-resident (whole waves only), grid-stride over the queries
     int occ = 0;
-    if (find_probe()) {
-        BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<false, true>, FIND_THREADS, smem));
-        int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
-        BXG_LAUNCH((k_find<false, true>), grid, FIND_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0,
-                   nq, t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, t->d_mask + q0, (const int64_t *)nullptr,
-                   (int32_t *)nullptr, d_total);
-    } else {
-        BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<false, false>, FIND_THREADS, smem));
-        int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
-        BXG_LAUNCH((k_find<false, false>), grid, FIND_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0,
-                   nq, t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, t->d_mask + q0, (const int64_t *)nullptr,
-                   (int32_t *)nullptr, d_total);
-    }
+    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<false, PROBE>, FIND_THREADS, smem));
+    int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
+    BXG_LAUNCH((k_find<false, PROBE>), grid, FIND_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, nq,
+               t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, t->d_mask + q0, (const int64_t *)nullptr, (int32_t *)nullptr,
+               d_total);
     return BXG_OK;
+}
+
+static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t nq,
+                        unsigned long long *d_total, int64_t q0 = 0) {
+    switch (find_probe()) {
+        case 0: return launch_count_as<0>(t, dqt, dqs, dqe, nq, d_total, q0);
+        case 1: return launch_count_as<1>(t, dqt, dqs, dqe, nq, d_total, q0);
+        default: return launch_count_as<2>(t, dqt, dqs, dqe, nq, d_total, q0);
+    }
 }
 
 // pass B over queries [q0, q0+nq): writes hits at the (global) CSR offsets d_off[q0..]
@@ -707,9 +729,9 @@ static int launch_fill(bxg_itree *t, const int32_t *dqs, int64_t nq, int64_t q0 
                    (const int64_t *)(t->d_off + q0), t->d_hits);
         return BXG_OK;
     }
-    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<true, false>, FIND_THREADS, 0));
+    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<true, 0>, FIND_THREADS, 0));
     int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
-    BXG_LAUNCH((k_find<true, false>), grid, FIND_THREADS, 0, t->view(), (const int32_t *)nullptr, dqs + q0,
+    BXG_LAUNCH((k_find<true, 0>), grid, FIND_THREADS, 0, t->view(), (const int32_t *)nullptr, dqs + q0,
                (const int32_t *)nullptr, nq, t->d_cnt + q0, t->d_lo + q0, t->d_hi + q0, t->d_mask + q0,
                (const int64_t *)(t->d_off + q0), t->d_hits, (unsigned long long *)nullptr);
     return BXG_OK;
@@ -910,6 +932,19 @@ int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, c
         int gk = grid_for(cdiv(nout_pad, 256), 8);
         BXG_LAUNCH(k_sample_level, gk, 256, 0, t->S, n, ss, t->KS[j], nout, nout_pad);
         BXG_LAUNCH(k_sample_level, gk, 256, 0, t->PM, n, ss, t->KP[j], nout, nout_pad);
+    }
+    // 8-ary levels for the single-sector rounds of search_walk_probe8 (strides 8^j; +18 % of S / PM in total)
+    t->QS[0] = t->S;
+    t->QP[0] = t->PM;
+    t->n8 = std::min(MAX_QLEV, std::max(1, (t->shift + 2) / 3));
+    for (int j = 1; j < t->n8; j++) {
+        const int ss = 3 * j;
+        const int64_t nout = cdiv(n, 1ll << ss), nout_pad = ((nout + 7) & ~7ll) + 8;
+        BUILD_CUDA(cudaMalloc(&t->QS[j], (size_t)nout_pad * 4));
+        BUILD_CUDA(cudaMalloc(&t->QP[j], (size_t)nout_pad * 4));
+        int gk = grid_for(cdiv(nout_pad, 256), 8);
+        BXG_LAUNCH(k_sample_level, gk, 256, 0, t->S, n, ss, t->QS[j], nout, nout_pad);
+        BXG_LAUNCH(k_sample_level, gk, 256, 0, t->PM, n, ss, t->QP[j], nout, nout_pad);
     }
 
     BUILD_CUDA(cudaMemcpyAsync(c.mailbox + 4, c.d_mailbox + 4, 8, cudaMemcpyDeviceToHost, c.stream));
@@ -1132,8 +1167,10 @@ static int ensure_fused_state(bxg_itree *t, int64_t nq) {
 
 // one fused launch over queries [q0, q0+n); slot selects the ticket / result pair, tile0 the tile-state region;
 // the chunk's base offset is read on the device from d_off[q0]
-static int launch_fused(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t n, int64_t q0,
-                        int slot, int64_t tile0) {
+extern "C++" {
+template <int PROBE>
+static int launch_fused_as(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t n, int64_t q0,
+                           int slot, int64_t tile0) {
     Context &c = ctx();
     const int64_t ntiles = cdiv(n, FUSED_THREADS);
     BXG_CUDA(cudaMemsetAsync(t->d_tiles + tile0, 0, (size_t)ntiles * 8, c.stream));
@@ -1142,25 +1179,26 @@ static int launch_fused(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
     size_t smem = find_smem_bytes(t);
     static bool attr_set = false;
     if (!attr_set) {
-        BXG_CUDA(cudaFuncSetAttribute(k_find_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        BXG_CUDA(cudaFuncSetAttribute(k_find_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        BXG_CUDA(cudaFuncSetAttribute(k_find_fused<PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set = true;
     }
     int occ = 0;
-    if (find_probe()) {
-        BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_fused<true>, FUSED_THREADS, smem));
-        int grid = grid_for(ntiles, occ > 0 ? occ : 1);     // every CTA is resident: the look-back cannot starve
-        BXG_LAUNCH(k_find_fused<true>, grid, FUSED_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, n,
-                   t->d_off + q0, t->d_hits, t->hits_cap, (const int64_t *)(t->d_off + q0), t->d_tiles + tile0,
-                   t->d_ticket + slot, t->d_result + 2 * slot);
-    } else {
-        BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_fused<false>, FUSED_THREADS, smem));
-        int grid = grid_for(ntiles, occ > 0 ? occ : 1);
-        BXG_LAUNCH(k_find_fused<false>, grid, FUSED_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, n,
-                   t->d_off + q0, t->d_hits, t->hits_cap, (const int64_t *)(t->d_off + q0), t->d_tiles + tile0,
-                   t->d_ticket + slot, t->d_result + 2 * slot);
-    }
+    BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find_fused<PROBE>, FUSED_THREADS, smem));
+    int grid = grid_for(ntiles, occ > 0 ? occ : 1);     // every CTA is resident: the look-back cannot starve
+    BXG_LAUNCH(k_find_fused<PROBE>, grid, FUSED_THREADS, smem, t->view(), dqt ? dqt + q0 : nullptr, dqs + q0, dqe + q0, n,
+               t->d_off + q0, t->d_hits, t->hits_cap, (const int64_t *)(t->d_off + q0), t->d_tiles + tile0,
+               t->d_ticket + slot, t->d_result + 2 * slot);
     return BXG_OK;
+}
+}  // extern "C++"
+
+static int launch_fused(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t n, int64_t q0,
+                        int slot, int64_t tile0) {
+    switch (find_probe()) {
+        case 0: return launch_fused_as<0>(t, dqt, dqs, dqe, n, q0, slot, tile0);
+        case 1: return launch_fused_as<1>(t, dqt, dqs, dqe, n, q0, slot, tile0);
+        default: return launch_fused_as<2>(t, dqt, dqs, dqe, n, q0, slot, tile0);
+    }
 }
 
 static int find_fused(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq, int loc,

@@ -438,6 +438,111 @@ BXG_HD void search_walk_probe(const int32_t *const *KS, const int32_t *const *KP
     walk_hits_halves(E, M, nlev, lo, hi, qs, ld8, ld, f);
 }
 
+// ---- third form: the same single search + backward probe over 8-ARY levels --------------------------------------
+//
+// A 16-entry round costs two 32-byte sectors and resolves 4 bits; an 8-entry round costs one and resolves 3.  With the
+// count kernels bound by sectors, the levels Q[j][i] = A[i << 3j] (strides 8, 64, 512, ...) take the window from the
+// splitters (2^shift items) down to one item in ceil(shift / 3) single-sector rounds: 4 sectors for shift = 12 where
+// the 16-ary levels need 6.  The probe reads one sector of QP[1] (8 samples of the running max = 64 items of reach).
+BXG_HD Round round_prepare8(const Win &w, int ss) {
+    Round r{0, 0, 0, false};
+    if (w.lo >= w.hi) return r;
+    r.m0 = (w.lo + (1u << ss) - 1) >> ss;
+    r.m1 = ((w.hi - 1) >> ss) + 1;
+    r.g = r.m0 & ~7u;
+    r.active = r.m0 < r.m1 && r.m1 - r.g <= 8u;
+    return r;
+}
+
+template <bool LESS_EQ, typename LD8>
+BXG_HD unsigned sector_mask(const int32_t *p, int32_t key, const LD8 &ld8) {
+    int4 a, b;
+    ld8(reinterpret_cast<const int4 *>(p), a, b);
+    return (unsigned)before<LESS_EQ>(a.x, key) | (unsigned)before<LESS_EQ>(a.y, key) << 1 |
+           (unsigned)before<LESS_EQ>(a.z, key) << 2 | (unsigned)before<LESS_EQ>(a.w, key) << 3 |
+           (unsigned)before<LESS_EQ>(b.x, key) << 4 | (unsigned)before<LESS_EQ>(b.y, key) << 5 |
+           (unsigned)before<LESS_EQ>(b.z, key) << 6 | (unsigned)before<LESS_EQ>(b.w, key) << 7;
+}
+
+// one search over the 8-ary levels Q[n8-1] .. Q[0] (Q[0] = the array itself), starting from a splitter window
+template <bool LESS_EQ, typename LD8, typename LD>
+BXG_HD void rounds8(const int32_t *const *Q, int n8, Win &w, int32_t key, const LD8 &ld8, const LD &ld, int last_level) {
+    for (int j = n8 - 1; j >= last_level; j--) {
+        const int ss = 3 * j;
+        const Round r = round_prepare8(w, ss);
+        if (r.active) round_apply(w, r, ss, sector_mask<LESS_EQ>(Q[j] + r.g, key, ld8));
+    }
+    (void)ld;
+}
+
+template <typename SP, typename LD8, typename LD, typename F>
+BXG_HD void search_walk_probe8(const int32_t *const *QS, const int32_t *const *QP, int n8, const SP &spS, const SP &spPM,
+                               int shift, uint32_t seg_lo, uint32_t seg_hi, int32_t qe, int32_t qs, const int32_t *E,
+                               const int32_t *const *M, int nlev, const LD8 &ld8, const LD &ld, uint32_t &hi_out,
+                               uint32_t &lo_out, F &&f) {
+    hi_out = lo_out = seg_hi;
+    if (seg_lo >= seg_hi) return;
+    const uint32_t k0 = (seg_lo + (1u << shift) - 1) >> shift, k1 = ((seg_hi - 1) >> shift) + 1;
+    uint32_t a_s = k0, step0 = 0;
+    if (k0 < k1) {
+        step0 = 1;
+        while (step0 * 2 <= k1 - k0) step0 *= 2;
+        for (uint32_t step = step0; step > 0; step >>= 1) a_s = lift_step<false>(spS, a_s, step, k1, qe);
+    }
+    Win ws = splitter_window(a_s, k0, k1, shift, seg_lo, seg_hi);
+    rounds8<false>(QS, n8, ws, qe, ld8, ld, 1);
+    // final S round (one sector of S) together with the probe sector of QP[1]; without a sampled level (tiny index) the
+    // walk simply starts at the front of the segment
+    const Round rs = round_prepare8(ws, 0);
+    uint32_t sb = ((ws.hi ? ws.hi - 1u : 0u) >> 3) & ~7u;
+    unsigned s_lt = 0;
+    if (rs.active) s_lt = sector_mask<false>(QS[0] + rs.g, qe, ld8);
+    unsigned pm_le = n8 >= 2 ? sector_mask<true>(QP[1] + sb, qs, ld8) : 0u;
+    if (rs.active) round_apply(ws, rs, 0, s_lt);
+    const uint32_t hi = finish_binary<false>(QS[0], ws, qe, ld);
+    hi_out = lo_out = hi;
+    if (hi <= seg_lo) return;                          // no item starts before qe
+    uint32_t lo_c = seg_lo;
+    if (n8 >= 2) {
+        const uint32_t m_hi = (hi - 1u) >> 3;          // sample block of the last candidate
+        if (m_hi < sb) {
+            sb = m_hi & ~7u;
+            pm_le = sector_mask<true>(QP[1] + sb, qs, ld8);
+        }
+        const uint32_t jmin = (seg_lo + 7u) >> 3;      // first sample position inside the segment
+        bool found = false;
+        for (int tries = 0; tries < 3; tries++) {
+            unsigned valid = 0xffu;
+            if (m_hi < sb + 7u) valid &= (2u << (m_hi - sb)) - 1u;
+            if (jmin > sb) valid &= (jmin - sb >= 8u) ? 0u : (~0u << (jmin - sb));
+            const unsigned ok = pm_le & valid;
+            if (ok) {
+                lo_c = (sb + (uint32_t)fls8(ok)) << 3;
+                found = true;
+                break;
+            }
+            if (jmin >= sb) {                          // ran off the front of the tree
+                lo_c = seg_lo;
+                found = true;
+                break;
+            }
+            if (tries == 2) break;
+            sb -= 8u;
+            pm_le = sector_mask<true>(QP[1] + sb, qs, ld8);
+        }
+        if (!found) {                                  // something long is open in front: the full PM search (coarse)
+            uint32_t a_p = k0;
+            for (uint32_t step = step0; step > 0; step >>= 1) a_p = lift_step<true>(spPM, a_p, step, k1, qs);
+            Win wp = splitter_window(a_p, k0, k1, shift, seg_lo, seg_hi);
+            rounds8<true>(QP, n8, wp, qs, ld8, ld, 1);
+            lo_c = wp.lo;
+        }
+    }
+    const uint32_t lo = lo_c < hi ? lo_c : hi;
+    lo_out = lo;
+    walk_hits_halves(E, M, nlev, lo, hi, qs, ld8, ld, f);
+}
+
 // Write the item ids of the hits of one 16-item group: the whole aligned group of I is fetched with four 16-byte
 // loads issued back to back (one 64-byte line), THEN the selected ids are stored -- a load per hit interleaved with
 // the stores would serialise on every store (the compiler must assume hits[] may alias I[]).
@@ -446,6 +551,30 @@ BXG_HD void emit_group_to(const int32_t *I, uint32_t k0, unsigned mask, SINK &ou
     const int4 *p = reinterpret_cast<const int4 *>(group_ptr(I, k0, mul));
     int4 a, b, c, d;
     ld4(p, a, b, c, d);
+    if (mask & 0x0001u) out.put(a.x);
+    if (mask & 0x0002u) out.put(a.y);
+    if (mask & 0x0004u) out.put(a.z);
+    if (mask & 0x0008u) out.put(a.w);
+    if (mask & 0x0010u) out.put(b.x);
+    if (mask & 0x0020u) out.put(b.y);
+    if (mask & 0x0040u) out.put(b.z);
+    if (mask & 0x0080u) out.put(b.w);
+    if (mask & 0x0100u) out.put(c.x);
+    if (mask & 0x0200u) out.put(c.y);
+    if (mask & 0x0400u) out.put(c.z);
+    if (mask & 0x0800u) out.put(c.w);
+    if (mask & 0x1000u) out.put(d.x);
+    if (mask & 0x2000u) out.put(d.y);
+    if (mask & 0x4000u) out.put(d.z);
+    if (mask & 0x8000u) out.put(d.w);
+}
+
+// The same with half-group loads: only the 32-byte halves of the I group that hold a selected item are read.
+template <typename LD8, typename SINK>
+BXG_HD void emit_group_halves_to(const int32_t *I, uint32_t k0, unsigned mask, SINK &out, const LD8 &ld8) {
+    int4 a{}, b{}, c{}, d{};
+    if (mask & 0x00ffu) ld8(reinterpret_cast<const int4 *>(I + k0), a, b);
+    if (mask & 0xff00u) ld8(reinterpret_cast<const int4 *>(I + k0 + 8), c, d);
     if (mask & 0x0001u) out.put(a.x);
     if (mask & 0x0002u) out.put(a.y);
     if (mask & 0x0004u) out.put(a.z);

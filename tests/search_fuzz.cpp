@@ -69,6 +69,24 @@ int main(int argc, char **argv) {
             KS[j] = ls[j].data();
             KP[j] = lp[j].data();
         }
+        // 8-ary levels (strides 8^j) for search_walk_probe8
+        const int n8 = std::max(1, (shift + 2) / 3);
+        std::vector<std::vector<int32_t>> qs8(n8), qp8(n8);
+        std::vector<const int32_t *> QS(n8), QP(n8);
+        for (int j = 0; j < n8; j++) {
+            const int ss = 3 * j;
+            const long nout = (n + (1l << ss) - 1) >> ss, pad = ((nout + 7) & ~7l) + 8;
+            qs8[j].assign(pad, INT_MAX);
+            qp8[j].assign(pad, INT_MAX);
+            for (long i = 0; i < nout; i++) {
+                qs8[j][i] = S[i << ss];
+                qp8[j][i] = PM[i << ss];
+            }
+            QS[j] = qs8[j].data();
+            QP[j] = qp8[j].data();
+        }
+        QS[0] = S.data();
+        QP[0] = PM.data();
         // max hierarchy
         std::vector<std::vector<int32_t>> M;
         {
@@ -169,6 +187,22 @@ int main(int argc, char **argv) {
                 if (hi3 != ehi || lo3 > std::min(elo, ehi) || lo3 < toff[t] || got3 != want3) {
                     printf("SEARCH_WALK_PROBE MISMATCH trial %d n=%d nk=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u got=%zu want=%zu\n",
                            trial, n, nk, toff[t], toff[t + 1], qs, qe, hi3, ehi, lo3, elo, got3.size(), want3.size());
+                    return 1;
+                }
+                std::vector<uint32_t> got4;
+                uint32_t hi4, lo4;
+                bxs::search_walk_probe8(QS.data(), QP.data(), n8, spS.data(), spPM.data(), shift, toff[t], toff[t + 1], qe,
+                                        qs, E.data(), Mp.data(), (int)Mp.size(), ld8, ld, hi4, lo4,
+                                        [&](uint32_t k0, unsigned mask) {
+                                            while (mask) {
+                                                int b = bxs::ffs32(mask) - 1;
+                                                mask &= mask - 1;
+                                                got4.push_back(k0 + b);
+                                            }
+                                        });
+                if (hi4 != ehi || lo4 > std::min(elo, ehi) || lo4 < toff[t] || got4 != want3) {
+                    printf("SEARCH_WALK_PROBE8 MISMATCH trial %d n=%d n8=%d shift=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u got=%zu want=%zu\n",
+                           trial, n, n8, shift, toff[t], toff[t + 1], qs, qe, hi4, ehi, lo4, elo, got4.size(), want3.size());
                     return 1;
                 }
                 if (hi2 != ehi || lo2 > std::min(elo, ehi) || got2 != want) {
