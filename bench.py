@@ -415,15 +415,29 @@ def run_ours(args):
     e2e_serial = q_all * e2e_steps / time_host(step_host_serial, e2e_steps)
     assert np.array_equal(h_off.array, off), "host-path offsets differ from device-path offsets"
     serial_hits = h_hits.array[:hits_total].copy()
-    e2e_value = q_all * e2e_steps / time_host(step_host, e2e_steps)
+    e2e_i64 = q_all * e2e_steps / time_host(step_host, e2e_steps)
     r_off = np.frombuffer((C.c_int64 * (nq + 1)).from_address(p_off.value), np.int64)
     r_hits = np.frombuffer((C.c_int32 * total.value).from_address(p_hits.value), np.int32)
     assert np.array_equal(r_off, off) and np.array_equal(r_hits, serial_hits), "pipelined host path differs"
+    # the same call with int32 CSR offsets (IntervalForest.find_batch(..., offsets32=True)): the return leg is PCIe-bound
+    # and the offsets are 8 of its ~34 bytes per query.  Every rank's hits fit int32 here; if they did not, the int64
+    # figure above would be the headline.
+    off_bytes = 8
+    e2e_value = e2e_i64
+    if hits_total < 2**31:
+        def step_host32():
+            check(L.bxg_itree_find_host32(forest.handle, ptr(h_qt.array), ptr(h_qs.array), ptr(h_qe.array), nq,
+                                          C.byref(p_off), C.byref(p_hits), C.byref(total)))
+        e2e_value = q_all * e2e_steps / time_host(step_host32, e2e_steps)
+        r_off32 = np.frombuffer((C.c_int32 * (nq + 1)).from_address(p_off.value), np.int32)
+        r_hits = np.frombuffer((C.c_int32 * total.value).from_address(p_hits.value), np.int32)
+        assert np.array_equal(r_off32, off) and np.array_equal(r_hits, serial_hits), "int32-offset host path differs"
+        off_bytes = 4
     del serial_hits
 
     extra = {"build_ms": min(build_ms), "hits_per_step": hits_all, "hits_per_query": hits_all / q_all,
              "per_chrom_hits_checksum": int((per_chrom * np.arange(1, 25)).sum()), "parity_spot_check": parity,
-             "e2e_serial_copies": e2e_serial, "single_pass_kernel_ms_per_step": single_pass_ms,
+             "e2e_serial_copies": e2e_serial, "e2e_int64_offsets": e2e_i64, "single_pass_kernel_ms_per_step": single_pass_ms,
              "sorted_queries_ms_per_step": sorted_ms}
 
     if rank != 0:
@@ -495,8 +509,8 @@ def run_ours(args):
         "dtype": "int32", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clock_summary, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": int(12 * nq), "d2h_bytes_per_step": int(8 * (nq + 1) + 4 * hits_total),
-                "steps": e2e_steps, "timing": "host wall clock around bxg_itree_find_host (pinned host arrays in, pinned host CSR out; copies overlapped with kernels), max over ranks"},
+                "h2d_bytes_per_step": int(12 * nq), "d2h_bytes_per_step": int(off_bytes * (nq + 1) + 4 * hits_total),
+                "steps": e2e_steps, "timing": "host wall clock around bxg_itree_find_host32 (pinned host arrays in, pinned host CSR out with int32 offsets; copies overlapped with kernels), max over ranks; extra.e2e_int64_offsets is the int64-offset call"},
         "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
     print(json.dumps(line))

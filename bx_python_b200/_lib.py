@@ -76,6 +76,7 @@ SIGNATURES = {
     "bxg_itree_fetch": [vp, vp, vp],
     "bxg_set_find_mode": [cint],
     "bxg_itree_find_host": [vp, vp, vp, vp, i64, pvp, pvp, pi64],
+    "bxg_itree_find_host32": [vp, vp, vp, vp, i64, pvp, pvp, pi64],
     "bxg_itree_find_small": [vp, vp, vp, vp, i32, pvp, pvp, pi64],
     "bxg_itree_result_dev": [vp, pvp, pvp, pi64, pi64],
     "bxg_itree_count": [vp, vp, vp, vp, i64, cint, vp, pi64],

@@ -1247,8 +1247,15 @@ static int grow_host_hits(bxg_itree *t, int64_t end, int64_t keep, double progre
 
 // Host arrays, copies overlapped with the fused kernel: chunk k+1 is uploaded and searched while chunk k's hits and
 // offsets travel back.  Each chunk's kernel reads its base offset from d_off[q0], written by the previous chunk.
+// narrow = true: the offsets travel back as int32 (a tiny kernel narrows each chunk's int64 offsets into d_cnt, unused
+// on this path) -- 4 instead of 8 bytes per query on the PCIe-bound leg; valid while the total stays below 2^31.
+__global__ void k_narrow_offsets(const int64_t *__restrict__ src, int32_t *__restrict__ dst, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (int32_t)src[i];
+}
+
 static int find_host_fused(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
-                           const int64_t **offsets, const int32_t **hits, int64_t *total) {
+                           const int64_t **offsets, const int32_t **hits, int64_t *total, bool narrow = false) {
     Context &c = ctx();
     BXG_TRY(ensure_pipeline(t));
     BXG_TRY(ensure_query_buffers(t, nq));
@@ -1261,7 +1268,8 @@ static int find_host_fused(bxg_itree_t *t, const int32_t *qtree, const int32_t *
     }
     t->nq = nq;
     t->total = 0;
-    t->h_off[0] = 0;
+    t->h_off[0] = 0;                                   // (also the int32 view's element 0)
+    int32_t *h_off32 = (int32_t *)t->h_off;
     if (offsets) *offsets = t->h_off;
     if (hits) *hits = t->h_hits;
     if (total) *total = 0;
@@ -1282,6 +1290,9 @@ static int find_host_fused(bxg_itree_t *t, const int32_t *qtree, const int32_t *
     auto launch_chunk = [&](int k) -> int {
         const int64_t q0 = k * per, n = std::min(per, nq - q0);
         BXG_TRY(launch_fused(t, has_tree ? dqt : nullptr, dqs, dqe, n, q0, k, k * tiles_per));
+        if (narrow)
+            BXG_LAUNCH(k_narrow_offsets, grid_for(cdiv(n, 1024), 4), 256, 0, (const int64_t *)(t->d_off + q0 + 1),
+                       t->d_cnt + q0 + 1, n);
         BXG_CUDA(cudaMemcpyAsync(t->h_result + 2 * k, t->d_result + 2 * k, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
         BXG_CUDA(cudaEventRecord(t->ev_scan[k], c.stream));
         return BXG_OK;
@@ -1311,7 +1322,10 @@ static int find_host_fused(bxg_itree_t *t, const int32_t *qtree, const int32_t *
         BXG_CUDA(cudaStreamWaitEvent(t->s_out, t->ev_scan[k], 0));
         if (end > base)
             BXG_CUDA(cudaMemcpyAsync(t->h_hits + base, t->d_hits + base, (size_t)(end - base) * 4, cudaMemcpyDeviceToHost, t->s_out));
-        BXG_CUDA(cudaMemcpyAsync(t->h_off + q0 + 1, t->d_off + q0 + 1, (size_t)n * 8, cudaMemcpyDeviceToHost, t->s_out));
+        if (narrow)
+            BXG_CUDA(cudaMemcpyAsync(h_off32 + q0 + 1, t->d_cnt + q0 + 1, (size_t)n * 4, cudaMemcpyDeviceToHost, t->s_out));
+        else
+            BXG_CUDA(cudaMemcpyAsync(t->h_off + q0 + 1, t->d_off + q0 + 1, (size_t)n * 8, cudaMemcpyDeviceToHost, t->s_out));
         base = end;
         return BXG_OK;
     };
@@ -1322,6 +1336,10 @@ static int find_host_fused(bxg_itree_t *t, const int32_t *qtree, const int32_t *
     }
     BXG_CUDA(cudaStreamSynchronize(t->s_out));
     BXG_CUDA(cudaStreamSynchronize(c.stream));
+    if (narrow && base > 0x7fffffffll) {
+        t->nq = -1;
+        return set_error(BXG_ERR_MISMATCH, "%lld hits do not fit int32 offsets: use bxg_itree_find_host", (long long)base);
+    }
     t->total = base;
     if (offsets) *offsets = t->h_off;
     if (hits) *hits = t->h_hits;
@@ -1440,6 +1458,16 @@ int bxg_itree_find_host(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs,
     if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
     return find_mode() != 0 ? find_host_fused(t, qtree, qs, qe, nq, offsets, hits, total)
                             : find_host_three_pass(t, qtree, qs, qe, nq, offsets, hits, total);
+}
+
+int bxg_itree_find_host32(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
+                          const int32_t **offsets, const int32_t **hits, int64_t *total) {
+    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
+    if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
+    const int64_t *off64 = nullptr;
+    BXG_TRY(find_host_fused(t, qtree, qs, qe, nq, &off64, hits, total, true));
+    if (offsets) *offsets = (const int32_t *)off64;     // the same pinned buffer, filled as int32
+    return BXG_OK;
 }
 
 int bxg_itree_fetch(bxg_itree_t *t, int64_t *offsets, int32_t *hits) {

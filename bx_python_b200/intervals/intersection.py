@@ -110,15 +110,28 @@ class _DeviceIndex:
     def build(self, tree, start, end, ntrees):
         check(_lib.lib().bxg_itree_build(self._h, ptr(tree), ptr(start), ptr(end), len(start), ntrees, _lib.HOST))
 
-    def find(self, qtree, qs, qe, copy=True):
+    def find(self, qtree, qs, qe, copy=True, offsets32=False):
         """Batched find over host arrays (copies overlapped with the kernels, bxg_itree_find_host).
-        copy=False returns views of the index's pinned result buffers, valid until its next find."""
+        copy=False returns views of the index's pinned result buffers, valid until its next find.
+        offsets32=True asks for int32 CSR offsets (half the offset bytes over PCIe); falls back to int64 when the
+        hits do not fit."""
         L = _lib.lib()
         total = C.c_int64()
         p_off, p_hits = C.c_void_p(), C.c_void_p()
+        nq = len(qs)
+        if offsets32:
+            rc = L.bxg_itree_find_host32(self._h, ptr(qtree), ptr(qs), ptr(qe), nq, C.byref(p_off), C.byref(p_hits),
+                                         C.byref(total))
+            if rc == 0:
+                n = total.value
+                off = np.frombuffer((C.c_int32 * (nq + 1)).from_address(p_off.value), np.int32)
+                hits = (np.frombuffer((C.c_int32 * n).from_address(p_hits.value), np.int32) if n else np.empty(0, np.int32))
+                return (off.copy(), hits.copy()) if copy else (off, hits)
+            if rc != _lib.ERR_MISMATCH:
+                check(rc)
         check(L.bxg_itree_find_host(self._h, ptr(qtree), ptr(qs), ptr(qe), len(qs), C.byref(p_off), C.byref(p_hits),
                                     C.byref(total)))
-        nq, n = len(qs), total.value
+        n = total.value
         off = np.frombuffer((C.c_int64 * (nq + 1)).from_address(p_off.value), np.int64)
         hits = (np.frombuffer((C.c_int32 * n).from_address(p_hits.value), np.int32) if n else np.empty(0, np.int32))
         if copy:
@@ -204,12 +217,13 @@ class IntervalTree:
         v = self._values
         return [v[i] for i in hits]
 
-    def find_batch(self, starts, ends):
-        """-> (offsets int64[nq+1], hits int32[total]): item indices (insertion order) per query, reference order."""
+    def find_batch(self, starts, ends, offsets32=False):
+        """-> (offsets int64[nq+1], hits int32[total]): item indices (insertion order) per query, reference order.
+        offsets32=True returns int32 offsets when the hits fit (less PCIe traffic)."""
         qs, qe = as_i32(starts), as_i32(ends)
         if not self._starts:
-            return np.zeros(len(qs) + 1, np.int64), np.empty(0, np.int32)
-        return self._ensure().find(None, qs, qe)
+            return np.zeros(len(qs) + 1, np.int32 if offsets32 else np.int64), np.empty(0, np.int32)
+        return self._ensure().find(None, qs, qe, offsets32=offsets32)
 
     def count_batch(self, starts, ends):
         """len(find(s, e)) for every query -> int32 array."""
@@ -302,10 +316,11 @@ class IntervalForest:
         self._index.build(t, s, e, self.ntrees)
         return self
 
-    def find_batch(self, tree_ids, starts, ends, copy=True):
+    def find_batch(self, tree_ids, starts, ends, copy=True, offsets32=False):
         """-> CSR (offsets, hits); hits are positions in the arrays passed to build().
-        copy=False returns zero-copy views of pinned buffers that the next find_batch overwrites."""
-        return self._index.find(as_i32(tree_ids), as_i32(starts), as_i32(ends), copy=copy)
+        copy=False returns zero-copy views of pinned buffers that the next find_batch overwrites.
+        offsets32=True returns int32 offsets when the hits fit (less PCIe traffic), int64 otherwise."""
+        return self._index.find(as_i32(tree_ids), as_i32(starts), as_i32(ends), copy=copy, offsets32=offsets32)
 
     def count_batch(self, tree_ids, starts, ends):
         return self._index.count(as_i32(tree_ids), as_i32(starts), as_i32(ends))

@@ -250,6 +250,27 @@ def test_find_large_properties(bx):
     assert inc.all()
 
 
+def test_find_int32_offsets(bx):
+    """find_batch(offsets32=True): same CSR with int32 offsets (bxg_itree_find_host32), single tree and forest, several
+    pipeline chunks."""
+    rng = np.random.default_rng(31)
+    s, e = synth.uniform_intervals(rng, 300_000, 5_000_000)
+    qs, qe = synth.uniform_intervals(rng, 2_500_000, 5_000_000)
+    t = tree_of(bx, s, e)
+    off64, hits64 = t.find_batch(qs, qe)
+    off32, hits32 = t.find_batch(qs, qe, offsets32=True)
+    assert off32.dtype == np.int32 and off64.dtype == np.int64
+    assert np.array_equal(off32, off64) and np.array_equal(hits32, hits64)
+    tid = (np.arange(len(s)) % 5).astype(np.int32)
+    qt = (np.arange(len(qs)) % 6).astype(np.int32)
+    f = bx.ix.IntervalForest(5).build(tid, s, e)
+    a = f.find_batch(qt, qs, qe)
+    b = f.find_batch(qt, qs, qe, offsets32=True)
+    assert b[0].dtype == np.int32 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    e0 = bx.ix.IntervalTree().find_batch([1, 2], [3, 4], offsets32=True)
+    assert e0[0].tolist() == [0, 0, 0] and len(e0[1]) == 0
+
+
 def test_find_small_path(bx, orc):
     """bxg_itree_find_small (the scalar IntervalTree.find route): up to 32 queries answered by one warp into mapped
     pinned memory; identical CSR to the batched path, incl. the fallback when more than 65536 hits come back."""
