@@ -49,6 +49,7 @@ SIGNATURES = {
     "bxg_bits_geometry": [vp, pi32, pi32, pi32],
     "bxg_bits_clone": [vp, pvp],
     "bxg_bits_set_ranges": [vp, vp, vp, i64, cint],
+    "bxg_bits_set_ranges_multi": [pvp, i32, vp, vp, vp, i64, cint],
     "bxg_bits_set_bits": [vp, vp, i64, cint, cint],
     "bxg_bits_read": [vp, vp, i64, vp, cint],
     "bxg_bits_and": [vp, vp],

@@ -93,7 +93,10 @@ def aggregate_scores_in_intervals(scores_by_chrom, interval_lines, out_file, mas
         chroms.append(fields[0])
         starts.append(int(fields[1]))
         stops.append(int(fields[2]))
-    names = list(scores_by_chrom.keys()) if hasattr(scores_by_chrom, "keys") else None
+    try:
+        names = list(scores_by_chrom.keys())
+    except (AttributeError, NotImplementedError, TypeError):
+        names = None
     if names is None:                                  # a dict-like without iteration (FileBinnedArrayDir, :30-57)
         names = []
         for c in dict.fromkeys(chroms):

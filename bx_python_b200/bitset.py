@@ -271,6 +271,25 @@ def and_count_many(dst, src):
     return _batch(0, dst, src, True)
 
 
+def set_ranges_many(sets, which, starts, counts):
+    """``sets[which[i]].set_range(starts[i], counts[i])`` for every i in one kernel launch -- the per-line loop of
+    lib/bx/bitset_builders.py:40-53 over a whole file.  Same IndexError as the scalar call for the first offending
+    entry of each set, raised before any device work."""
+    sets = list(sets)
+    w, s, c = as_i32(which), as_i32(starts), as_i32(counts)
+    if len(w) and (w.min() < 0 or w.max() >= len(sets)):
+        raise IndexError("bit set index out of range")
+    for k, b in enumerate(sets):
+        sel = w == k
+        if sel.any():
+            b._check_arrays(s[sel], c[sel])
+        b._flush()
+    if len(s) == 0:
+        return
+    h = (C.c_void_p * len(sets))(*[b._h for b in sets])
+    check(_lib.lib().bxg_bits_set_ranges_multi(h, len(sets), ptr(w), ptr(s), ptr(c), len(s), _lib.HOST))
+
+
 def count_ranges_many(sets, which, starts, counts, strict=True):
     """``sets[which[i]].count_range(starts[i], counts[i])`` for every i in one kernel launch -- the per-line lookup
     of scripts/bed_intersect.py:46-53 (`bitsets[chrom].count_range(start, end - start)`).  Entries whose ``which`` is

@@ -3,8 +3,8 @@ Drop-in for ``bx.bitset_builders`` (``/root/reference/lib/bx/bitset_builders.py`
 built from interval text / lists.
 
 Same function names, arguments, per-line semantics and exceptions as the reference; the difference is that the
-``set_range`` calls of one chromosome are collected and issued as ONE batched kernel (``BinnedBitSet.set_ranges``)
-instead of one C call per line.  Text parsing stays on the host (it is Python in the reference too).
+``set_range`` calls of a whole file are collected and issued as ONE batched kernel (``bitset.set_ranges_many``; a
+single chromosome: ``BinnedBitSet.set_ranges``) instead of one C call per line.  Text parsing stays on the host (it is Python in the reference too).
 """
 from __future__ import annotations
 
@@ -13,7 +13,7 @@ from warnings import warn
 
 import numpy as np
 
-from .bitset import MAX, BinnedBitSet
+from .bitset import MAX, BinnedBitSet, set_ranges_many
 
 
 class _Collector:
@@ -34,9 +34,15 @@ class _Collector:
         self._c[chrom].append(count)
 
     def finish(self):
-        for chrom, b in self.bitsets.items():
-            if self._s[chrom]:
-                b.set_ranges(np.asarray(self._s[chrom], np.int32), np.asarray(self._c[chrom], np.int32))
+        chroms = [c for c in self.bitsets if self._s[c]]
+        if len(chroms) == 1:
+            c = chroms[0]
+            self.bitsets[c].set_ranges(np.asarray(self._s[c], np.int32), np.asarray(self._c[c], np.int32))
+        elif chroms:                                   # the whole file in one launch
+            which = np.concatenate([np.full(len(self._s[c]), k, np.int32) for k, c in enumerate(chroms)])
+            starts = np.concatenate([np.asarray(self._s[c], np.int32) for c in chroms])
+            counts = np.concatenate([np.asarray(self._c[c], np.int32) for c in chroms])
+            set_ranges_many([self.bitsets[c] for c in chroms], which, starts, counts)
         return self.bitsets
 
 

@@ -335,6 +335,81 @@ __global__ void k_set_bits(uint64_t *__restrict__ words, uint8_t *__restrict__ s
     }
 }
 
+// Genome-wide form: range i goes into bitmap descs[which[i]] -- one launch for a whole BED file instead of one per
+// chromosome (24 launches of ~260 k ranges each barely fill one wave and pay 24 launch gaps and tails).  Entries whose
+// `which` is outside the table, or that do not fit their bitmap, are skipped (the shim has raised before).
+struct SetDesc {
+    uint64_t *words;
+    uint8_t *state;
+    int32_t bin_size, flat, size;
+};
+
+__global__ void __launch_bounds__(256)
+k_set_ranges_multi(const SetDesc *__restrict__ descs, int nsets, const int32_t *__restrict__ which,
+                   const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n) {
+    __shared__ int64_t s_long[2 * LONG_SLOTS];
+    __shared__ uint64_t *s_long_w[LONG_SLOTS];
+    __shared__ unsigned int s_nlong;
+    const int lane = threadIdx.x & 31;
+    for (int64_t tile = (int64_t)blockIdx.x * blockDim.x; tile < n; tile += (int64_t)gridDim.x * blockDim.x) {
+        if (threadIdx.x == 0) s_nlong = 0;
+        __syncthreads();
+        const int64_t i = tile + threadIdx.x;
+        int64_t mb = 0, me = 0;
+        uint64_t *words = nullptr;
+        if (i < n) {
+            const int32_t t = __ldg(which + i), s = __ldg(start + i), c = __ldg(count + i);
+            if (t >= 0 && t < nsets && c > 0 && s >= 0) {
+                const SetDesc d = descs[t];
+                if ((int64_t)s + c <= d.size) {
+                    words = d.words;
+                    int32_t last = s + c - 1;
+                    int64_t w0 = s >> 6, w1 = last >> 6;
+                    unsigned long long m0 = ~0ull << (s & 63), m1 = ~0ull >> (63 - (last & 63));
+                    if (w0 == w1) {
+                        atomicOr((unsigned long long *)words + w0, m0 & m1);
+                    } else {
+                        atomicOr((unsigned long long *)words + w0, m0);
+                        atomicOr((unsigned long long *)words + w1, m1);
+                    }
+                    if (!d.flat) {
+                        int b1 = last / d.bin_size;
+                        for (int b = s / d.bin_size; b <= b1; b++)
+                            if (d.state[b] == BZ) d.state[b] = BA;     // benign race: every writer stores BA
+                    }
+                    mb = w0 + 1;
+                    me = w1;
+                }
+            }
+        }
+        if (me - mb > LONG_WORDS) {
+            unsigned int slot = atomicAdd(&s_nlong, 1u);
+            if (slot < LONG_SLOTS) {
+                s_long[2 * slot] = mb;
+                s_long[2 * slot + 1] = me;
+                s_long_w[slot] = words;
+                me = mb;
+            }
+        }
+        unsigned has = __ballot_sync(0xffffffffu, me > mb);
+        while (has) {
+            int src = __ffs(has) - 1;
+            has &= has - 1;
+            const int64_t b = __shfl_sync(0xffffffffu, mb, src), e = __shfl_sync(0xffffffffu, me, src);
+            uint64_t *w = (uint64_t *)__shfl_sync(0xffffffffu, (unsigned long long)words, src);
+            for (int64_t k = b + lane; k < e; k += 32) w[k] = ~0ull;
+        }
+        __syncthreads();
+        const unsigned int nl = min(s_nlong, (unsigned int)LONG_SLOTS);
+        for (unsigned int r = 0; r < nl; r++) {
+            const int64_t b = s_long[2 * r], e = s_long[2 * r + 1];
+            uint64_t *w = s_long_w[r];
+            for (int64_t k = b + threadIdx.x; k < e; k += blockDim.x) w[k] = ~0ull;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void k_read_bits(const uint64_t *__restrict__ words, const int32_t *__restrict__ pos, int64_t n,
                             uint8_t *__restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -607,6 +682,32 @@ int bxg_bits_set_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *coun
                (const int32_t *)ds, (const int32_t *)dc, n);
     invalidate(b);
     if (loc == BXG_HOST) BXG_CUDA(cudaStreamSynchronize(ctx().stream));   // caller may reuse its arrays on return
+    return BXG_OK;
+}
+
+int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int32_t *which, const int32_t *start,
+                              const int32_t *count, int64_t n, int loc) {
+    BXG_TRY(ensure_init());
+    if (nsets <= 0 || nsets > BATCH_MAX_PAIRS) return set_error(BXG_ERR_ARG, "nsets must be in [1, %d]", BATCH_MAX_PAIRS);
+    if (n <= 0) return BXG_OK;
+    static SetDesc h_desc[BATCH_MAX_PAIRS];
+    for (int k = 0; k < nsets; k++) {
+        bxg_bits *b = sets[k];
+        if (!b) return set_error(BXG_ERR_ARG, "null bitset handle %d", k);
+        h_desc[k] = SetDesc{b->words, b->state, b->bin_size, b->flat ? 1 : 0, b->size};
+    }
+    Context &c = ctx();
+    void *d_desc;
+    BXG_TRY(scratch(3, sizeof(SetDesc) * (size_t)nsets, &d_desc));
+    BXG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(SetDesc) * (size_t)nsets, cudaMemcpyHostToDevice, c.stream));
+    const void *dw, *ds, *dc;
+    BXG_TRY(stage_in(0, which, (size_t)n * 4, loc, &dw));
+    BXG_TRY(stage_in(1, start, (size_t)n * 4, loc, &ds));
+    BXG_TRY(stage_in(5, count, (size_t)n * 4, loc, &dc));
+    BXG_LAUNCH(k_set_ranges_multi, grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets, (const int32_t *)dw,
+               (const int32_t *)ds, (const int32_t *)dc, n);
+    for (int k = 0; k < nsets; k++) invalidate(sets[k]);
+    BXG_CUDA(cudaStreamSynchronize(c.stream));         // h_desc is static and the caller may reuse its arrays
     return BXG_OK;
 }
 

@@ -1380,7 +1380,17 @@ struct SmallQueries {
 
 __global__ void __launch_bounds__(32)
 k_find_small(IndexView ix, SmallQueries a, int nq, long long *__restrict__ out_off, int32_t *__restrict__ out_hits) {
+    // the S splitters go to shared memory first (one coalesced sweep by the warp): the 12 dependent steps of the
+    // splitter search then cost shared-memory latency instead of 12 L2 round trips.  PM splitters are only needed by
+    // the rare fallback of the probe search and are read from global memory there.
+    __shared__ __align__(16) int32_t s_sp[MAX_SPLIT];
     const int q = threadIdx.x;
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(ix.spS);
+        int4 *dst = reinterpret_cast<int4 *>(s_sp);
+        for (int i = q; i < ix.nsplit_pad / 4; i += 32) dst[i] = __ldg(src + i);
+        __syncwarp();
+    }
     uint32_t lo = 0, hi = 0;
     int32_t qs = 0;
     int c = 0;
@@ -1389,9 +1399,8 @@ k_find_small(IndexView ix, SmallQueries a, int nq, long long *__restrict__ out_o
         qs = a.qs[q];
         if (t >= 0 && t < ix.ntrees) {
             const uint32_t seg_lo = (uint32_t)ix.toff[t], seg_hi = (uint32_t)ix.toff[t + 1];
-            bxs::dual_search(ix.KS, ix.KP, ix.nk, ix.spS, ix.spPM, ix.shift, seg_lo, seg_hi, qe, qs, Ld4(), Ld1(), hi, lo,
-                             bxs::NoPrefetch(), 1, true);
-            bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(), [&](uint32_t, unsigned m) { c += __popc(m); });
+            bxs::search_walk_probe8(ix.QS, ix.QP, ix.n8, (const int32_t *)s_sp, ix.spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E,
+                                    ix.M, ix.nlev, Ld8(), Ld1(), hi, lo, [&](uint32_t, unsigned m) { c += __popc(m); });
         }
     }
     int incl = c;
@@ -1407,8 +1416,11 @@ k_find_small(IndexView ix, SmallQueries a, int nq, long long *__restrict__ out_o
     }
     if (total > SMALL_CAP || c == 0) return;
     int32_t *dst = out_hits + (incl - c);
-    bxs::walk_hits(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld4(), Ld1(),
-                   [&](uint32_t k0, unsigned m) { dst = bxs::emit_group(ix.I, k0, m, dst, Ld4()); });
+    bxs::walk_hits_halves(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld8(), Ld1(), [&](uint32_t k0, unsigned m) {
+        bxs::PtrSink out{dst};
+        bxs::emit_group_halves_to(ix.I, k0, m, out, Ld8());
+        dst = out.p;
+    });
 }
 
 int bxg_itree_find_small(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int32_t nq,

@@ -91,6 +91,11 @@ int bxg_bits_clone(const bxg_bits_t *b, bxg_bits_t **out);                      
  * 0 <= start, 0 <= count, start+count <= size (the host shim raises the reference's IndexError first). */
 int bxg_bits_set_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *count, int64_t n, int loc);
 /* binBitsSetOne / binBitsClearOne (binBits.c:67-96), n positions per call, value 1 = set, 0 = clear */
+/* Genome-wide set_range: range i goes into sets[which[i]] -- the per-line `bitsets[chrom].set_range(start, end - start)`
+ * of lib/bx/bitset_builders.py:40-53 for a whole file in one launch.  Entries with `which` outside [0, nsets), count <= 0
+ * or start + count > size are skipped (the caller validates first, as bitset.pyx:184-189 does). */
+int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int32_t *which, const int32_t *start,
+                              const int32_t *count, int64_t n, int loc);
 int bxg_bits_set_bits(bxg_bits_t *b, const int32_t *pos, int64_t n, int value, int loc);
 /* binBitsReadOne (binBits.c:49-65) for n positions */
 int bxg_bits_read(const bxg_bits_t *b, const int32_t *pos, int64_t n, uint8_t *out, int loc);

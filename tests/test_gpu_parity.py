@@ -647,6 +647,40 @@ def test_set_ranges_long_and_short_mixed(bx, orc):
     assert b2.count_all() == 0 and b2.next_set(0) == size
 
 
+def test_set_ranges_many_vs_oracle(bx, orc):
+    """bitset.set_ranges_many: a shuffled multi-chromosome batch in one launch == per-set oracle, incl. a very long range,
+    binned and flat sets mixed, and the scalar call's IndexError for an offending entry."""
+    rng = np.random.default_rng(41)
+    sizes = [1_000_003, 250_000, 64, 5_000_000]
+    sets = [bx.bitset.BinnedBitSet(sizes[0]), bx.bitset.BinnedBitSet(sizes[1], 7), bx.bitset.BitSet(sizes[2]),
+            bx.bitset.BinnedBitSet(sizes[3])]
+    oracles = [orc.OracleBinnedBitSet(sizes[0]), orc.OracleBinnedBitSet(sizes[1], 7), orc.OracleBitSet(sizes[2]),
+               orc.OracleBinnedBitSet(sizes[3])]
+    n = 40_000
+    which = rng.integers(0, 4, n).astype(np.int32)
+    size_of = np.asarray(sizes)[which]
+    start = (rng.random(n) * (size_of - 1)).astype(np.int64)
+    count = np.minimum(rng.integers(0, 3000, n), size_of - start)
+    start[0], count[0], which[0] = 1000, 4_000_000, 3          # one range far above the warp-sweep limit
+    bx.bitset.set_ranges_many(sets, which, start, count)
+    for k, (b, o) in enumerate(zip(sets, oracles)):
+        sel = which == k
+        for s_, c_ in zip(start[sel].tolist(), count[sel].tolist()):
+            o.set_range(s_, c_)
+        words = o.words() if hasattr(o, "words") else None
+        if words is not None:
+            assert np.array_equal(b.to_words(), words), f"set {k}"
+        else:
+            pos = rng.integers(0, sizes[k], 64)
+            assert b.get_many(pos).tolist() == [o[int(p)] for p in pos]
+        assert b.count_range(0, sizes[k]) == o.count_range(0, sizes[k])
+    with pytest.raises(IndexError):
+        bx.bitset.set_ranges_many(sets, [2], [60], [10])
+    with pytest.raises(IndexError):
+        bx.bitset.set_ranges_many(sets, [4], [0], [1])
+    bx.bitset.set_ranges_many(sets, [], [], [])
+
+
 def test_count_ranges_many_vs_oracle(bx, orc):
     """bed_intersect's per-line `bitsets[chrom].count_range(...)` as one launch over several bit sets (strict mode incl.
     inverted sets), with lines naming a chromosome that has no bitset."""
