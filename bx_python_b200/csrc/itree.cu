@@ -284,11 +284,33 @@ struct LdK4 {
             : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(p + 2), "l"(pol));
     }
 };
+// L1: the top sampled level (QS[n8-1], ~80 KB for 10 M items) is read by every query -- LdTop8 asks L1 to keep it
+// (evict_last) while every other index sector is touched once per query at random and would only push it out, so
+// LdK8 does not allocate in L1 (-DFIND_L1_POLICY=0: default L1 behaviour for both).
+#ifndef FIND_L1_POLICY
+#define FIND_L1_POLICY 1
+#endif
 struct LdK8 {
     uint64_t pol;
     __device__ __forceinline__ LdK8() : pol(l2_keep_policy()) {}
     __device__ __forceinline__ void operator()(const int4 *p, int4 &a, int4 &b) const {
+#if FIND_L1_POLICY
+        asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+#else
         asm("ld.global.nc.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+#endif
+            : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p), "l"(pol));
+    }
+};
+struct LdTop8 {
+    uint64_t pol;
+    __device__ __forceinline__ LdTop8() : pol(l2_keep_policy()) {}
+    __device__ __forceinline__ void operator()(const int4 *p, int4 &a, int4 &b) const {
+#if FIND_L1_POLICY
+        asm("ld.global.nc.L1::evict_last.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+#else
+        asm("ld.global.nc.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+#endif
             : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p), "l"(pol));
     }
 };
@@ -300,6 +322,7 @@ __device__ __forceinline__ void st_stream_q(unsigned long long *p, unsigned long
 #else
 typedef Ld4 LdK4;
 typedef Ld8 LdK8;
+typedef Ld8 LdTop8;
 __device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldg(p); }
 __device__ __forceinline__ unsigned long long ld_stream(const unsigned long long *p) { return *p; }
 __device__ __forceinline__ long long ld_stream(const long long *p) { return *p; }
@@ -314,8 +337,8 @@ template <int PROBE, typename SP, typename F>
 __device__ __forceinline__ void query_search_walk(const IndexView &ix, const SP &spS, const SP &spPM, uint32_t seg_lo,
                                                   uint32_t seg_hi, int32_t qe, int32_t qs, uint32_t &hi, uint32_t &lo, F &&f) {
     if (PROBE == 2)
-        bxs::search_walk_probe8(ix.QS, ix.QP, ix.n8, spS, spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdK8(),
-                                Ld1(), hi, lo, f);
+        bxs::search_walk_probe8(ix.QS, ix.QP, ix.n8, spS, spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdTop8(),
+                                LdK8(), Ld1(), hi, lo, f);
     else if (PROBE == 1)
         bxs::search_walk_probe(ix.KS, ix.KP, ix.nk, spS, spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdK4(),
                                LdK8(), Ld1(), hi, lo, f);
@@ -1400,7 +1423,7 @@ k_find_small(IndexView ix, SmallQueries a, int nq, long long *__restrict__ out_o
         if (t >= 0 && t < ix.ntrees) {
             const uint32_t seg_lo = (uint32_t)ix.toff[t], seg_hi = (uint32_t)ix.toff[t + 1];
             bxs::search_walk_probe8(ix.QS, ix.QP, ix.n8, (const int32_t *)s_sp, ix.spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E,
-                                    ix.M, ix.nlev, Ld8(), Ld1(), hi, lo, [&](uint32_t, unsigned m) { c += __popc(m); });
+                                    ix.M, ix.nlev, Ld8(), Ld8(), Ld1(), hi, lo, [&](uint32_t, unsigned m) { c += __popc(m); });
         }
     }
     int incl = c;

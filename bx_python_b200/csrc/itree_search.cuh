@@ -320,12 +320,35 @@ BXG_HD int fls8(unsigned x) {   // 0-based index of the highest set bit of a non
 
 // walk_hits with half-group loads: of each aligned 16-item group only the 8-item halves that intersect [lo, hi) are
 // read (one 32-byte sector each); a half that is not read contributes no hits.
+// E > qs mask of the halves of group k that intersect [lo, hi) (a half that is not read contributes no hits)
+template <typename LD8>
+BXG_HD unsigned group_hits_halves(const int32_t *E, uint32_t k, uint32_t lo, uint32_t hi, int32_t qs, const LD8 &ld8) {
+    unsigned mask = 0;
+    if (lo < k + 8u) mask |= 0xffu & ~sector_mask_le(E + k, qs, ld8);                             // items k..k+7
+    if (hi > k + 8u && lo < k + 16u) mask |= (0xffu & ~sector_mask_le(E + k + 8, qs, ld8)) << 8;
+    if (k < lo) mask &= ~0u << (lo - k);
+    if (k + 16u > hi) mask &= (1u << (hi - k)) - 1u;
+    return mask;
+}
+
 template <typename LD8, typename LD, typename F>
 BXG_HD void walk_hits_halves(const int32_t *E, const int32_t *const *M, int nlev, uint32_t lo, uint32_t hi, int32_t qs,
                              const LD8 &ld8, const LD &ld, F &&f) {
     if (lo >= hi) return;
     uint32_t k = lo & ~15u;
     bool prev_empty = false;
+#ifndef BXS_NO_WALK_PREFETCH
+    // Most walks span two groups.  The loop below decides about group 2 only after group 1's mask is known (a branch
+    // on loaded data), i.e. two dependent memory latencies; issuing both groups' loads up front makes it one.
+    if (k + 16u < hi) {
+        const unsigned m0 = group_hits_halves(E, k, lo, hi, qs, ld8);
+        const unsigned m1 = group_hits_halves(E, k + 16u, lo, hi, qs, ld8);
+        if (m0) f(k, m0);
+        if (m1) f(k + 16u, m1);
+        prev_empty = m1 == 0;
+        k += 32u;
+    }
+#endif
     while (k < hi) {
         if (prev_empty && (k & 31u) == 0 && k + 32u <= hi && ld(M[0] + (k >> 5)) <= qs) {
             uint32_t idx = k >> 5;
@@ -340,11 +363,7 @@ BXG_HD void walk_hits_halves(const int32_t *E, const int32_t *const *M, int nlev
             k = (idx + 1u) << (5 * (lvl + 1));
             continue;
         }
-        unsigned mask = 0;
-        if (lo < k + 8u) mask |= 0xffu & ~sector_mask_le(E + k, qs, ld8);                         // E > qs, items k..k+7
-        if (hi > k + 8u && lo < k + 16u) mask |= (0xffu & ~sector_mask_le(E + k + 8, qs, ld8)) << 8;
-        if (k < lo) mask &= ~0u << (lo - k);
-        if (k + 16u > hi) mask &= (1u << (hi - k)) - 1u;
+        const unsigned mask = group_hits_halves(E, k, lo, hi, qs, ld8);
         prev_empty = mask == 0;
         if (mask) f(k, mask);
         k += 16;
@@ -465,21 +484,25 @@ BXG_HD unsigned sector_mask(const int32_t *p, int32_t key, const LD8 &ld8) {
 }
 
 // one search over the 8-ary levels Q[n8-1] .. Q[0] (Q[0] = the array itself), starting from a splitter window
-template <bool LESS_EQ, typename LD8, typename LD>
-BXG_HD void rounds8(const int32_t *const *Q, int n8, Win &w, int32_t key, const LD8 &ld8, const LD &ld, int last_level) {
+// ld8_top loads the top level (a few tens of KB that every query reads: worth keeping in L1), ld8 the others
+template <bool LESS_EQ, typename LD8T, typename LD8>
+BXG_HD void rounds8(const int32_t *const *Q, int n8, Win &w, int32_t key, const LD8T &ld8_top, const LD8 &ld8,
+                    int last_level) {
     for (int j = n8 - 1; j >= last_level; j--) {
         const int ss = 3 * j;
         const Round r = round_prepare8(w, ss);
-        if (r.active) round_apply(w, r, ss, sector_mask<LESS_EQ>(Q[j] + r.g, key, ld8));
+        if (!r.active) continue;
+        const unsigned m = (j == n8 - 1 && j >= 2) ? sector_mask<LESS_EQ>(Q[j] + r.g, key, ld8_top)
+                                                   : sector_mask<LESS_EQ>(Q[j] + r.g, key, ld8);
+        round_apply(w, r, ss, m);
     }
-    (void)ld;
 }
 
-template <typename SP, typename LD8, typename LD, typename F>
+template <typename SP, typename LD8T, typename LD8, typename LD, typename F>
 BXG_HD void search_walk_probe8(const int32_t *const *QS, const int32_t *const *QP, int n8, const SP &spS, const SP &spPM,
                                int shift, uint32_t seg_lo, uint32_t seg_hi, int32_t qe, int32_t qs, const int32_t *E,
-                               const int32_t *const *M, int nlev, const LD8 &ld8, const LD &ld, uint32_t &hi_out,
-                               uint32_t &lo_out, F &&f) {
+                               const int32_t *const *M, int nlev, const LD8T &ld8_top, const LD8 &ld8, const LD &ld,
+                               uint32_t &hi_out, uint32_t &lo_out, F &&f) {
     hi_out = lo_out = seg_hi;
     if (seg_lo >= seg_hi) return;
     const uint32_t k0 = (seg_lo + (1u << shift) - 1) >> shift, k1 = ((seg_hi - 1) >> shift) + 1;
@@ -490,7 +513,7 @@ BXG_HD void search_walk_probe8(const int32_t *const *QS, const int32_t *const *Q
         for (uint32_t step = step0; step > 0; step >>= 1) a_s = lift_step<false>(spS, a_s, step, k1, qe);
     }
     Win ws = splitter_window(a_s, k0, k1, shift, seg_lo, seg_hi);
-    rounds8<false>(QS, n8, ws, qe, ld8, ld, 1);
+    rounds8<false>(QS, n8, ws, qe, ld8_top, ld8, 1);
     // final S round (one sector of S) together with the probe sector of QP[1]; without a sampled level (tiny index) the
     // walk simply starts at the front of the segment
     const Round rs = round_prepare8(ws, 0);
@@ -534,7 +557,7 @@ BXG_HD void search_walk_probe8(const int32_t *const *QS, const int32_t *const *Q
             uint32_t a_p = k0;
             for (uint32_t step = step0; step > 0; step >>= 1) a_p = lift_step<true>(spPM, a_p, step, k1, qs);
             Win wp = splitter_window(a_p, k0, k1, shift, seg_lo, seg_hi);
-            rounds8<true>(QP, n8, wp, qs, ld8, ld, 1);
+            rounds8<true>(QP, n8, wp, qs, ld8, ld8, 1);
             lo_c = wp.lo;
         }
     }

@@ -192,7 +192,7 @@ int main(int argc, char **argv) {
                 std::vector<uint32_t> got4;
                 uint32_t hi4, lo4;
                 bxs::search_walk_probe8(QS.data(), QP.data(), n8, spS.data(), spPM.data(), shift, toff[t], toff[t + 1], qe,
-                                        qs, E.data(), Mp.data(), (int)Mp.size(), ld8, ld, hi4, lo4,
+                                        qs, E.data(), Mp.data(), (int)Mp.size(), ld8, ld8, ld, hi4, lo4,
                                         [&](uint32_t k0, unsigned mask) {
                                             while (mask) {
                                                 int b = bxs::ffs32(mask) - 1;
