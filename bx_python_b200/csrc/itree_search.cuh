@@ -337,9 +337,10 @@ BXG_HD void walk_hits_halves(const int32_t *E, const int32_t *const *M, int nlev
     if (lo >= hi) return;
     uint32_t k = lo & ~15u;
     bool prev_empty = false;
-#ifndef BXS_NO_WALK_PREFETCH
+#ifdef BXS_WALK_PREFETCH
     // Most walks span two groups.  The loop below decides about group 2 only after group 1's mask is known (a branch
     // on loaded data), i.e. two dependent memory latencies; issuing both groups' loads up front makes it one.
+    // Measured SLOWER on B200 (count kernel 0.427 -> 0.460 ms, profiles/r01z): kept as an opt-in experiment.
     if (k + 16u < hi) {
         const unsigned m0 = group_hits_halves(E, k, lo, hi, qs, ld8);
         const unsigned m1 = group_hits_halves(E, k + 16u, lo, hi, qs, ld8);

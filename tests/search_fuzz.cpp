@@ -7,6 +7,9 @@
 #include <cstdlib>
 #include <vector>
 
+#ifdef FUZZ_WALK_PREFETCH
+#define BXS_WALK_PREFETCH
+#endif
 #include "../bx_python_b200/csrc/itree_search.cuh"
 
 static uint32_t rnd_state = 12345;
