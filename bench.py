@@ -482,9 +482,9 @@ def run_ours(args):
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dom_ms,
-                "note": "find is not HBM-bound (SURVEY 8d): one divergent 64-byte group read per lane and search round makes the "
-                        "count kernel L1 data-pipe (wavefront) bound -- ncu l1tex__data_pipe_lsu_wavefronts, profiles/; "
-                        "frac is reported, not targeted"}
+                "note": "find is not HBM-bound (SURVEY 8d): every query is a dependent chain of ~5 random 32-byte sector reads "
+                        "(8-ary sampled levels, probe, E halves) over an 85 MB index; the count kernel is latency-bound with the "
+                        "L1 wavefront pipe ~60 % busy (ncu, profiles/) -- frac is reported, not targeted"}
     step_ms = sum(v["avg_ms"] * v["launches"] for v in kern.values()) / args.steps
     extra["kernels"] = {k: {"avg_ms": round(v["avg_ms"], 4), "per_step": v["launches"] / args.steps,
                             "share": round(v["avg_ms"] * v["launches"] / args.steps / step_ms, 4)} for k, v in kern.items()}
@@ -494,6 +494,20 @@ def run_ours(args):
     extra["scalar_api"] = bench_scalar_api(db)
     if not args.no_bitset:
         extra["bitset"] = bench_bitset(args, peak, peak_src)
+        # BASELINE.json's metric has two halves (queries/s and bitset-AND GB/s against the HBM roof): surface the second one
+        # next to the find kernel's entry -- the genome-wide AND launch (configs[2]), kernel-only, CUDA events per launch
+        bk = extra["bitset"].get("kernels", {}).get("k_binop_batch<OP_AND, false>")
+        if bk:
+            tj = {}
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            except (OSError, ValueError):
+                pass
+            roofline["bitset_and"] = {
+                "kernel": "k_binop_batch<OP_AND, false>", "bound": "hbm", "achieved": bk["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": bk["frac"], "traffic": tj.get("k_binop_batch<0, 0>"),
+                "algorithmic_bytes_per_launch": extra["bitset"]["algorithmic_bytes_per_pass"], "avg_launch_ms": bk["avg_ms"],
+                "workload": "a &= b over 24 hg38-length bitmap pairs (3.09 Gbit per operand set), one launch"}
         extra["bed_intersect"] = bench_bed_intersect(peak)
         extra["aggregate"] = bench_aggregate(peak)
         extra["score_sources"] = bench_score_sources(peak)
@@ -931,7 +945,7 @@ def bench_score_sources(peak):
         alg = 12 * k + 4 * n
         out[f"set_spans_{tag}"] = {"ms": ms, "records": k, "bases_per_s": n / (ms * 1e-3), "algorithmic_bytes": alg,
                                    "gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
-                                   "note": "includes the sorted/disjoint check kernel and its 24-byte D2H round trip"}
+                                   "note": "one pass (write + sortedness check) and the 24-byte D2H round trip of its flags"}
         L.bxg_scores_free(h)
     # overlapping batch -> owner/apply path
     k = 1_000_000

@@ -527,6 +527,7 @@ BXG_HD void search_walk_probe8(const int32_t *const *QS, const int32_t *const *Q
     hi_out = lo_out = hi;
     if (hi <= seg_lo) return;                          // no item starts before qe
     uint32_t lo_c = seg_lo;
+    bool found = false;
     if (n8 >= 2) {
         const uint32_t m_hi = (hi - 1u) >> 3;          // sample block of the last candidate
         if (m_hi < sb) {
@@ -534,7 +535,6 @@ BXG_HD void search_walk_probe8(const int32_t *const *QS, const int32_t *const *Q
             pm_le = sector_mask<true>(QP[1] + sb, qs, ld8);
         }
         const uint32_t jmin = (seg_lo + 7u) >> 3;      // first sample position inside the segment
-        bool found = false;
         for (int tries = 0; tries < 3; tries++) {
             unsigned valid = 0xffu;
             if (m_hi < sb + 7u) valid &= (2u << (m_hi - sb)) - 1u;
@@ -554,13 +554,13 @@ BXG_HD void search_walk_probe8(const int32_t *const *QS, const int32_t *const *Q
             sb -= 8u;
             pm_le = sector_mask<true>(QP[1] + sb, qs, ld8);
         }
-        if (!found) {                                  // something long is open in front: the full PM search (coarse)
-            uint32_t a_p = k0;
-            for (uint32_t step = step0; step > 0; step >>= 1) a_p = lift_step<true>(spPM, a_p, step, k1, qs);
-            Win wp = splitter_window(a_p, k0, k1, shift, seg_lo, seg_hi);
-            rounds8<true>(QP, n8, wp, qs, ld8, ld8, 1);
-            lo_c = wp.lo;
-        }
+    }
+    if (!found) {   // something long is open in front, or an index too small for sampled levels: the PM search (coarse)
+        uint32_t a_p = k0;
+        for (uint32_t step = step0; step > 0; step >>= 1) a_p = lift_step<true>(spPM, a_p, step, k1, qs);
+        Win wp = splitter_window(a_p, k0, k1, shift, seg_lo, seg_hi);
+        rounds8<true>(QP, n8, wp, qs, ld8, ld8, 1);
+        lo_c = wp.lo;
     }
     const uint32_t lo = lo_c < hi ? lo_c : hi;
     lo_out = lo;
