@@ -57,6 +57,62 @@ int main(void) {
         printf("\n");
     }
     printf("total %lld\n", (long long)total);
+    /* the same through the small-batch entry point (scalar IntervalTree.find) and with int32 offsets */
+    const int64_t *soff;
+    const int32_t *shits;
+    CHK(bxg_itree_find_small(t, NULL, fs, fe, 4, &soff, &shits, &total));
+    for (int q = 0; q < 4; q++) {
+        printf("small %d:", q);
+        for (int64_t k = soff[q]; k < soff[q + 1]; k++) printf(" %d", shits[k]);
+        printf("\n");
+    }
+    const int32_t *off32;
+    CHK(bxg_itree_find_host32(t, NULL, fs, fe, 4, &off32, &hits, &total));
+    printf("off32 %d %d %d %d %d\n", off32[0], off32[1], off32[2], off32[3], off32[4]);
+    /* join: left intervals against the tree's items, mincols = 3 (join.py:35-50) */
+    int32_t ls[2] = {0, 18}, le[2] = {16, 40};
+    int64_t npairs = 0;
+    CHK(bxg_itree_join(t, NULL, ls, le, 2, s, e, 3, BXG_HOST, &npairs));
+    int64_t poff[3];
+    int32_t pitems[16];
+    uint8_t visited[5];
+    CHK(bxg_itree_join_fetch(poff, pitems, visited));
+    printf("join %lld:", (long long)npairs);
+    for (int q = 0; q < 2; q++) {
+        for (int64_t k = poff[q]; k < poff[q + 1]; k++) printf(" %d>%d", q, pitems[k]);
+    }
+    printf(" visited %d%d%d%d%d\n", visited[0], visited[1], visited[2], visited[3], visited[4]);
     CHK(bxg_itree_free(t));
+
+    /* score sources: a 64-cell track, ordered span writes (the last record wins), reads, a bigWig-style summary */
+    bxg_scores_t *sc;
+    CHK(bxg_scores_alloc(64, 0, -1.0f, &sc));
+    int32_t ps[3] = {2, 4, 3}, pe[3] = {6, 5, 4};
+    float pv[3] = {1.0f, 2.0f, 3.0f};
+    CHK(bxg_scores_set_spans(sc, ps, pe, pv, 3, BXG_HOST));
+    float cells[8];
+    CHK(bxg_scores_get_range(sc, 0, 8, cells));
+    printf("cells");
+    for (int i = 0; i < 8; i++) printf(" %g", cells[i]);
+    printf("\n");
+    CHK(bxg_scores_free(sc));
+    int32_t is_[3] = {0, 5, 9}, ie[3] = {5, 8, 20};
+    float iv[3] = {1.5f, 2.5f, -1.0f};
+    double vc[3] = {0, 0, 0}, mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0}, sm[3] = {0, 0, 0}, sq[3] = {0, 0, 0};
+    CHK(bxg_summarize(is_, ie, iv, 3, BXG_HOST, 0, 21, 3, vc, mn, mx, sm, sq));
+    printf("summary %g %g %g | %g %g %g | %g %g %g\n", vc[0], vc[1], vc[2], sm[0], sm[1], sm[2], sq[0], sq[1], sq[2]);
+
+    /* genome-wide set_range: two bitmaps, one launch */
+    bxg_bits_t *g[2];
+    CHK(bxg_bits_create(1000, 10, &g[0]));
+    CHK(bxg_bits_create(500, 10, &g[1]));
+    int32_t gw[3] = {1, 0, 1}, gs[3] = {10, 0, 400}, gc[3] = {20, 300, 100};
+    CHK(bxg_bits_set_ranges_multi(g, 2, gw, gs, gc, 3, BXG_HOST));
+    int64_t c0 = 0, c1 = 0;
+    CHK(bxg_bits_count_all(g[0], &c0));
+    CHK(bxg_bits_count_all(g[1], &c1));
+    printf("multi %lld %lld\n", (long long)c0, (long long)c1);
+    CHK(bxg_bits_free(g[0]));
+    CHK(bxg_bits_free(g[1]));
     return 0;
 }
