@@ -15,20 +15,26 @@ const uint64_t *bxg_bits_words_internal(const bxg_bits *b);
 int32_t bxg_bits_size_internal(const bxg_bits *b);
 
 // one window: strict left-to-right float32 accumulation over positions [ws,we) of one track
-__device__ __forceinline__ void aggregate_window(const float *__restrict__ v, int64_t n, int64_t origin,
+__device__ __forceinline__ void aggregate_window(const float *__restrict__ v, int64_t n, int64_t origin, float fill,
                                                  const uint64_t *__restrict__ mask, int64_t mask_size, int64_t ws, int64_t we,
                                                  float &sum, float &avg, int32_t &cnt, float &mn, float &mx) {
     int64_t a = ws - origin, b = we - origin;
-    if (a < 0) a = 0;                     // positions without a score read as NaN -> skipped
-    if (b > n) b = n;
+    // positions outside the track read as the array's default (BinnedArray.get, binned_array.py:89-94): NaN or 0.0 --
+    // both skipped by the script -- for every array the script itself builds, so the window is clipped to the track;
+    // any other default (a FileBinnedArray written with one) counts, and the window is walked in full
+    const bool fill_counts = !(fill == 0.0f || fill != fill);
+    if (!fill_counts) {
+        if (a < 0) a = 0;
+        if (b > n) b = n;
+    }
     float total = 0.0f, lo = 100000000.0f, hi = -100000000.0f;   // script sentinels (:112-113), exact in float32
     int32_t c = 0;
     for (int64_t i = a; i < b; i++) {
-        float s = __ldg(v + i);
+        float s = (i >= 0 && i < n) ? __ldg(v + i) : fill;
         if (s == 0.0f || s != s) continue;
         if (mask) {
             int64_t p = i + origin;
-            if (p < mask_size && ((__ldg((const unsigned long long *)mask + (p >> 6)) >> (p & 63)) & 1ull)) continue;
+            if (p >= 0 && p < mask_size && ((__ldg((const unsigned long long *)mask + (p >> 6)) >> (p & 63)) & 1ull)) continue;
         }
         total = __fadd_rn(total, s);      // strict left-to-right float32 (no fma contraction possible, but be explicit)
         c++;
@@ -48,19 +54,20 @@ __device__ __forceinline__ void aggregate_window(const float *__restrict__ v, in
 }
 
 __global__ void __launch_bounds__(256)
-k_aggregate(const float *__restrict__ v, int64_t n, int64_t origin, const uint64_t *__restrict__ mask, int64_t mask_size,
+k_aggregate(const float *__restrict__ v, int64_t n, int64_t origin, float fill, const uint64_t *__restrict__ mask, int64_t mask_size,
             const int32_t *__restrict__ ws, const int32_t *__restrict__ we, int64_t nw,
             float *__restrict__ sum, float *__restrict__ avg, int32_t *__restrict__ cnt, float *__restrict__ mn,
             float *__restrict__ mx) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += stride)
-        aggregate_window(v, n, origin, mask, mask_size, __ldg(ws + w), __ldg(we + w), sum[w], avg[w], cnt[w], mn[w], mx[w]);
+        aggregate_window(v, n, origin, fill, mask, mask_size, __ldg(ws + w), __ldg(we + w), sum[w], avg[w], cnt[w], mn[w], mx[w]);
 }
 
 // genome-wide form: every window names its track (chromosome); one launch for the whole BED file
 struct TrackDesc {
     const float *v;
     int64_t n, origin;
+    float fill;
     const uint64_t *mask;
     int64_t mask_size;
 };
@@ -75,7 +82,7 @@ k_aggregate_multi(const TrackDesc *__restrict__ tracks, int ntracks, const int32
         const int32_t t = __ldg(wt + w);
         if (t >= 0 && t < ntracks) {
             const TrackDesc d = tracks[t];
-            aggregate_window(d.v, d.n, d.origin, d.mask, d.mask_size, __ldg(ws + w), __ldg(we + w), sum[w], avg[w], cnt[w],
+            aggregate_window(d.v, d.n, d.origin, d.fill, d.mask, d.mask_size, __ldg(ws + w), __ldg(we + w), sum[w], avg[w], cnt[w],
                              mn[w], mx[w]);
         } else {                          // `chrom not in scores_by_chrom` (:115): nothing counted
             const float qnan = __int_as_float(0x7fc00000);
@@ -130,7 +137,7 @@ int bxg_aggregate(const bxg_scores_t *s, const bxg_bits_t *mask, const int32_t *
         dmx = dmn + nw;
         dcnt = (int32_t *)(dmx + nw);
     }
-    BXG_LAUNCH(k_aggregate, grid_for(cdiv(nw, 256), 8), 256, 0, s->v, s->n, (int64_t)s->origin,
+    BXG_LAUNCH(k_aggregate, grid_for(cdiv(nw, 256), 8), 256, 0, s->v, s->n, (int64_t)s->origin, s->fill,
                bxg_bits_words_internal((const bxg_bits *)mask), (int64_t)bxg_bits_size_internal((const bxg_bits *)mask),
                (const int32_t *)dws, (const int32_t *)dwe, nw, dsum, davg, dcnt, dmn, dmx);
     if (loc == BXG_HOST) {
@@ -156,7 +163,7 @@ int bxg_aggregate_multi(const bxg_scores_t *const *tracks, const bxg_bits_t *con
     for (int t = 0; t < ntracks; t++) {
         if (!tracks[t]) return set_error(BXG_ERR_ARG, "null scores handle %d", t);
         const bxg_bits *m = masks ? (const bxg_bits *)masks[t] : nullptr;
-        h_desc[t] = TrackDesc{tracks[t]->v, tracks[t]->n, (int64_t)tracks[t]->origin, bxg_bits_words_internal(m),
+        h_desc[t] = TrackDesc{tracks[t]->v, tracks[t]->n, (int64_t)tracks[t]->origin, tracks[t]->fill, bxg_bits_words_internal(m),
                               (int64_t)bxg_bits_size_internal(m)};
     }
     void *d_desc;

@@ -197,6 +197,23 @@ def test_aggregate_script_golden():
         assert lines[-1] == ["chrUn", "5", "50", "nan", "nan", "nan"]
 
 
+def test_aggregate_nonnan_default_counts_outside_the_track():
+    """A BinnedArray whose default is neither NaN nor 0 contributes that default for positions nobody set -- also
+    beyond the highest written bin (binned_array.py:89-94 feeding the script's loop, :113-124)."""
+    from bx_python_b200 import aggregate
+    from bx_python_b200.binned_array import BinnedArray
+    ba = BinnedArray(bin_size=16, default=2.0, max_size=256)
+    ba.set_many([3, 4], [5.0, 0.0])
+    res = aggregate.aggregate_genome([ba], [0, 0], [0, 100], [8, 104])
+    # window [0,8): 2,2,2,5,(0 skipped),2,2,2 ; window [100,104): four defaults beyond the device track
+    assert res["count"].tolist() == [7, 4]
+    assert res["sum"].tolist() == [17.0, 8.0] and res["min"].tolist() == [2.0, 2.0] and res["max"].tolist() == [5.0, 2.0]
+    nan_default = BinnedArray(bin_size=16, max_size=256)
+    nan_default.set_many([3], [5.0])
+    res = aggregate.aggregate_genome([nan_default], [0, 0], [0, 100], [8, 104])
+    assert res["count"].tolist() == [1, 0]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # bigWig summary
 # ---------------------------------------------------------------------------------------------------------------
