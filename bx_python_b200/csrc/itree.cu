@@ -559,6 +559,25 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 
+// hits of one query into `out`, from the masks the count walk kept in registers (E is not read again; only the halves
+// of the I groups that hold a hit are loaded), or by re-walking when the walk was too long for the stash
+template <typename SINK>
+__device__ __forceinline__ void emit_query(const IndexView &ix, const MaskStash &st, uint32_t hi, int32_t qs, SINK &out) {
+    if (!st.overflow) {
+        unsigned long long m = st.m;
+        uint32_t k0 = st.base;
+        while (m) {
+            const unsigned mk = (unsigned)(m & 0xffffull);
+            if (mk) bxs::emit_group_halves_to(ix.WI, k0, mk, out, Ld8());
+            m >>= 16;
+            k0 += 16;
+        }
+    } else {
+        bxs::walk_hits_halves(ix.WE, ix.M, ix.nlev, st.base, hi, qs, Ld8(), Ld1(),
+                              [&](uint32_t k0, unsigned mask) { bxs::emit_group_halves_to(ix.WI, k0, mask, out, Ld8()); });
+    }
+}
+
 template <int PROBE>
 __global__ void __launch_bounds__(FUSED_THREADS, FIND_MIN_CTAS)
 k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, const int32_t *__restrict__ qs_,
@@ -625,25 +644,12 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
         __syncthreads();
         const long long base = s_base;
         const bool fits = base + tile_total <= hits_cap;
-        if (q < nq) {
-            off[q] = base + excl;
-            if (fits && c > 0) {
-                int32_t *dst = hits + base + excl;
-                if (!st.overflow) {                            // emit from the masks kept in registers: E is not read again
-                    unsigned long long m = st.m;
-                    uint32_t k0 = st.base;
-                    while (m) {
-                        const unsigned mk = (unsigned)(m & 0xffffull);
-                        if (mk) dst = bxs::emit_group(ix.WI, k0, mk, dst, Ld4(), ix.mul);
-                        m >>= 16;
-                        k0 += 16;
-                    }
-                } else {
-                    bxs::walk_hits(ix.WE, ix.M, ix.nlev, st.base, hi, qs, Ld4(), Ld1(),
-                                   [&](uint32_t k0, unsigned mask) { dst = bxs::emit_group(ix.WI, k0, mask, dst, Ld4(), ix.mul); },
-                                   bxs::NoPrefetch(), ix.mul);
-                }
-            }
+        if (q < nq) off[q] = base + excl;
+        if (fits && c > 0) {
+            // direct stores: staging the warp's span through shared memory, as k_fill_staged does, was measured SLOWER
+            // here (single-pass 0.81 -> 1.05 ms per 10 M queries, profiles/r01g2): the tile loop is already barrier-bound
+            bxs::PtrSink out{hits + base + excl};
+            emit_query(ix, st, hi, qs, out);
         }
         if (threadIdx.x == 0) {
             if (!fits) result[1] = 1;
