@@ -260,7 +260,7 @@ def run_ours(args):
     from bx_python_b200._lib import check, ptr
     from bx_python_b200.intervals import IntervalForest
     L = _lib.lib()
-    numa = _lib.bind_to_gpu_numa_node() if world > 1 else "single rank: not bound"
+    numa = _lib.bind_to_gpu_numa_node()       # sysfs, or a copy-rate probe where sysfs reports no node; never raises
     comm = Comm("nccl")
     info = _lib.device_info()
     t_gen = time.perf_counter()

@@ -206,28 +206,85 @@ def device_info() -> dict:
     return {"name": name.value.decode(), "sm_count": sm.value, "total_mem": mem.value, "cc": (maj.value, mnr.value)}
 
 
+def _numa_nodes() -> dict:
+    """{node: set(cpus)} from sysfs (empty when the kernel exposes no NUMA topology)."""
+    import glob
+    nodes = {}
+    for d in glob.glob("/sys/devices/system/node/node[0-9]*"):
+        try:
+            cpus = set()
+            for part in open(os.path.join(d, "cpulist")).read().strip().split(","):
+                if part:
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            nodes[int(d.rsplit("node", 1)[1])] = cpus
+        except (OSError, ValueError):
+            continue
+    return nodes
+
+
+def _probe_numa_node(allowed) -> str:
+    """sysfs does not say which NUMA node the GPU hangs off (virtualised boxes report -1): measure it.  For every node
+    with usable CPUs, run on that node, allocate pinned memory there (cudaMallocHost places pages on the caller's node)
+    and time device-to-host copies; stay on the fastest node if it is clearly (> 10 %) faster than the slowest."""
+    cand = {k: c & allowed for k, c in _numa_nodes().items() if c & allowed}
+    if len(cand) < 2:
+        return "NUMA affinity unknown and fewer than two nodes to probe"
+    import time
+    L = lib()
+    n = 16 << 20
+    dev = DeviceBuffer(np.zeros(n, np.int32))
+    rates = {}
+    for k, cpus in sorted(cand.items()):
+        os.sched_setaffinity(0, cpus)
+        pin = PinnedArray(n, np.int32)
+        pin.array[:] = 0
+        check(L.bxg_memcpy_d2h(ptr(pin.array), dev.ptr, n * 4))
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            check(L.bxg_memcpy_d2h(ptr(pin.array), dev.ptr, n * 4))
+        sync()
+        rates[k] = 3 * n * 4 / (time.perf_counter() - t0) / 1e9
+        del pin
+    best = max(rates, key=rates.get)
+    shown = ", ".join(f"node {k}: {v:.1f} GB/s" for k, v in sorted(rates.items()))
+    if rates[best] > 1.1 * min(rates.values()):
+        os.sched_setaffinity(0, cand[best])
+        return f"probed D2H ({shown}): bound to NUMA node {best} ({len(cand[best])} CPUs)"
+    os.sched_setaffinity(0, allowed)
+    return f"probed D2H ({shown}): no clear winner, not bound"
+
+
 def bind_to_gpu_numa_node() -> str:
     """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers allocated afterwards
     (first touch) and the copy threads are local to the GPU's PCIe root.  Matters when several ranks share a two-socket
-    host.  Returns a short description; never raises (a box without sysfs NUMA info is left alone)."""
+    host (measured: 39.6 instead of 57 GB/s device-to-host from the far socket).  The node comes from sysfs, or, where
+    sysfs reports none, from a short copy-rate probe.  Returns a short description; never raises."""
+    allowed = None
     try:
+        allowed = os.sched_getaffinity(0)
         buf = C.create_string_buffer(64)
         check(lib().bxg_device_pci_bus_id(buf, 64))
         bus = buf.value.decode().lower()
-        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        try:
+            node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        except (OSError, ValueError):
+            node = -1
         if node < 0:
-            return f"{bus}: no NUMA affinity reported"
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
+            return f"{bus}: " + _probe_numa_node(allowed)
+        cpus = _numa_nodes().get(node, set()) & allowed
         if not cpus:
             return f"{bus}: NUMA node {node} has no usable CPU"
         os.sched_setaffinity(0, cpus)
         return f"{bus}: bound to NUMA node {node} ({len(cpus)} CPUs)"
-    except (OSError, ValueError, RuntimeError) as e:
-        return f"not bound ({e})"
+    except Exception as e:                             # noqa: BLE001 -- a tuning aid must never take the run down
+        try:
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+        except OSError:
+            pass
+        return f"not bound ({type(e).__name__}: {e})"
 
 
 class Timer:
