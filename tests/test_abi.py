@@ -79,3 +79,50 @@ def test_host_side_checks_match_reference_messages():
     assert repr(Interval(3, 7, value=5)) == "Interval(3, 7, value=5)"
     assert IntervalTree().find(100, 300) == []
     assert IntervalTree().traverse(lambda x: None) is None
+
+
+def header_prototypes():
+    """{name: [parameter type class, ...]} parsed from include/bxb200.h (classes: ptr, i32, i64, u32, f32, f64)."""
+    src = open(os.path.join(ROOT, "include", "bxb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for name, params in re.findall(r"\b(bxg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src, flags=re.S):
+        classes = []
+        for p in (q.strip() for q in params.split(",")):
+            if p in ("", "void"):
+                continue
+            if "*" in p or "[" in p:
+                classes.append("ptr")
+            elif "float" in p:
+                classes.append("f32")
+            elif "double" in p:
+                classes.append("f64")
+            elif "int64_t" in p:
+                classes.append("i64")
+            elif "uint32_t" in p:
+                classes.append("u32")
+            elif "int32_t" in p:
+                classes.append("i32")
+            else:
+                assert re.match(r"(const )?int\b", p), (name, p)
+                classes.append("i32")                  # int is 32 bits on every platform this library targets
+        out[name] = classes
+    return out
+
+
+def test_python_binding_matches_header_prototypes():
+    """Guards the hand-written ctypes table against ABI drift: same parameter count and the same kind of type
+    (pointer / 32-bit / 64-bit / float / double) in every position as the C prototype."""
+    from bx_python_b200 import _lib
+    kind = {C.c_int32: "i32", C.c_int: "i32", C.c_int64: "i64", C.c_uint32: "u32", C.c_float: "f32", C.c_double: "f64"}
+
+    def classify(t):
+        if t in kind:
+            return kind[t]
+        assert t in (C.c_void_p, C.c_char_p) or issubclass(t, C._Pointer), t
+        return "ptr"
+    protos = header_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, classes in protos.items():
+        got = [classify(t) for t in _lib.SIGNATURES[name]]
+        assert got == classes, (name, got, classes)
