@@ -103,3 +103,26 @@ def test_quicksect_traverse_order():
     t.traverse(lambda n: seen.append(n.linenum))
     # chromosomes in order of first insert; by start; among equal starts the later insert first (quicksect.py:52-70)
     assert seen == [3, 5, 2, 0, 4, 1]
+
+
+def test_wiggle_reference_known_answers():
+    """The known answers of lib/bx/wiggle_tests.py:44-92 (UCSC's three-format example: a bedGraph section, a
+    variableStep block with span=4, a fixedStep block with step=300 span=3, browser / track / comment lines between)."""
+    text = "\n".join([
+        "browser position chr19:59302001-59311000", "browser hide all", "#\tcomment",
+        'track type=wiggle_0 name="Bed Format" priority=20',
+        "chr19 59302000 59302005 -1.0", "chr19 59302300 59302305 -0.75",
+        "#\tcomment", 'track type=wiggle_0 name="variableStep" priority=10',
+        "variableStep chrom=chr19 span=4", "59304701 10.0", "59304901 12.5",
+        'track type=wiggle_0 name="fixedStep" priority=30',
+        "fixedStep chrom=chr19 start=59307401 step=300 span=3", "1000", " 900", " 800", ""])
+    got = [",".join(map(str, v)) for v in wiggle.IntervalReader(io.StringIO(text))]
+    assert got == ["chr19,59302000,59302005,+,-1.0", "chr19,59302300,59302305,+,-0.75", "chr19,59304700,59304704,+,10.0",
+                   "chr19,59304900,59304904,+,12.5", "chr19,59307400,59307403,+,1000.0", "chr19,59307700,59307703,+,900.0",
+                   "chr19,59308000,59308003,+,800.0"]
+    pos = [",".join(map(str, v)) for v in wiggle.Reader(io.StringIO(text))]
+    assert len(pos) == 27 and pos[0] == "chr19,59302000,-1.0" and pos[9] == "chr19,59302304,-0.75"
+    assert pos[10] == "chr19,59304700,10.0" and pos[18:21] == ["chr19,59307400,1000.0", "chr19,59307401,1000.0",
+                                                              "chr19,59307402,1000.0"] and pos[-1] == "chr19,59308002,800.0"
+    spans = wiggle.read_spans(io.StringIO(text))
+    assert list(spans) == ["chr19"] and spans["chr19"][0].tolist()[:3] == [59302000, 59302300, 59304700]
