@@ -12,6 +12,16 @@
 #endif
 #include "../bx_python_b200/csrc/itree_search.cuh"
 
+// -DFUZZ_OFFSET=<n> shifts every coordinate by n with saturation: FUZZ_OFFSET=2147400000 exercises the top of the int32
+// range (items and queries that touch INT32_MAX, where the padding values of the sampled levels live), a negative
+// offset the bottom.
+#ifndef FUZZ_OFFSET
+#define FUZZ_OFFSET 0
+#endif
+static int32_t shifted(long long v) {
+    v += (long long)FUZZ_OFFSET;
+    return (int32_t)std::min<long long>(INT_MAX, std::max<long long>(INT_MIN, v));
+}
 static uint32_t rnd_state = 12345;
 static uint32_t rnd() {
     rnd_state = rnd_state * 1664525u + 1013904223u;
@@ -37,14 +47,14 @@ int main(int argc, char **argv) {
         const long npad = ((n + 15) & ~15l) + 16;
         std::vector<int32_t> S(npad, INT_MAX), PM(npad, INT_MAX), E(npad, INT_MIN);
         for (int t = 0; t < ntrees; t++) {
-            for (uint32_t i = toff[t]; i < toff[t + 1]; i++) S[i] = (int)(rnd() % (uint32_t)range) - 50;
+            for (uint32_t i = toff[t]; i < toff[t + 1]; i++) S[i] = shifted((long long)(rnd() % (uint32_t)range) - 50);
             std::sort(S.begin() + toff[t], S.begin() + toff[t + 1]);
             int pm = INT_MIN;
             const bool adversarial = trial % 5 == 0;
             for (uint32_t i = toff[t]; i < toff[t + 1]; i++) {
                 int len = (int)(rnd() % 40) - 2;
                 if (adversarial && i < toff[t] + 2) len = range * 2;     // chromosome-long items in front
-                E[i] = S[i] + len;
+                E[i] = (int32_t)std::min<long long>(INT_MAX, std::max<long long>(INT_MIN, (long long)S[i] + len));
                 pm = std::max(pm, E[i]);
                 PM[i] = pm;
             }
@@ -124,8 +134,8 @@ int main(int argc, char **argv) {
         }
         for (int q = 0; q < 150; q++) {
             const int t = (int)(rnd() % (uint32_t)ntrees);
-            const int32_t qs = (int)(rnd() % (uint32_t)(range + 40)) - 70;
-            const int32_t qe = qs + (int)(rnd() % 60) - 5;
+            const int32_t qs = shifted((long long)(rnd() % (uint32_t)(range + 40)) - 70);
+            const int32_t qe = (int32_t)std::min<long long>(INT_MAX, std::max<long long>(INT_MIN, (long long)qs + (int)(rnd() % 60) - 5));
             uint32_t hi, lo;
             const bool coarse = (q % 2) == 1;      // coarse_lo: lo may be up to 15 items early, never late
             bxs::dual_search(KS.data(), KP.data(), nk, spS.data(), spPM.data(), shift, toff[t], toff[t + 1], qe, qs, ld4,
