@@ -516,6 +516,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         cpu = cpu_baseline(db, qq)
+        extra["cpu_reference"] = cpu_reference_extras()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -570,6 +571,69 @@ def cpu_baseline(db, qq):
     dt = time.perf_counter() - t0
     return {"value": len(qq[c][0]) / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"chr21 shard: {len(db[c][0])} intervals, {len(qq[c][0])} queries; C restatement (oracle/bx_oracle.c)"}
+
+
+def cpu_reference_extras():
+    """The reference's own CPU path for the other halves of the metric, timed on this box's host cores (one thread: the
+    reference holds the GIL) on bounded samples: bitset AND / count over one chr1-length BinnedBitSet pair (249 Mbp,
+    built from the C3 law), the set_range / count_range call loop of bed_intersect, and the per-base loop of
+    aggregate_scores_in_intervals.  Uses oracle/_ref (the unmodified reference compiled here); returns {} without it.
+    No GPU work; never raises (a failure is reported as a string)."""
+    try:
+        from oracle import oracle as orc
+        if not orc.ref_available():
+            return {}
+        bs, _ = orc.ref_modules()
+        size = int(synth.HG38_LENS[0])
+        nranges = int(400_000 * size / 250_000_000)
+        (sa, ca), (sb, cb), (ps, pc) = synth.c3_case(size, nranges, 3000, nq=20000)
+        a, b = bs.BinnedBitSet(size), bs.BinnedBitSet(size)
+        t0 = time.perf_counter()
+        for s_, c_ in zip(sa.tolist(), ca.tolist()):
+            a.set_range(s_, c_)
+        t_set = time.perf_counter() - t0
+        for s_, c_ in zip(sb.tolist(), cb.tolist()):
+            b.set_range(s_, c_)
+        t0 = time.perf_counter()
+        a.iand(b)
+        t_and = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        total = a.count_range(0, size)
+        t_cnt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for s_, c_ in zip(ps.tolist(), pc.tolist()):
+            a.count_range(s_, c_)
+        t_q = time.perf_counter() - t0
+        nbytes = 3 * ((size + 63) // 64) * 8
+        out = {"kind": "reference", "cores": 1,
+               "sample": f"one chr1-length BinnedBitSet pair ({size} bits, {nranges} set_range calls each), unmodified bx.bitset",
+               "bitset_and": {"ms": t_and * 1e3, "gbs": nbytes / t_and / 1e9, "algorithmic_bytes": nbytes},
+               "count_all": {"ms": t_cnt * 1e3, "gbs": nbytes / 3 / t_cnt / 1e9, "bits_set": int(total)},
+               "set_range": {"calls_per_s": len(sa) / t_set}, "count_range": {"calls_per_s": len(ps) / t_q}}
+        # aggregate: the script's per-base loop (scripts/aggregate_scores_in_intervals.py:107-124) over a dense float32 list
+        rng = np.random.default_rng(5003)
+        v = synth.aggregate_scores(rng, 200_000)
+        ws = rng.integers(0, len(v) - 50, 20_000)
+        we = ws + rng.integers(1, 41, 20_000)
+        t0 = time.perf_counter()
+        acc = 0
+        for a_, b_ in zip(ws.tolist(), we.tolist()):
+            tot, cnt = 0, 0
+            for i in range(a_, b_):
+                sc = v[i]
+                if sc and sc == sc:
+                    tot += sc
+                    cnt += 1
+            acc += cnt
+        dt = time.perf_counter() - t0
+        out["aggregate"] = {"windows_per_s": len(ws) / dt, "bases_per_s": float((we - ws).sum()) / dt,
+                            "sample": "20000 windows of 1..40 bases over 200000 float32 scores; the script's per-base Python loop without "
+                                      "mask, reading a plain numpy array -- a LOWER bound of the reference's cost (its loop goes "
+                                      "through BinnedArray.__getitem__ twice per base; that pure-Python class does not travel to "
+                                      "the GPU box)"}
+        return out
+    except Exception as e:                             # noqa: BLE001 -- reported, never fatal for the bench line
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def bench_bitset(args, peak, peak_src):
