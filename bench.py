@@ -517,6 +517,9 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         cpu = cpu_baseline(db, qq)
         extra["cpu_reference"] = cpu_reference_extras()
+        if "bitset_and" in roofline and "bitset_and" in extra["cpu_reference"]:      # the metric's "vs Cython CPU" for this half
+            roofline["bitset_and"]["cpu_reference_gbs"] = extra["cpu_reference"]["bitset_and"]["gbs"]
+            roofline["bitset_and"]["cpu_reference_cores"] = 1
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
