@@ -205,7 +205,8 @@ int bxg_itree_neighbors(bxg_itree_t *t, const int32_t *qtree, const int32_t *pos
 /* Overlap join (lib/bx/intervals/operations/join.py:14-75 over operations/quicksect.py:11-125): for every left
  * interval q the items of the index with start < item.end && end > item.start (quicksect.py:115-121) whose `overlap`
  * by the case analysis of join.py:35-50 is >= mincols.  istart/iend are the index's items in INSERTION order (the ids
- * `find` returns index them).  Results stay on the device until bxg_itree_join_fetch: CSR pair_offsets[nq+1] /
+ * `find` returns index them).  Results stay on the device, in ONE library-wide buffer, until bxg_itree_join_fetch (fetch
+ * before the next join; like every entry point this is not thread-safe): CSR pair_offsets[nq+1] /
  * pair_items[total] (item ids, index order within a left interval -- the reference's own order is a random treap
  * walk) and visited[n] = 1 for every item kept at least once (join.py:54, drives the left-fill pass :62-75). */
 int bxg_itree_join(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
