@@ -209,6 +209,11 @@ def run_reference(args):
     if not orc.ref_available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
         return
+    # load the reference's extension module in THIS process too (the workers are forked from it), so the driver's record
+    # of loaded native libraries shows which implementation this arm ran
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import bx.intervals.intersection as _ref_ix
+    log(f"reference module: {_ref_ix.__file__}")
     db, qq, _ = make_workload(max(1, args.gpus), args.n_db, args.nq)
     cores = usable_cores()
     # measured on the GPU box (cgroup quota 16 CPUs of a 2 x 32-core Xeon 8562Y+): 8 procs 3.8e6, 24 procs 6.5e6,
@@ -435,16 +440,47 @@ def run_ours(args):
         off_bytes = 4
     del serial_hits
 
+    # ---- count-only e2e: len(find()) per line is all scripts/bed_count_overlapping.py:27-33 needs -- 16 bytes per query
+    #      cross PCIe (12 up, 4 down) instead of ~42 ---------------------------------------------------------------------
+    h_cnt = _lib.PinnedArray(nq, np.int32)
+
+    def step_host_count():
+        check(L.bxg_itree_count(forest.handle, ptr(h_qt.array), ptr(h_qs.array), ptr(h_qe.array), nq, _lib.HOST,
+                                ptr(h_cnt.array), C.byref(total)))
+    e2e_count = q_all * e2e_steps / time_host(step_host_count, e2e_steps)
+    assert np.array_equal(h_cnt.array, cnt.astype(np.int32)) and total.value == hits_total, "count-only host path differs"
+
+    # ---- what the box can copy when every rank copies at once (the ceiling of e2e) ---------------------------------------
+    probe = copy_probe(comm)
+    e2e_bytes = 12 * nq + off_bytes * (nq + 1) + 4 * hits_total
+    e2e_gbs_rank = e2e_bytes / (nq / (e2e_value / world)) / 1e9            # bytes this rank moves / its step time
+
+    # ---- strong scaling: the N=1 workload (10 M queries in total) split over the ranks -------------------------------------
+    strong = None
+    if world > 1:
+        nq_s = max(1, nq // world)
+        tot_s = C.c_int64()
+
+        def step_dev_strong():
+            check(L.bxg_itree_find(forest.handle, d_qt.ptr, d_qs.ptr, d_qe.ptr, nq_s, _lib.DEVICE, C.byref(tot_s)))
+
+        def step_host_strong():
+            check(L.bxg_itree_find_host32(forest.handle, ptr(h_qt.array), ptr(h_qs.array), ptr(h_qe.array), nq_s,
+                                          C.byref(p_off), C.byref(p_hits), C.byref(tot_s)))
+        q_s_all = int(comm.allreduce_sum_i64(np.array([nq_s]))[0])
+        ms_s = DevTimer(comm)(step_dev_strong, args.steps, warm=3)
+        strong = {"queries_total": q_s_all, "value": q_s_all / (ms_s * 1e-3), "ms_per_step": ms_s,
+                  "e2e": q_s_all * e2e_steps / time_host(step_host_strong, e2e_steps)}
+        step_dev()
+
     extra = {"build_ms": min(build_ms), "hits_per_step": hits_all, "hits_per_query": hits_all / q_all,
              "per_chrom_hits_checksum": int((per_chrom * np.arange(1, 25)).sum()), "parity_spot_check": parity,
-             "e2e_serial_copies": e2e_serial, "e2e_int64_offsets": e2e_i64, "single_pass_kernel_ms_per_step": single_pass_ms,
-             "sorted_queries_ms_per_step": sorted_ms}
+             "e2e_serial_copies": e2e_serial, "e2e_int64_offsets": e2e_i64, "e2e_count_only": e2e_count,
+             "single_pass_kernel_ms_per_step": single_pass_ms, "sorted_queries_ms_per_step": sorted_ms,
+             "copy_probe": probe, "strong_scaling": strong}
+    del h_off, h_hits, h_cnt, h_qt, h_qs, h_qe, d_qt, d_qs, d_qe
+    forest = None                                          # free the index before the bitmap / score legs
 
-    if rank != 0:
-        comm.close()
-        return
-
-    # ---- roofline of the dominant kernel -------------------------------------------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -452,6 +488,23 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+    # ---- configs[2..4]: every rank takes part (chromosomes sharded, counters all-reduced inside the timed step) ----------
+    legs = {}
+    if not args.no_bitset:
+        for name, fn in (("bitset", leg_bitset), ("bed_intersect", leg_bed_intersect), ("aggregate", leg_aggregate)):
+            t_leg = time.perf_counter()
+            legs[name] = fn(comm, peak, args)
+            if rank == 0:
+                legs[name]["wall_s_incl_setup_and_checks"] = round(time.perf_counter() - t_leg, 1)
+                log(f"{name}: {legs[name].get('ms_per_step', legs[name].get('and_genome', {}).get('ms_per_pass'))} ms, "
+                    f"parity_ok={legs[name]['parity_ok']} ({legs[name]['wall_s_incl_setup_and_checks']} s wall)")
+
+    if rank != 0:
+        comm.close()
+        return
+
+    # ---- roofline of the dominant find kernel ------------------------------------------------------------------------------
     n_items = len(s)
     alg = {
         # per launch, bytes that must move (DESIGN.md "algorithmic bytes"):
@@ -473,43 +526,26 @@ def run_ours(args):
     dom = max((k for k in kern if k in alg), key=lambda k: kern[k]["avg_ms"] * kern[k]["launches"])
     dom_ms = kern[dom]["avg_ms"]
     achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    tj = {}
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(dom, tj.get(dom.replace("PROBE", os.environ.get("BXB200_FIND_PROBE", "2"))))
     except (OSError, ValueError):
         pass
+    traffic = tj.get(dom, tj.get(dom.replace("PROBE", os.environ.get("BXB200_FIND_PROBE", "2"))))
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dom_ms,
-                "note": "find is not HBM-bound (SURVEY 8d): every query is a dependent chain of ~5 random 32-byte sector reads "
-                        "(8-ary sampled levels, probe, E halves) over an 85 MB index; the count kernel is latency-bound with the "
-                        "L1 wavefront pipe ~60 % busy (ncu, profiles/) -- frac is reported, not targeted"}
+                "note": "find is not HBM-bound (SURVEY 8d): every query is a dependent chain of random 32-byte sector reads over "
+                        "an ~85 MB index; frac is reported, not targeted.  The HBM-bound half of the metric is bitset_and_* below; "
+                        "c4_* / c5_* are BASELINE configs[3] / [4] (all ranks, NCCL reduce inside the timed step)"}
     step_ms = sum(v["avg_ms"] * v["launches"] for v in kern.values()) / args.steps
     extra["kernels"] = {k: {"avg_ms": round(v["avg_ms"], 4), "per_step": v["launches"] / args.steps,
                             "share": round(v["avg_ms"] * v["launches"] / args.steps / step_ms, 4)} for k, v in kern.items()}
 
-    # ---- bitset AND (configs[2]) -----------------------------------------------------------------------------------------
     extra["pcie"] = bench_pcie()
     extra["scalar_api"] = bench_scalar_api(db)
     if not args.no_bitset:
-        extra["bitset"] = bench_bitset(args, peak, peak_src)
-        # BASELINE.json's metric has two halves (queries/s and bitset-AND GB/s against the HBM roof): surface the second one
-        # next to the find kernel's entry -- the genome-wide AND launch (configs[2]), kernel-only, CUDA events per launch
-        bk = extra["bitset"].get("kernels", {}).get("k_binop_batch<OP_AND, false>")
-        if bk:
-            tj = {}
-            try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            except (OSError, ValueError):
-                pass
-            roofline["bitset_and"] = {
-                "kernel": "k_binop_batch<OP_AND, false>", "bound": "hbm", "achieved": bk["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": bk["frac"], "traffic": tj.get("k_binop_batch<0, 0>"),
-                "algorithmic_bytes_per_launch": extra["bitset"]["algorithmic_bytes_per_pass"], "avg_launch_ms": bk["avg_ms"],
-                "workload": "a &= b over 24 hg38-length bitmap pairs (3.09 Gbit per operand set), one launch"}
-        extra["bed_intersect"] = bench_bed_intersect(peak)
-        extra["aggregate"] = bench_aggregate(peak)
+        extra.update(legs)
         extra["score_sources"] = bench_score_sources(peak)
 
     # ---- CPU baseline (bounded sample, single thread = the reference's only native mode) -----------------------------------
@@ -517,22 +553,79 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         cpu = cpu_baseline(db, qq)
         extra["cpu_reference"] = cpu_reference_extras()
-        if "bitset_and" in roofline and "bitset_and" in extra["cpu_reference"]:      # the metric's "vs Cython CPU" for this half
-            roofline["bitset_and"]["cpu_reference_gbs"] = extra["cpu_reference"]["bitset_and"]["gbs"]
-            roofline["bitset_and"]["cpu_reference_cores"] = 1
 
+    # ---- BASELINE.json's metric has two halves (queries/s and bitset-AND GB/s against the HBM roof) and two more configs
+    #      on N GPUs: flat scalar keys next to the find kernel's entry, at every N (all ranks took part) ---------------------
+    if legs:
+        bs, c4, c5 = legs["bitset"], legs["bed_intersect"], legs["aggregate"]
+        roofline.update({
+            "bitset_and_gbs": bs["and_genome"]["gbs"], "bitset_and_frac": bs["and_genome"]["frac"],
+            "bitset_and_ms": bs["and_genome"]["ms_per_pass"], "bitset_and_peak_gbs": peak * world,
+            "bitset_and_bytes": bs["algorithmic_bytes_per_pass"], "bitset_and_traffic": tj.get("k_binop_batch<0, 0>"),
+            "bitset_and_count_gbs": bs["and_count_genome"]["gbs"], "bitset_and_count_frac": bs["and_count_genome"]["frac"],
+            "bitset_and_per_pair_gbs": bs["and_per_pair"]["gbs"], "bitset_and_per_pair_frac": bs["and_per_pair"]["frac"],
+            "bitset_and_parity_ok": bs["parity_ok"],
+            "bitset_and_workload": "a &= b over 24 BinnedBitSet(250000000) pairs, all ranks, one launch per rank",
+            "c4_ms": c4["ms_per_step"], "c4_intervals_per_s": c4["intervals_per_s"], "c4_gbs": c4["gbs"], "c4_frac": c4["frac"],
+            "c4_parity_ok": c4["parity_ok"], "c4_workload": c4["workload"],
+            "c5_ms": c5["ms_per_step"], "c5_windows_per_s": c5["windows_per_s"], "c5_gbs": c5["gbs"], "c5_frac": c5["frac"],
+            "c5_parity_ok": c5["parity_ok"], "c5_workload": c5["workload"],
+        })
+        cr = (extra.get("cpu_reference") or {})
+        if "bitset_and" in cr:                               # the metric's "vs Cython CPU" for this half (one thread)
+            roofline["bitset_and_cpu_gbs"] = cr["bitset_and"]["gbs"]
+            roofline["bitset_and_cpu_cores"] = 1
+        for k_cpu, k_out in (("bed_intersect_intervals_per_s", "c4_cpu_intervals_per_s"),
+                             ("aggregate_windows_per_s", "c5_cpu_windows_per_s")):
+            if k_cpu in cr:
+                roofline[k_out] = cr[k_cpu]
+
+    e2e = {"value": e2e_value, "unit": UNIT,
+           "h2d_bytes_per_step": int(12 * nq), "d2h_bytes_per_step": int(off_bytes * (nq + 1) + 4 * hits_total),
+           "steps": e2e_steps,
+           "timing": "host wall clock around bxg_itree_find_host32 (pinned host arrays in, pinned host CSR out with int32 offsets; "
+                     "copies overlapped with kernels), max over ranks; extra.e2e_int64_offsets is the int64-offset call",
+           # what the box sustains when all ranks copy at once, and how much of it the e2e call uses (per rank)
+           "copy_ceiling_gbs_per_rank": probe["bidir_gbs_min"], "copy_ceiling_gbs_aggregate": probe["bidir_gbs_sum"],
+           "copy_gbs_achieved_per_rank": e2e_gbs_rank,
+           "frac_of_copy_ceiling": e2e_gbs_rank / probe["bidir_gbs_min"] if probe["bidir_gbs_min"] else None,
+           "count_only_value": e2e_count, "count_only_h2d_bytes_per_step": int(12 * nq),
+           "count_only_d2h_bytes_per_step": int(4 * nq)}
+    if strong:
+        e2e["strong_scaling_value"] = strong["value"]
+        e2e["strong_scaling_e2e"] = strong["e2e"]
+        e2e["strong_scaling_queries_total"] = strong["queries_total"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clock_summary, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": int(12 * nq), "d2h_bytes_per_step": int(off_bytes * (nq + 1) + 4 * hits_total),
-                "steps": e2e_steps, "timing": "host wall clock around bxg_itree_find_host32 (pinned host arrays in, pinned host CSR out with int32 offsets; copies overlapped with kernels), max over ranks; extra.e2e_int64_offsets is the int64-offset call"},
-        "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+        "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
     print(json.dumps(line))
     comm.close()
+
+
+def copy_probe(comm):
+    """Every rank copies 256 MB blocks through pinned memory at the same time: H2D alone, D2H alone, both at once."""
+    import ctypes as C
+
+    from bx_python_b200 import _lib
+    L = _lib.lib()
+    h2d, d2h, bi = C.c_double(), C.c_double(), C.c_double()
+    _lib.sync()
+    comm.barrier()
+    _lib.check(L.bxg_copy_probe(256 << 20, 6, C.byref(h2d), C.byref(d2h), C.byref(bi)))
+    vals = np.array([h2d.value, d2h.value, bi.value])
+    mx = comm.allreduce_max_f64(vals.copy())
+    mn = -comm.allreduce_max_f64(-vals.copy())
+    # sums through the int64 reduction (MB/s resolution is plenty)
+    sm = comm.allreduce_sum_i64((vals * 1000).astype(np.int64)) / 1000.0
+    return {"h2d_gbs_min": float(mn[0]), "h2d_gbs_max": float(mx[0]), "h2d_gbs_sum": float(sm[0]),
+            "d2h_gbs_min": float(mn[1]), "d2h_gbs_max": float(mx[1]), "d2h_gbs_sum": float(sm[1]),
+            "bidir_gbs_min": float(mn[2]), "bidir_gbs_max": float(mx[2]), "bidir_gbs_sum": float(sm[2]),
+            "ranks": comm.world, "bytes_per_copy": 256 << 20,
+            "note": "all ranks probe simultaneously after a barrier; bidir = H2D + D2H bytes on two streams / the later finish"}
 
 
 def spot_check(forest, tid, s, e, qt, qs, qe, total):
@@ -587,9 +680,8 @@ def cpu_reference_extras():
         if not orc.ref_available():
             return {}
         bs, _ = orc.ref_modules()
-        size = int(synth.HG38_LENS[0])
-        nranges = int(400_000 * size / 250_000_000)
-        (sa, ca), (sb, cb), (ps, pc) = synth.c3_case(size, nranges, 3000, nq=20000)
+        size, nranges = C3_SIZE, C3_RANGES                                       # one pair of configs[2]
+        (sa, ca), (sb, cb), (ps, pc) = synth.c3_case(size, nranges, 0, nq=20000)
         a, b = bs.BinnedBitSet(size), bs.BinnedBitSet(size)
         t0 = time.perf_counter()
         for s_, c_ in zip(sa.tolist(), ca.tolist()):
@@ -609,10 +701,12 @@ def cpu_reference_extras():
         t_q = time.perf_counter() - t0
         nbytes = 3 * ((size + 63) // 64) * 8
         out = {"kind": "reference", "cores": 1,
-               "sample": f"one chr1-length BinnedBitSet pair ({size} bits, {nranges} set_range calls each), unmodified bx.bitset",
+               "sample": f"one BinnedBitSet({size}) pair of configs[2] ({nranges} set_range calls each), unmodified bx.bitset",
                "bitset_and": {"ms": t_and * 1e3, "gbs": nbytes / t_and / 1e9, "algorithmic_bytes": nbytes},
                "count_all": {"ms": t_cnt * 1e3, "gbs": nbytes / 3 / t_cnt / 1e9, "bits_set": int(total)},
-               "set_range": {"calls_per_s": len(sa) / t_set}, "count_range": {"calls_per_s": len(ps) / t_q}}
+               "set_range": {"calls_per_s": len(sa) / t_set}, "count_range": {"calls_per_s": len(ps) / t_q},
+               # configs[3] is one set_range per file-2 line plus one count_range per file-1 line
+               "bed_intersect_intervals_per_s": 2.0 / (t_set / len(sa) + t_q / len(ps))}
         # aggregate: the script's per-base loop (scripts/aggregate_scores_in_intervals.py:107-124) over a dense float32 list
         rng = np.random.default_rng(5003)
         v = synth.aggregate_scores(rng, 200_000)
@@ -629,6 +723,7 @@ def cpu_reference_extras():
                     cnt += 1
             acc += cnt
         dt = time.perf_counter() - t0
+        out["aggregate_windows_per_s"] = len(ws) / dt
         out["aggregate"] = {"windows_per_s": len(ws) / dt, "bases_per_s": float((we - ws).sum()) / dt,
                             "sample": "20000 windows of 1..40 bases over 200000 float32 scores; the script's per-base Python loop without "
                                       "mask, reading a plain numpy array -- a LOWER bound of the reference's cost (its loop goes "
@@ -639,101 +734,366 @@ def cpu_reference_extras():
         return {"error": f"{type(e).__name__}: {e}"}
 
 
-def bench_bitset(args, peak, peak_src):
-    """configs[2]: AND + count over 24 chromosome-length bitmaps (hg38 lengths), 400k ranges per operand."""
+# ---------------------------------------------------------------------------------------------------------------------
+# configs[2..4] on every rank: chromosomes sharded over the ranks, per-chromosome counters reduced with NCCL inside the
+# device-timed step.  Every leg is called by ALL ranks and returns its report on rank 0.
+# ---------------------------------------------------------------------------------------------------------------------
+C3_SIZE = 250_000_000              # configs[2]: 24 x BinnedBitSet(250 Mbp)
+C3_RANGES = 400_000
+N_CHROM = 24
+
+
+def load_full_golden():
+    """tests/golden/full_size.json: digests of the compiled reference's answers at full size (make_golden_full.py)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "full_size.json")))
+    except (OSError, ValueError):
+        return {}
+
+
+def sha_arrays(*arrays):
+    import hashlib
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+class DevTimer:
+    """barrier -> CUDA events on the library stream around `reps` calls -> max over ranks, in ms per call."""
+
+    def __init__(self, comm):
+        from bx_python_b200 import _lib
+        self.comm, self.t, self._lib = comm, _lib.Timer(), _lib
+
+    def __call__(self, fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
+        self._lib.sync()
+        self.comm.barrier()
+        self.t.start()
+        for _ in range(reps):
+            fn()
+        self.t.stop()
+        ms = self.t.elapsed_ms() / reps
+        return float(self.comm.allreduce_max_f64(np.array([ms]))[0])
+
+
+def all_ok(comm, ok):
+    """True when every rank's check passed."""
+    return int(comm.allreduce_sum_i64(np.array([0 if ok else 1]))[0]) == 0
+
+
+def leg_bitset(comm, peak, args):
+    """configs[2]: a &= b (and the fused a &= b; count) over 24 BinnedBitSet(250 000 000) pairs, 400 k set_range calls per
+    operand; the pairs are dealt round-robin to the ranks.  GB/s = 3 x 8 bytes per word of every pair on every
+    rank / the slowest rank's device time."""
     import ctypes as C
 
     from bx_python_b200 import _lib
-    from bx_python_b200._lib import check
+    from bx_python_b200._lib import check, ptr
     from bx_python_b200.bitset import BinnedBitSet
     L = _lib.lib()
+    rank, world = comm.rank, comm.world
+    mine = lpt_assign([1.0] * N_CHROM, world)[rank]
     A, B = [], []
-    words = 0
-    for c, size in enumerate(synth.HG38_LENS.tolist()):
-        (sa, ca), (sb, cb), _ = synth.c3_case(size, 400_000, c, nq=1)
-        a, b = BinnedBitSet(size), BinnedBitSet(size)
+    for c in mine:
+        (sa, ca), (sb, cb), _ = synth.c3_case(C3_SIZE, C3_RANGES, c, nq=1)
+        a, b = BinnedBitSet(C3_SIZE), BinnedBitSet(C3_SIZE)
         a.set_ranges(sa, ca)
         b.set_ranges(sb, cb)
         A.append(a)
         B.append(b)
-        words += (size + 63) // 64
-    timer = _lib.Timer()
-    n = C.c_int64()
+    words = (C3_SIZE + 63) // 64
+    n = len(mine)
+    ha = (C.c_void_p * max(n, 1))(*[a._h for a in A])
+    hb = (C.c_void_p * max(n, 1))(*[b._h for b in B])
+    counts = np.zeros(max(n, 1), np.int64)
+    timed = DevTimer(comm)
 
-    def one_pass(count):
+    def batch(count):
+        if n:
+            check(L.bxg_bits_binop_batch(0, ha, hb, n, ptr(counts) if count else None))
+
+    def per_pair(count):
         for a, b in zip(A, B):
-            if count:
-                check(L.bxg_bits_and_count(a._h, b._h, None))
-            else:
-                check(L.bxg_bits_and(a._h, b._h))
-    ha = (C.c_void_p * 24)(*[a._h for a in A])
-    hb = (C.c_void_p * 24)(*[b._h for b in B])
-    counts = np.empty(24, np.int64)
+            check(L.bxg_bits_and_count(a._h, b._h, None) if count else L.bxg_bits_and(a._h, b._h))
+    total_bytes = 3 * words * 8 * N_CHROM
+    res = {"workload": f"{N_CHROM} x BinnedBitSet({C3_SIZE}) pairs, {C3_RANGES} set_range calls per operand, "
+                       f"{N_CHROM // world if N_CHROM % world == 0 else f'{N_CHROM}/{world}'} pairs per rank",
+           "algorithmic_bytes_per_pass": total_bytes, "unit": "GB/s", "bound": "hbm",
+           "l2_policy": f"each rank streams {3 * words * 8 * max(1, N_CHROM // world) / 1e6:.0f} MB per pass (> 126 MB L2)"}
+    for name, fn, count, reps in (("and_genome", batch, False, 10), ("and_count_genome", batch, True, 10),
+                                  ("and_per_pair", per_pair, False, 5), ("and_count_per_pair", per_pair, True, 5)):
+        ms = timed(lambda: fn(count), reps, warm=2)
+        gbs = total_bytes / (ms * 1e-3) / 1e9
+        res[name] = {"ms_per_pass": ms, "gbs": gbs, "frac": gbs / (peak * world),
+                     "launches_per_pass_per_rank": 1 if fn is batch else n}
+    # parity: the fused popcounts of the AND against the compiled reference's answer at full size (golden), all ranks
+    gold = load_full_golden().get("c3")
+    batch(True)
+    ok, how = True, "no golden file: unchecked"
+    if gold:
+        ok = all(int(counts[k]) == gold[c]["dense"]["count_and"] for k, c in enumerate(mine))
+        how = "popcount(a & b) of every pair == compiled reference (tests/golden/full_size.json c3.dense.count_and)"
+    res["parity_ok"] = all_ok(comm, ok)
+    res["parity"] = how
+    if rank != 0:
+        return None
+    # kernel-only launch durations (CUDA events around each launch) on rank 0
+    _lib.profile_enable(True)
+    for _ in range(5):
+        batch(False)
+        batch(True)
+        per_pair(False)
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    for kname, (nl, tot) in prof.items():
+        per_launch = 3 * words * 8 * (n if "batch" in kname else 1)
+        avg_ms = tot / nl
+        res.setdefault("kernels_rank0", {})[kname.strip("()")] = {
+            "launches": nl, "avg_ms": avg_ms, "gbs": per_launch / (avg_ms * 1e-3) / 1e9,
+            "frac": per_launch / (avg_ms * 1e-3) / 1e9 / peak}
+    # single-bitmap operations on one 250 Mbp pair (31 MB per bitmap: these FIT the 126 MB L2, so they are L2 figures)
+    t = _lib.Timer()
 
-    def batch_pass(count):
-        check(L.bxg_bits_binop_batch(0, ha, hb, 24, ptr(counts) if count else None))
-
-    from bx_python_b200._lib import ptr
-    res = {}
-    for name, fn, count in (("and", one_pass, False), ("and_count", one_pass, True),
-                            ("and_genome", batch_pass, False), ("and_count_genome", batch_pass, True)):
-        for _ in range(3):
-            fn(count)
-        _lib.sync()
-        reps = 10
-        timer.start()
-        for _ in range(reps):
-            fn(count)
-        timer.stop()
-        ms = timer.elapsed_ms() / reps
-        gbs = 3 * words * 8 / (ms * 1e-3) / 1e9
-        res[name] = {"ms_per_pass": ms, "gbs": gbs, "frac": gbs / peak,
-                     "launches_per_pass": 24 if fn is one_pass else 1}
-    assert int(counts.sum()) == sum(a.count_all() for a in A), "fused genome-wide popcount differs from count_all"
-    # invert (2 W 8 bytes), count_all (W 8 bytes) and run extraction (2 passes over W 8 bytes + 8 bytes per run), chr1 pair
-    w1 = (int(synth.HG38_LENS[0]) + 63) // 64
-
-    def timed(fn, reps=10):
+    def timed1(fn, reps=10):
         fn()
         _lib.sync()
-        timer.start()
+        t.start()
         for _ in range(reps):
             fn()
-        timer.stop()
-        return timer.elapsed_ms() / reps
-    ms = timed(lambda: check(L.bxg_bits_not(A[0]._h)))
-    res["invert_chr1"] = {"ms": ms, "gbs": 2 * w1 * 8 / (ms * 1e-3) / 1e9, "frac": 2 * w1 * 8 / (ms * 1e-3) / 1e9 / peak}
-    ms = timed(lambda: check(L.bxg_bits_count_all(A[0]._h, C.byref(n))))
-    res["count_all_chr1"] = {"ms": ms, "gbs": w1 * 8 / (ms * 1e-3) / 1e9, "frac": w1 * 8 / (ms * 1e-3) / 1e9 / peak,
-                             "note": "includes the 8-byte D2H + stream sync of the scalar result"}
-    nr = C.c_int64()
+        t.stop()
+        return t.elapsed_ms() / reps
+    n64, nr = C.c_int64(), C.c_int64()
+    ms = timed1(lambda: check(L.bxg_bits_not(A[0]._h)))
+    res["invert_one"] = {"ms": ms, "gbs": 2 * words * 8 / (ms * 1e-3) / 1e9, "resident": "L2 (31 MB bitmap)"}
+    ms = timed1(lambda: check(L.bxg_bits_count_all(A[0]._h, C.byref(n64))))
+    res["count_all_one"] = {"ms": ms, "gbs": words * 8 / (ms * 1e-3) / 1e9, "resident": "L2 (31 MB bitmap)",
+                            "note": "includes the 8-byte D2H + stream sync of the scalar result"}
 
     def runs_pass():
         check(L.bxg_bits_not(B[0]._h))              # invalidates the cached runs so each repetition extracts again
         check(L.bxg_bits_runs_count(B[0]._h, C.byref(nr)))
-    ms_pair = timed(runs_pass, reps=6)
-    ms_not = timed(lambda: check(L.bxg_bits_not(B[0]._h)), reps=6)
-    res["runs_chr1"] = {"ms": ms_pair - ms_not, "runs": nr.value,
-                        "gbs": (2 * w1 * 8 + 8 * nr.value) / ((ms_pair - ms_not) * 1e-3) / 1e9}
-    # kernel-only durations (CUDA events around each launch) -> the per-launch roofline of the bitset kernels
-    _lib.profile_enable(True)
-    for _ in range(5):
-        batch_pass(False)
-        batch_pass(True)
-        one_pass(False)
-    prof = _lib.profile_report()
-    _lib.profile_enable(False)
-    for kname, (nl, tot) in prof.items():
-        per_launch_bytes = 3 * words * 8 if "batch" in kname else 3 * words * 8 / 24
-        avg_ms = tot / nl
-        res.setdefault("kernels", {})[kname.strip("()")] = {
-            "launches": nl, "avg_ms": avg_ms, "gbs": per_launch_bytes / (avg_ms * 1e-3) / 1e9,
-            "frac": per_launch_bytes / (avg_ms * 1e-3) / 1e9 / peak}
-    check(L.bxg_bits_count_all(A[0]._h, C.byref(n)))
-    res.update({"bitmaps": 48, "total_bits": int(synth.HG38_LENS.sum()), "algorithmic_bytes_per_pass": 3 * words * 8,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "bound": "hbm",
-                "l2_policy": "one pass streams 1.16 GB through 24 operand pairs (> 126 MB L2)"})
+    ms_pair = timed1(runs_pass, reps=6)
+    ms_not = timed1(lambda: check(L.bxg_bits_not(B[0]._h)), reps=6)
+    res["runs_one"] = {"ms": ms_pair - ms_not, "runs": nr.value, "resident": "L2 (31 MB bitmap)",
+                       "gbs": (2 * words * 8 + 8 * nr.value) / max(1e-6, (ms_pair - ms_not) * 1e-3) / 1e9}
     return res
+
+
+def c4_shards(f1, f2, world):
+    """bed_intersect shards: chromosome weight = bitmap words + intervals of both files (LPT)."""
+    w = [float((int(L) + 63) // 64) / 8 + len(f1[c][0]) + len(f2[c][0]) for c, L in enumerate(synth.HG38_LENS)]
+    return lpt_assign(w, world)
+
+
+def flat_file(per_chrom, chroms, seed):
+    """(chrom id, start, count) of the selected chromosomes in shuffled (file) order, chromosome ids GLOBAL."""
+    which = np.concatenate([np.full(len(per_chrom[c][0]), c, np.int32) for c in chroms] or [np.zeros(0, np.int32)])
+    s = np.concatenate([per_chrom[c][0] for c in chroms] or [np.zeros(0, np.int32)])
+    cnt = np.concatenate([(per_chrom[c][1] - per_chrom[c][0]).astype(np.int32) for c in chroms] or [np.zeros(0, np.int32)])
+    perm = np.random.default_rng(seed).permutation(len(which))
+    return which[perm], s[perm], cnt[perm], perm
+
+
+def leg_bed_intersect(comm, peak, args):
+    """configs[3] (scripts/bed_intersect.py:42-53 over lib/bx/bitset_builders.py:17-54): file 2 (50 M intervals) -> one
+    BinnedBitSet per chromosome (set_range per line); file 1 (50 M intervals) -> count_range(start, end - start) >= 1 per
+    line.  Chromosomes are sharded over the ranks (no exchange); the step ends with ONE NCCL all-reduce of the
+    per-chromosome counters [overlapping lines, overlapping bases summed over lines, covered bases] and their D2H copy.
+    A step = clear bitmaps, set ranges, build rank tables, count, reduce -- everything on the library stream."""
+    import ctypes as C
+
+    from bx_python_b200 import _lib
+    from bx_python_b200._lib import check, ptr
+    from bx_python_b200.bitset import BinnedBitSet
+    from oracle import oracle as orc
+    L = _lib.lib()
+    rank, world = comm.rank, comm.world
+    n = args.c4_n
+    f2 = synth.genome_intervals(n, 4002)
+    f1 = synth.genome_intervals(n, 4001)
+    mine = c4_shards(f1, f2, world)[rank]
+    bits = {c: BinnedBitSet(int(synth.HG38_LENS[c])) for c in mine}
+    sets = (C.c_void_p * N_CHROM)(*[(bits[c]._h if c in bits else None) for c in range(N_CHROM)])
+    w2, s2, c2, _ = flat_file(f2, mine, 40 + rank)
+    w1, s1, c1, perm1 = flat_file(f1, mine, 41 + rank)
+    n2, n1 = len(w2), len(w1)
+    d2 = [_lib.DeviceBuffer(a) for a in (w2, s2, c2)]
+    d1 = [_lib.DeviceBuffer(a) for a in (w1, s1, c1)]
+    d_out = _lib.DeviceBuffer(np.zeros(max(n1, 1), np.int32))
+    d_stats = _lib.DeviceBuffer(np.zeros(3 * N_CHROM, np.int64))
+    h_stats = _lib.PinnedArray(3 * N_CHROM, np.int64)
+    p_stats = d_stats.ptr.value
+
+    def step():
+        check(L.bxg_dev_memset(d_stats.ptr, 0, 8 * 3 * N_CHROM))
+        for b in bits.values():
+            check(L.bxg_bits_clear(b._h))
+        check(L.bxg_bits_set_ranges_multi(sets, N_CHROM, d2[0].ptr, d2[1].ptr, d2[2].ptr, n2, _lib.DEVICE))
+        check(L.bxg_bits_count_ranges_multi(sets, N_CHROM, d1[0].ptr, d1[1].ptr, d1[2].ptr, n1, d_out.ptr, 1, _lib.DEVICE))
+        check(L.bxg_group_stats_i32(d1[0].ptr, d_out.ptr, n1, N_CHROM, 1, d_stats.ptr, _lib.DEVICE))
+        check(L.bxg_bits_count_all_multi(sets, N_CHROM, C.c_void_p(p_stats + 16 * N_CHROM), 1, _lib.DEVICE))
+        check(L.bxg_comm_allreduce_i64_dev(d_stats.ptr, 3 * N_CHROM))
+        check(L.bxg_memcpy_d2h(ptr(h_stats.array), d_stats.ptr, 8 * 3 * N_CHROM))
+        _lib.sync()
+    timed = DevTimer(comm)
+    check(L.bxg_launch_count_reset())
+    step()
+    launches = _lib.launch_count()
+    ms = timed(step, args.c4_steps, warm=1)
+    stats = h_stats.array.copy()
+    per = stats[:2 * N_CHROM].reshape(N_CHROM, 2)
+    covered = stats[2 * N_CHROM:]
+    # ---- parity: (i) this rank's chromosomes, every line's count vs the oracle restatement; (ii) digests + reduced
+    #      per-chromosome counters vs the compiled reference at full size (golden file)
+    got = np.empty(n1, np.int32)
+    if n1:
+        check(L.bxg_memcpy_d2h(ptr(got), d_out.ptr, got.nbytes))
+        _lib.sync()
+    file_order = np.empty(n1, np.int32)
+    file_order[perm1] = got                                # back to generated (per-chromosome) order
+    gold = load_full_golden().get("c4") if n == 50_000_000 else None
+    ok, pos, checked = True, 0, 0
+    for c in mine:
+        m = len(f1[c][0])
+        mine_counts = file_order[pos:pos + m]
+        pos += m
+        if gold:
+            ok &= sha_arrays(mine_counts) == gold[c]["sha256"]
+        if (not gold) or c == mine[-1]:                    # the oracle restatement on one chromosome (all, without goldens)
+            ob = orc.OracleBinnedBitSet(int(synth.HG38_LENS[c]))
+            ob.set_ranges(f2[c][0], f2[c][1] - f2[c][0])
+            ok &= bool(np.array_equal(mine_counts, ob.count_ranges(f1[c][0], f1[c][1] - f1[c][0])))
+        checked += m
+    if gold:                                               # the all-reduced counters, on every rank
+        ok &= all(int(per[c, 0]) == gold[c]["overlapping"] and int(per[c, 1]) == gold[c]["sum_counts"] and
+                  int(covered[c]) == gold[c]["covered"] for c in range(N_CHROM))
+    ok = all_ok(comm, ok)
+    # ---- per-kernel device times on rank 0 (separate pass)
+    prof = None
+    if rank == 0:
+        _lib.profile_enable(True)
+        step()
+        prof = _lib.profile_report()
+        _lib.profile_enable(False)
+    words_written = int(comm.allreduce_sum_i64(np.array(
+        [sum(int(np.sum((f2[c][1] - 1) // 64 - f2[c][0] // 64 + 1)) for c in mine)]))[0])
+    if rank != 0:
+        return None
+    W = int(sum((int(x) + 63) // 64 for x in synth.HG38_LENS))
+    # SURVEY 8d: clear W*8 + set (12 n2 in + 8 per word written) + rank build (W*8 read + W words/4 x 4 B table) +
+    # count (12 n1 in + 4 n1 out) + per-chromosome counters (8 n1)
+    alg = 8 * W + 12 * n + 8 * words_written + 8 * W + W + 16 * n + 8 * n
+    kern = {k.strip("()"): {"launches": v[0], "ms": round(v[1], 4)} for k, v in prof.items()}
+    return {"workload": f"bed_intersect {n} x {n} hg38-shaped BED intervals, {N_CHROM} chromosomes sharded over {world} rank(s)",
+            "ms_per_step": ms, "intervals_per_s": 2 * n / (ms * 1e-3), "lines_per_s": n / (ms * 1e-3),
+            "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / (peak * world),
+            "launches_per_step_rank0": launches, "steps": args.c4_steps,
+            "overlapping_lines": int(per[:, 0].sum()), "overlapping_bases": int(per[:, 1].sum()),
+            "covered_bases": int(covered.sum()), "kernels_rank0": kern, "parity_ok": ok,
+            "parity": (f"every line's count on every rank: SHA-256 per chromosome == compiled reference (full_size.json c4), "
+                       f"all-reduced [overlapping, sum, covered] x {N_CHROM} == reference, + oracle restatement on one chromosome per rank"
+                       if gold else "every line's count on every rank == oracle restatement (no full-size golden for this size)"),
+            "collective": "one ncclAllReduce(int64 x 72) inside the timed step"}
+
+
+def leg_aggregate(comm, peak, args):
+    """configs[4] (scripts/aggregate_scores_in_intervals.py:107-134): 100 M float32 scores as dense per-chromosome tracks,
+    5 M BED windows of 1..40 bases.  Chromosomes (tracks + their windows) are sharded over the ranks; a step = one
+    genome-wide aggregate launch over the rank's windows (BED order), the per-chromosome counters
+    [windows with a value, counted bases], ONE NCCL all-reduce of them and their D2H copy."""
+    import ctypes as C
+
+    from bx_python_b200 import _lib
+    from bx_python_b200._lib import check, ptr
+    from oracle import oracle as orc
+    L = _lib.lib()
+    rank, world = comm.rank, comm.world
+    tracks = synth.genome_scores(args.c5_scores, args.c5_windows, 5001)
+    mine = lpt_assign([len(t[1]) + 20.0 * len(t[2]) for t in tracks], world)[rank]
+    handles = {}
+    for c in mine:
+        origin, v, _, _ = tracks[c]
+        h = C.c_void_p()
+        check(L.bxg_scores_create(ptr(v), len(v), origin, _lib.HOST, C.byref(h)))
+        handles[c] = h
+    ht = (C.c_void_p * N_CHROM)(*[(handles[c] if c in handles else None) for c in range(N_CHROM)])
+    wt = np.concatenate([np.full(len(tracks[c][2]), c, np.int32) for c in mine] or [np.zeros(0, np.int32)])
+    ws = np.concatenate([tracks[c][2] for c in mine] or [np.zeros(0, np.int32)])
+    we = np.concatenate([tracks[c][3] for c in mine] or [np.zeros(0, np.int32)])
+    nw = len(wt)
+    perm = np.random.default_rng(50 + rank).permutation(nw)          # BED order, not grouped by chromosome
+    d_w = [_lib.DeviceBuffer(a[perm]) for a in (wt, ws, we)]
+    outs = [_lib.DeviceBuffer(np.zeros(max(nw, 1), dt)) for dt in (np.float32, np.float32, np.int32, np.float32, np.float32)]
+    d_stats = _lib.DeviceBuffer(np.zeros(2 * N_CHROM, np.int64))
+    h_stats = _lib.PinnedArray(2 * N_CHROM, np.int64)
+
+    def step():
+        check(L.bxg_dev_memset(d_stats.ptr, 0, 16 * N_CHROM))
+        check(L.bxg_aggregate_multi(ht, None, N_CHROM, d_w[0].ptr, d_w[1].ptr, d_w[2].ptr, nw, _lib.DEVICE,
+                                    outs[0].ptr, outs[1].ptr, outs[2].ptr, outs[3].ptr, outs[4].ptr))
+        check(L.bxg_group_stats_i32(d_w[0].ptr, outs[2].ptr, nw, N_CHROM, 1, d_stats.ptr, _lib.DEVICE))
+        check(L.bxg_comm_allreduce_i64_dev(d_stats.ptr, 2 * N_CHROM))
+        check(L.bxg_memcpy_d2h(ptr(h_stats.array), d_stats.ptr, 16 * N_CHROM))
+        _lib.sync()
+    timed = DevTimer(comm)
+    check(L.bxg_launch_count_reset())
+    step()
+    launches = _lib.launch_count()
+    ms = timed(step, args.c5_steps, warm=1)
+    stats = h_stats.array.copy().reshape(N_CHROM, 2)
+    # ---- parity: every window of this rank's chromosomes, bit for bit, vs the oracle restatement; SHA-256 of the
+    #      avg/min/max columns per chromosome vs what the reference script itself printed at full size (golden)
+    host = [np.empty(max(nw, 1), dt) for dt in (np.float32, np.float32, np.int32, np.float32, np.float32)]
+    for h, dbuf in zip(host, outs):
+        if nw:
+            check(L.bxg_memcpy_d2h(ptr(h), dbuf.ptr, h.nbytes))
+    _lib.sync()
+    inv = np.empty(nw, np.int64)
+    inv[perm] = np.arange(nw)
+    gold = load_full_golden().get("c5") if (args.c5_scores, args.c5_windows) == (100_000_000, 5_000_000) else None
+    ok, pos = True, 0
+    for c in mine:
+        origin, v, cws, cwe = tracks[c]
+        m = len(cws)
+        sel = inv[pos:pos + m]
+        pos += m
+        dense = np.full(origin + len(v), np.nan, np.float32)
+        dense[origin:] = v
+        ref = orc.aggregate(dense, cws, cwe)
+        for k, name in enumerate(("sum", "avg", "count", "min", "max")):
+            ok &= bool(np.array_equal(host[k][sel].view(np.uint32), ref[name].view(np.uint32)))
+        if gold:
+            ok &= sha_arrays(host[1][sel], host[3][sel], host[4][sel]) == gold[c]["sha256"]
+            ok &= int(m - stats[c, 0]) == gold[c]["nan_lines"]
+    ok = all_ok(comm, ok)
+    bases = int(comm.allreduce_sum_i64(np.array([int(np.sum(we.astype(np.int64) - ws))]))[0])
+    nw_all = int(comm.allreduce_sum_i64(np.array([nw]))[0])
+    prof = None
+    if rank == 0:
+        _lib.profile_enable(True)
+        step()
+        prof = _lib.profile_report()
+        _lib.profile_enable(False)
+    for h in handles.values():
+        L.bxg_scores_free(h)
+    if rank != 0:
+        return None
+    alg = 4 * bases + 12 * nw_all + 20 * nw_all + 8 * nw_all      # scores read, windows in, 5 columns out, counters pass
+    kern = {k.strip("()"): {"launches": v[0], "ms": round(v[1], 4)} for k, v in prof.items()}
+    return {"workload": f"aggregate_scores_in_intervals: {args.c5_scores} float32 scores, {nw_all} windows of 1..40 bases, "
+                        f"{N_CHROM} chromosomes sharded over {world} rank(s)",
+            "ms_per_step": ms, "windows_per_s": nw_all / (ms * 1e-3), "bases_per_s": bases / (ms * 1e-3),
+            "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / (peak * world),
+            "launches_per_step_rank0": launches, "steps": args.c5_steps,
+            "windows_with_value": int(stats[:, 0].sum()), "counted_bases": int(stats[:, 1].sum()),
+            "kernels_rank0": kern, "parity_ok": ok,
+            "parity": ("every window on every rank bit-identical to the oracle restatement (sum, avg, count, min, max)" +
+                       ("; SHA-256 of the avg/min/max columns per chromosome == the reference script's own output (full_size.json c5)"
+                        if gold else "")),
+            "collective": "one ncclAllReduce(int64 x 48) inside the timed step"}
 
 
 def bench_scalar_api(db):
@@ -783,193 +1143,6 @@ def bench_pcie():
         t.stop()
         out[name + "_gbs"] = 4 * n * 4 / (t.elapsed_ms() * 1e-3) / 1e9
     return out
-
-
-def bench_bed_intersect(peak):
-    """configs[3] per-GPU share (scripts/bed_intersect.py): file-2 intervals -> per-chromosome bitsets (set_range),
-    file-1 intervals -> count_range(start, end-start) >= 1 flags.  6.25 M + 6.25 M intervals (50 M / 8 GPUs)."""
-    import ctypes as C
-
-    from bx_python_b200 import _lib
-    from bx_python_b200._lib import check
-    from bx_python_b200.bitset import BinnedBitSet
-    from oracle import oracle as orc
-    L = _lib.lib()
-    n = 6_250_000
-    f2 = synth.genome_intervals(n, 4002)
-    f1 = synth.genome_intervals(n, 4001)
-    bits = [BinnedBitSet(int(sz)) for sz in synth.HG38_LENS]
-    dev = []
-    for c in range(24):
-        s2, e2 = f2[c]
-        s1, e1 = f1[c]
-        dev.append((_lib.DeviceBuffer(s2), _lib.DeviceBuffer((e2 - s2).astype(np.int32)), len(s2),
-                    _lib.DeviceBuffer(s1), _lib.DeviceBuffer((e1 - s1).astype(np.int32)), len(s1),
-                    _lib.DeviceBuffer(np.zeros(len(s1), np.int32))))
-    timer = _lib.Timer()
-
-    def set_pass():
-        for b, (ds, dc, m, *_r) in zip(bits, dev):
-            check(L.bxg_bits_set_ranges(b._h, ds.ptr, dc.ptr, m, _lib.DEVICE))
-
-    def count_pass():
-        for b, (_a, _b, _m, qs, qc, mq, out) in zip(bits, dev):
-            check(L.bxg_bits_count_ranges(b._h, qs.ptr, qc.ptr, mq, out.ptr, 1, _lib.DEVICE))
-    res = {}
-    set_pass()
-    _lib.sync()
-    timer.start()
-    set_pass()
-    timer.stop()
-    ms = timer.elapsed_ms()
-    words_written = sum(int(np.sum((e - 1) // 64 - s // 64 + 1)) for s, e in f2)
-    res["set_ranges"] = {"ms": ms, "ranges_per_s": n / (ms * 1e-3), "algorithmic_bytes": 8 * n + 8 * words_written,
-                         "gbs": (8 * n + 8 * words_written) / (ms * 1e-3) / 1e9}
-    # genome-wide form: the file's lines in shuffled (file) order with their chromosome id, one launch
-    w2 = np.concatenate([np.full(len(f2[c][0]), c, np.int32) for c in range(24)])
-    s2_all = np.concatenate([f2[c][0] for c in range(24)])
-    c2_all = np.concatenate([(f2[c][1] - f2[c][0]).astype(np.int32) for c in range(24)])
-    perm2 = np.random.default_rng(3).permutation(len(w2))
-    g_w, g_s, g_c = (_lib.DeviceBuffer(a[perm2]) for a in (w2, s2_all, c2_all))
-    hs2 = (C.c_void_p * 24)(*[b._h for b in bits])
-
-    def genome_set():
-        check(L.bxg_bits_set_ranges_multi(hs2, 24, g_w.ptr, g_s.ptr, g_c.ptr, len(w2), _lib.DEVICE))
-    genome_set()
-    timer.start()
-    for _ in range(3):
-        genome_set()
-    timer.stop()
-    gms = timer.elapsed_ms() / 3
-    res["set_ranges_genome"] = {"ms": gms, "ranges_per_s": n / (gms * 1e-3), "algorithmic_bytes": 12 * n + 8 * words_written,
-                                "gbs": (12 * n + 8 * words_written) / (gms * 1e-3) / 1e9, "launches_per_pass": 1,
-                                "note": "includes a stream synchronise per call (descriptor table is host-static)"}
-    count_pass()       # builds the rank tables
-    _lib.sync()
-    timer.start()
-    count_pass()
-    timer.stop()
-    ms = timer.elapsed_ms()
-    res["count_ranges"] = {"ms": ms, "queries_per_s": n / (ms * 1e-3), "algorithmic_bytes": 12 * n,
-                           "gbs": 12 * n / (ms * 1e-3) / 1e9,
-                           "note": "rank-table lookups (2 table words + 2 bitmap words per query): latency/L2-bound"}
-    # genome-wide form: every BED line carries its chromosome id; one launch
-    which = np.concatenate([np.full(len(f1[c][0]), c, np.int32) for c in range(24)])
-    qs_all = np.concatenate([f1[c][0] for c in range(24)])
-    qc_all = np.concatenate([(f1[c][1] - f1[c][0]).astype(np.int32) for c in range(24)])
-    perm = np.random.default_rng(2).permutation(len(which))
-    d_w, d_s, d_c = (_lib.DeviceBuffer(a[perm]) for a in (which, qs_all, qc_all))
-    d_out = _lib.DeviceBuffer(np.zeros(len(which), np.int32))
-    hs = (C.c_void_p * 24)(*[b._h for b in bits])
-
-    def genome_count():
-        check(L.bxg_bits_count_ranges_multi(hs, 24, d_w.ptr, d_s.ptr, d_c.ptr, len(which), d_out.ptr, 1, _lib.DEVICE))
-    genome_count()
-    _lib.sync()
-    timer.start()
-    for _ in range(5):
-        genome_count()
-    timer.stop()
-    ms = timer.elapsed_ms() / 5
-    res["count_ranges_genome"] = {"ms": ms, "queries_per_s": n / (ms * 1e-3), "algorithmic_bytes": 16 * n,
-                                  "gbs": 16 * n / (ms * 1e-3) / 1e9, "launches_per_pass": 1}
-    gout = np.empty(len(which), np.int32)
-    check(L.bxg_memcpy_d2h(gout.ctypes.data_as(C.c_void_p), d_out.ptr, gout.nbytes))
-    _lib.sync()
-    for r in res.values():
-        r["frac"] = r["gbs"] / peak
-    # parity of one chromosome against the oracle (strict count_range semantics)
-    c = 21
-    ob = orc.OracleBinnedBitSet(int(synth.HG38_LENS[c]))
-    ob.set_ranges(f2[c][0], f2[c][1] - f2[c][0])
-    got = np.empty(dev[c][5], np.int32)
-    check(L.bxg_memcpy_d2h(got.ctypes.data_as(C.c_void_p), dev[c][6].ptr, got.nbytes))
-    _lib.sync()
-    assert np.array_equal(got, ob.count_ranges(f1[c][0], f1[c][1] - f1[c][0])), "bed_intersect parity"
-    sel = which[perm] == c
-    inv = np.empty(len(perm), np.int64)
-    inv[perm] = np.arange(len(perm))
-    first = int(np.nonzero(which == c)[0][0])
-    assert np.array_equal(gout[inv[first:first + len(got)]], got) and int(sel.sum()) == len(got), "genome-wide count parity"
-    res["overlapping_chr22"] = int((got >= 1).sum())
-    res["parity"] = "chr22 counts bit-identical to oracle"
-    return res
-
-
-def bench_aggregate(peak):
-    """configs[4] per-GPU share (aggregate_scores_in_intervals): 12.5 M float32 positions, 625 k windows (1/8 of C5)."""
-    import ctypes as C
-
-    from bx_python_b200 import _lib
-    from bx_python_b200._lib import check
-    from oracle import oracle as orc
-    L = _lib.lib()
-    tracks = synth.genome_scores(12_500_000, 625_000, 5001)
-    handles = []
-    for origin, v, ws, we in tracks:
-        h = C.c_void_p()
-        check(L.bxg_scores_create(v.ctypes.data_as(C.c_void_p), len(v), origin, _lib.HOST, C.byref(h)))
-        nw = len(ws)
-        outs = [_lib.DeviceBuffer(np.zeros(nw, np.float32)) for _ in range(2)] + [_lib.DeviceBuffer(np.zeros(nw, np.int32))] + \
-               [_lib.DeviceBuffer(np.zeros(nw, np.float32)) for _ in range(2)]
-        handles.append((h, _lib.DeviceBuffer(ws), _lib.DeviceBuffer(we), nw, outs))
-    timer = _lib.Timer()
-
-    def one_pass():
-        for h, dws, dwe, nw, o in handles:
-            check(L.bxg_aggregate(h, None, dws.ptr, dwe.ptr, nw, _lib.DEVICE, o[0].ptr, o[1].ptr, o[2].ptr, o[3].ptr, o[4].ptr))
-    one_pass()
-    _lib.sync()
-    timer.start()
-    for _ in range(5):
-        one_pass()
-    timer.stop()
-    ms = timer.elapsed_ms() / 5
-    bases = sum(int(np.sum(we.astype(np.int64) - ws)) for _, _, ws, we in tracks)
-    nw_all = sum(len(t[2]) for t in tracks)
-    alg = 4 * bases + 28 * nw_all
-    origin, v, ws, we = tracks[20]
-    got = np.empty(len(ws), np.float32)
-    check(L.bxg_memcpy_d2h(got.ctypes.data_as(C.c_void_p), handles[20][4][1].ptr, got.nbytes))
-    _lib.sync()
-    dense = np.full(origin + len(v), np.nan, np.float32)
-    dense[origin:] = v
-    ref = orc.aggregate(dense, ws, we)["avg"]
-    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), "aggregate parity"
-    # genome-wide form: all windows (with their chromosome id) in one launch
-    wt_all = np.concatenate([np.full(len(t[2]), k, np.int32) for k, t in enumerate(tracks)])
-    ws_all = np.concatenate([t[2] for t in tracks])
-    we_all = np.concatenate([t[3] for t in tracks])
-    perm = np.random.default_rng(1).permutation(nw_all)          # BED order, not grouped by chromosome
-    d_wt, d_ws, d_we = (_lib.DeviceBuffer(a[perm]) for a in (wt_all, ws_all, we_all))
-    outs = [_lib.DeviceBuffer(np.zeros(nw_all, np.float32)) for _ in range(2)] + [_lib.DeviceBuffer(np.zeros(nw_all, np.int32))] + \
-           [_lib.DeviceBuffer(np.zeros(nw_all, np.float32)) for _ in range(2)]
-    ht = (C.c_void_p * len(handles))(*[h[0] for h in handles])
-
-    def genome_pass():
-        check(L.bxg_aggregate_multi(ht, None, len(handles), d_wt.ptr, d_ws.ptr, d_we.ptr, nw_all, _lib.DEVICE,
-                                    outs[0].ptr, outs[1].ptr, outs[2].ptr, outs[3].ptr, outs[4].ptr))
-    genome_pass()
-    _lib.sync()
-    timer.start()
-    for _ in range(5):
-        genome_pass()
-    timer.stop()
-    gms = timer.elapsed_ms() / 5
-    gavg = np.empty(nw_all, np.float32)
-    check(L.bxg_memcpy_d2h(gavg.ctypes.data_as(C.c_void_p), outs[1].ptr, gavg.nbytes))
-    _lib.sync()
-    sel = np.nonzero(wt_all[perm] == 20)[0]
-    ref2 = orc.aggregate(dense, ws_all[perm][sel], we_all[perm][sel])["avg"]
-    assert np.array_equal(gavg[sel].view(np.uint32), ref2.view(np.uint32)), "genome-wide aggregate parity"
-    for h, *_r in handles:
-        L.bxg_scores_free(h)
-    return {"ms": ms, "windows_per_s": nw_all / (ms * 1e-3), "bases_per_s": bases / (ms * 1e-3),
-            "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
-            "launches_per_pass": 24,
-            "genome": {"ms": gms, "windows_per_s": nw_all / (gms * 1e-3), "gbs": alg / (gms * 1e-3) / 1e9,
-                       "frac": alg / (gms * 1e-3) / 1e9 / peak, "launches_per_pass": 1},
-            "parity": "chr21 float32 averages bit-identical to oracle (per-chromosome and genome-wide launches)"}
 
 
 def bench_score_sources(peak):
@@ -1096,7 +1269,12 @@ def main():
     ap.add_argument("--nq", type=int, default=NQ_PER_GPU, help="queries per GPU")
     ap.add_argument("--ref-sample", type=float, default=0.1, help="fraction of each chromosome's queries per reference step")
     ap.add_argument("--ref-workers", type=int, default=0, help="processes for --impl reference (0 = usable cores - 1)")
-    ap.add_argument("--no-bitset", action="store_true")
+    ap.add_argument("--no-bitset", action="store_true", help="skip the configs[2..4] legs and the score-source extras")
+    ap.add_argument("--c4-n", dest="c4_n", type=int, default=50_000_000, help="intervals per BED file of configs[3]")
+    ap.add_argument("--c4-steps", dest="c4_steps", type=int, default=3)
+    ap.add_argument("--c5-scores", dest="c5_scores", type=int, default=100_000_000)
+    ap.add_argument("--c5-windows", dest="c5_windows", type=int, default=5_000_000)
+    ap.add_argument("--c5-steps", dest="c5_steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -34,6 +34,7 @@ SIGNATURES = {
     "bxg_host_free": [vp],
     "bxg_dev_alloc": [i64, pvp],
     "bxg_dev_free": [vp],
+    "bxg_dev_memset": [vp, cint, i64],
     "bxg_memcpy_h2d": [vp, vp, i64],
     "bxg_memcpy_d2h": [vp, vp, i64],
     "bxg_timer_create": [pvp],
@@ -42,12 +43,14 @@ SIGNATURES = {
     "bxg_timer_stop": [vp],
     "bxg_timer_elapsed_ms": [vp, C.POINTER(C.c_float)],
     "bxg_l2_flush": [],
+    "bxg_copy_probe": [i64, cint, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "bxg_profile_enable": [cint],
     "bxg_profile_report": [C.c_char_p, i64],
     "bxg_bits_create": [i32, i32, pvp],
     "bxg_bits_free": [vp],
     "bxg_bits_geometry": [vp, pi32, pi32, pi32],
     "bxg_bits_clone": [vp, pvp],
+    "bxg_bits_clear": [vp],
     "bxg_bits_set_ranges": [vp, vp, vp, i64, cint],
     "bxg_bits_set_ranges_multi": [pvp, i32, vp, vp, vp, i64, cint],
     "bxg_bits_set_bits": [vp, vp, i64, cint, cint],
@@ -60,6 +63,8 @@ SIGNATURES = {
     "bxg_bits_binop_batch": [cint, pvp, pvp, i32, vp],
     "bxg_bits_count_ranges": [vp, vp, vp, i64, vp, cint, cint],
     "bxg_bits_count_all": [vp, pi64],
+    "bxg_bits_count_all_multi": [pvp, i32, vp, i64, cint],
+    "bxg_group_stats_i32": [vp, vp, i64, i32, i32, vp, cint],
     "bxg_bits_count_ranges_multi": [pvp, i32, vp, vp, vp, i64, vp, cint, cint],
     "bxg_bits_next": [vp, i32, i32, cint, pi32],
     "bxg_bits_runs_count": [vp, pi64],
@@ -101,6 +106,7 @@ SIGNATURES = {
     "bxg_comm_init": [C.c_char_p, cint, cint],
     "bxg_comm_allreduce_i64": [vp, i64],
     "bxg_comm_allreduce_max_f64": [vp, i64],
+    "bxg_comm_allreduce_i64_dev": [vp, i64],
     "bxg_comm_barrier": [],
     "bxg_comm_destroy": [],
 }

@@ -238,6 +238,10 @@ class _DeviceBits:
         check(_lib.lib().bxg_bits_import_words(self._h, ptr(w)))
 
 
+GROUP = 1024        # sets per multi-set launch (the library's descriptor table, csrc/bits.cu BATCH_MAX_PAIRS); larger
+                    # genomes (scaffold-level assemblies with thousands of contigs) are served in groups of this many
+
+
 def _batch(op, dst, src, want_counts):
     dst, src = list(dst), list(src)
     if len(dst) != len(src):
@@ -249,10 +253,15 @@ def _batch(op, dst, src, want_counts):
     n = len(dst)
     if n == 0:
         return np.zeros(0, np.int64) if want_counts else None
-    ha = (C.c_void_p * n)(*[a._h for a in dst])
-    hb = (C.c_void_p * n)(*[b._h for b in src])
     counts = np.empty(n, np.int64) if want_counts else None
-    check(_lib.lib().bxg_bits_binop_batch(op, ha, hb, n, ptr(counts)))
+    for g in range(0, n, GROUP):
+        m = min(GROUP, n - g)
+        ha = (C.c_void_p * m)(*[a._h for a in dst[g:g + m]])
+        hb = (C.c_void_p * m)(*[b._h for b in src[g:g + m]])
+        part = np.empty(m, np.int64) if want_counts else None
+        check(_lib.lib().bxg_bits_binop_batch(op, ha, hb, m, ptr(part)))
+        if want_counts:
+            counts[g:g + m] = part
     return counts
 
 
@@ -271,40 +280,73 @@ def and_count_many(dst, src):
     return _batch(0, dst, src, True)
 
 
+def _check_many(sets, w, s, c):
+    """Vectorised bounds check of (which, start, count) triples: the first offending entry raises the IndexError the
+    scalar call on its set would raise (bitset.pyx:177-189), before any device work."""
+    if len(s) == 0:
+        return
+    sizes = np.asarray([b._size for b in sets], np.int64)
+    inside = (w >= 0) & (w < len(sets))
+    size_of = np.where(inside, sizes[np.clip(w, 0, len(sets) - 1)], np.int64(1) << 40)
+    s64, c64 = s.astype(np.int64), c.astype(np.int64)
+    bad = inside & ((s64 < 0) | (s64 >= size_of) | (c64 < 0) | (s64 + c64 > size_of))
+    if bad.any():
+        k = int(np.argmax(bad))
+        sets[int(w[k])]._check_range_count(int(s[k]), int(c[k]))
+
+
+def _groups(nsets, w):
+    """(first set, number of sets, entry selector or None) per launch group of at most GROUP sets."""
+    if nsets <= GROUP:
+        yield 0, nsets, None
+        return
+    for g in range(0, nsets, GROUP):
+        sel = np.nonzero((w >= g) & (w < g + GROUP))[0]
+        if len(sel):
+            yield g, min(GROUP, nsets - g), sel
+
+
 def set_ranges_many(sets, which, starts, counts):
-    """``sets[which[i]].set_range(starts[i], counts[i])`` for every i in one kernel launch -- the per-line loop of
-    lib/bx/bitset_builders.py:40-53 over a whole file.  Same IndexError as the scalar call for the first offending
-    entry of each set, raised before any device work."""
+    """``sets[which[i]].set_range(starts[i], counts[i])`` for every i in one kernel launch (one per 1024 sets) -- the
+    per-line loop of lib/bx/bitset_builders.py:40-53 over a whole file.  Same IndexError as the scalar call for the
+    first offending entry, raised before any device work."""
     sets = list(sets)
     w, s, c = as_i32(which), as_i32(starts), as_i32(counts)
     if len(w) and (w.min() < 0 or w.max() >= len(sets)):
         raise IndexError("bit set index out of range")
-    for k, b in enumerate(sets):
-        sel = w == k
-        if sel.any():
-            b._check_arrays(s[sel], c[sel])
+    _check_many(sets, w, s, c)
+    for b in sets:
         b._flush()
     if len(s) == 0:
         return
-    h = (C.c_void_p * len(sets))(*[b._h for b in sets])
-    check(_lib.lib().bxg_bits_set_ranges_multi(h, len(sets), ptr(w), ptr(s), ptr(c), len(s), _lib.HOST))
+    for g, m, sel in _groups(len(sets), w):
+        h = (C.c_void_p * m)(*[b._h for b in sets[g:g + m]])
+        gw, gs, gc = (w, s, c) if sel is None else (np.ascontiguousarray(w[sel] - g), np.ascontiguousarray(s[sel]),
+                                                    np.ascontiguousarray(c[sel]))
+        check(_lib.lib().bxg_bits_set_ranges_multi(h, m, ptr(gw), ptr(gs), ptr(gc), len(gs), _lib.HOST))
 
 
 def count_ranges_many(sets, which, starts, counts, strict=True):
-    """``sets[which[i]].count_range(starts[i], counts[i])`` for every i in one kernel launch -- the per-line lookup
-    of scripts/bed_intersect.py:46-53 (`bitsets[chrom].count_range(start, end - start)`).  Entries whose ``which`` is
-    outside the list count 0 (the script's `fields[0] in bitsets` test)."""
+    """``sets[which[i]].count_range(starts[i], counts[i])`` for every i in one kernel launch (one per 1024 sets) -- the
+    per-line lookup of scripts/bed_intersect.py:46-53 (`bitsets[chrom].count_range(start, end - start)`).  Entries whose
+    ``which`` is outside the list count 0 (the script's `fields[0] in bitsets` test)."""
     sets = list(sets)
     w, s, c = as_i32(which), as_i32(starts), as_i32(counts)
-    for k, b in enumerate(sets):
-        sel = w == k
-        if sel.any():
-            b._check_arrays(s[sel], c[sel])        # same IndexError as the scalar call, before any device work
+    _check_many(sets, w, s, c)                       # same IndexError as the scalar call, before any device work
+    for b in sets:
         b._flush()
-    out = np.empty(len(s), np.int32)
-    h = (C.c_void_p * len(sets))(*[b._h for b in sets])
-    check(_lib.lib().bxg_bits_count_ranges_multi(h, len(sets), ptr(w), ptr(s), ptr(c), len(s), ptr(out),
-                                                 1 if strict else 0, _lib.HOST))
+    out = np.zeros(len(s), np.int32)
+    if len(s) == 0 or not sets:
+        return out
+    for g, m, sel in _groups(len(sets), w):
+        h = (C.c_void_p * m)(*[b._h for b in sets[g:g + m]])
+        gw, gs, gc = (w, s, c) if sel is None else (np.ascontiguousarray(w[sel] - g), np.ascontiguousarray(s[sel]),
+                                                    np.ascontiguousarray(c[sel]))
+        part = out if sel is None else np.empty(len(gs), np.int32)
+        check(_lib.lib().bxg_bits_count_ranges_multi(h, m, ptr(gw), ptr(gs), ptr(gc), len(gs), ptr(part),
+                                                     1 if strict else 0, _lib.HOST))
+        if sel is not None:
+            out[sel] = part
     return out
 
 

@@ -161,7 +161,10 @@ int bxg_aggregate_multi(const bxg_scores_t *const *tracks, const bxg_bits_t *con
     Context &c = ctx();
     static TrackDesc h_desc[4096];
     for (int t = 0; t < ntracks; t++) {
-        if (!tracks[t]) return set_error(BXG_ERR_ARG, "null scores handle %d", t);
+        if (!tracks[t]) {                             // `chrom in scores_by_chrom` is false (:115): nothing is counted
+            h_desc[t] = TrackDesc{nullptr, 0, 0, __builtin_nanf(""), nullptr, 0};
+            continue;
+        }
         const bxg_bits *m = masks ? (const bxg_bits *)masks[t] : nullptr;
         h_desc[t] = TrackDesc{tracks[t]->v, tracks[t]->n, (int64_t)tracks[t]->origin, tracks[t]->fill, bxg_bits_words_internal(m),
                               (int64_t)bxg_bits_size_internal(m)};

@@ -21,7 +21,7 @@ struct bxg_bits {
     int64_t nwords_alloc = 0;  // nwords rounded up to a multiple of 4 (32 B)
     uint64_t *words = nullptr;
     uint8_t *state = nullptr;
-    uint32_t *rank = nullptr;  // exclusive prefix popcount per word, nwords_alloc+1 entries (lazy)
+    uint32_t *rank = nullptr;  // exclusive prefix popcount per 256-bit sector (4 words), nwords_alloc/4+1 entries (lazy)
     bool rank_valid = false;
     int32_t *run_s = nullptr, *run_e = nullptr;  // run extraction output (device)
     int64_t run_cap = 0, nruns = -1;
@@ -422,16 +422,70 @@ __global__ void k_read_bits(const uint64_t *__restrict__ words, const int32_t *_
 // ------------------------------------------------------------------------------------------------------------------
 // count_range x n  (binBits.c:130-178): rank table lookup, O(1) per query
 // ------------------------------------------------------------------------------------------------------------------
-struct PopcWord {
+// The rank table holds one exclusive prefix popcount per 256-bit SECTOR (4 words = one 32-byte DRAM sector): an eighth of
+// the bitmap's size (48 MB for a whole hg38 genome -- it stays in the 126 MB L2, where a per-word table of 193 MB did
+// not), built by one scan that reads the bitmap once.  rank(p) = table[p >> 8] + popcount of the sector's bits below
+// p & 255: one table sector + one bitmap sector (a single 256-bit load) per position.
+struct PopcSector {
     const uint64_t *w;
-    int64_t n;
-    __device__ __forceinline__ uint32_t operator()(int64_t i) const { return i < n ? (uint32_t)__popcll(w[i]) : 0u; }
+    int64_t nsec;
+    __device__ __forceinline__ uint32_t operator()(int64_t i) const {
+        if (i >= nsec) return 0u;
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(w + 4 * i);
+        const ulonglong2 a = __ldg(p), b = __ldg(p + 1);
+        return (uint32_t)(__popcll(a.x) + __popcll(a.y) + __popcll(b.x) + __popcll(b.y));
+    }
 };
 
-__device__ __forceinline__ uint32_t rank_at(const uint64_t *__restrict__ words, const uint32_t *__restrict__ rank, uint32_t p) {
-    uint32_t w = p >> 6, r = __ldg(rank + w), b = p & 63;
-    if (b) r += (uint32_t)__popcll(__ldg((const unsigned long long *)words + w) & ((1ull << b) - 1ull));
+__device__ __forceinline__ void ld_sector(const uint64_t *p, unsigned long long &a, unsigned long long &b,
+                                          unsigned long long &c, unsigned long long &d) {
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+
+// bits of the 256-bit sector (a,b,c,d) strictly below bit offset o in [1,255]
+__device__ __forceinline__ uint32_t popc_below(unsigned long long a, unsigned long long b, unsigned long long c,
+                                               unsigned long long d, uint32_t o) {
+    const uint32_t k = o >> 6;                                   // words fully below
+    const unsigned long long part = k == 0 ? a : k == 1 ? b : k == 2 ? c : d;
+    uint32_t r = (uint32_t)__popcll(part & ((1ull << (o & 63)) - 1ull));
+    if (k > 0) r += (uint32_t)__popcll(a);
+    if (k > 1) r += (uint32_t)__popcll(b);
+    if (k > 2) r += (uint32_t)__popcll(c);
     return r;
+}
+
+__device__ __forceinline__ uint32_t rank_at(const uint64_t *__restrict__ words, const uint32_t *__restrict__ rank, uint32_t p) {
+    const uint32_t sec = p >> 8, o = p & 255u;
+    uint32_t r = __ldg(rank + sec);
+    if (o) {
+        unsigned long long a, b, c, d;
+        ld_sector(words + 4 * (size_t)sec, a, b, c, d);
+        r += popc_below(a, b, c, d, o);
+    }
+    return r;
+}
+
+// popcount of [s, s + c), c > 0: when both ends fall into one sector a single sector load answers it without the table
+__device__ __forceinline__ int32_t count_span(const uint64_t *__restrict__ words, const uint32_t *__restrict__ rank, uint32_t s,
+                                              uint32_t c) {
+    const uint32_t e = s + c;
+    if ((s >> 8) == ((e - 1) >> 8)) {
+        unsigned long long w[4];
+        ld_sector(words + 4 * (size_t)(s >> 8), w[0], w[1], w[2], w[3]);
+        const uint32_t o0 = s & 255u, o1 = ((e - 1) & 255u) + 1u;   // bits [o0, o1) of the sector, o1 in [1,256]
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t lo = o0 > 64u * k ? o0 - 64u * k : 0u, hi = o1 > 64u * k ? o1 - 64u * k : 0u;
+            if (lo < 64u && hi > lo) {
+                unsigned long long m = hi >= 64u ? ~0ull : ((1ull << hi) - 1ull);
+                m &= ~0ull << lo;
+                r += (uint32_t)__popcll(w[k] & m);
+            }
+        }
+        return (int32_t)r;
+    }
+    return (int32_t)(rank_at(words, rank, e) - rank_at(words, rank, s));
 }
 
 __global__ void __launch_bounds__(256)
@@ -442,7 +496,7 @@ k_count_ranges(const uint64_t *__restrict__ words, const uint32_t *__restrict__ 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int32_t s = __ldg(start + i), c = __ldg(count + i), r = 0;
         if (c > 0) {
-            r = (int32_t)(rank_at(words, rank, (uint32_t)s + (uint32_t)c) - rank_at(words, rank, (uint32_t)s));
+            r = count_span(words, rank, (uint32_t)s, (uint32_t)c);
             // binBits.c:155,161: an ALL_ONE *sentinel* first bin contributes (k - offset) instead of k
             if (strict && state[s / bin_size] == BO) r -= s % bin_size;
         }
@@ -469,7 +523,7 @@ k_count_ranges_multi(const CountDesc *__restrict__ descs, int nsets, const int32
         if (w >= 0 && w < nsets && c > 0) {
             const CountDesc d = descs[w];
             if (s >= 0 && (int64_t)s + c <= d.size) {          // out-of-range queries are the host shim's IndexError
-                r = (int32_t)(rank_at(d.words, d.rank, (uint32_t)s + (uint32_t)c) - rank_at(d.words, d.rank, (uint32_t)s));
+                r = count_span(d.words, d.rank, (uint32_t)s, (uint32_t)c);
                 if (d.strict && d.state[s / d.bin_size] == BO) r -= s % d.bin_size;
             }
         }
@@ -568,6 +622,57 @@ __global__ void k_fill_u8(uint8_t *p, int64_t n, uint8_t v) {
 __global__ void k_mask_tail(uint64_t *words, int64_t nwords, int64_t nwords_alloc, uint64_t tail_mask) {
     int64_t i = nwords - 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == nwords - 1) words[i] &= tail_mask; else if (i < nwords_alloc) words[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Per-chromosome counters of a whole file (the numbers the multi-GPU runs reduce with NCCL): for every key k
+//   stats[2k]   += #(entries with key == k and val >= threshold)      e.g. BED lines that overlap (bed_intersect.py:53)
+//   stats[2k+1] += sum of val over the entries with key == k          e.g. overlapping bases / counted positions
+// Warp-aggregated (match_any groups the lanes of one key: one shared-memory atomic per key and warp), one global atomic
+// per key and CTA.  Bytes: 8 per entry.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int STATS_MAX_KEYS = 1024;
+
+__global__ void __launch_bounds__(256)
+k_group_stats(const int32_t *__restrict__ key, const int32_t *__restrict__ val, int64_t n, int nkeys, int32_t threshold,
+              unsigned long long *__restrict__ stats) {
+    __shared__ unsigned int s_cnt[STATS_MAX_KEYS];
+    __shared__ unsigned long long s_sum[STATS_MAX_KEYS];
+    for (int k = threadIdx.x; k < nkeys; k += blockDim.x) { s_cnt[k] = 0; s_sum[k] = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {   // warp-uniform
+        const int64_t i = base + lane;
+        int32_t k = -1, v = 0;
+        if (i < n) { k = __ldcs(key + i); v = __ldcs(val + i); }
+        if (k < 0 || k >= nkeys) k = -1;
+        const unsigned grp = __match_any_sync(0xffffffffu, k);
+        const unsigned ge = __ballot_sync(0xffffffffu, k >= 0 && v >= threshold);
+        // group sum of a signed 32-bit value without overflow: low and high halves separately
+        const unsigned lo16 = __reduce_add_sync(grp, (unsigned)v & 0xffffu);
+        const int hi16 = __reduce_add_sync(grp, v >> 16);
+        if (k >= 0 && lane == __ffs((int)grp) - 1) {
+            const unsigned c = (unsigned)__popc(ge & grp);
+            if (c) atomicAdd(&s_cnt[k], c);
+            const long long sum = (long long)hi16 * 65536ll + (long long)lo16;
+            if (sum) atomicAdd(&s_sum[k], (unsigned long long)sum);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nkeys; k += blockDim.x) {
+        if (s_cnt[k]) atomicAdd(stats + 2 * k, (unsigned long long)s_cnt[k]);
+        if (s_sum[k]) atomicAdd(stats + 2 * k + 1, s_sum[k]);
+    }
+}
+
+// out[k] = popcount of set k, read off the last entry of its rank table
+struct TotalDesc {
+    const uint32_t *rank_last;
+};
+__global__ void k_gather_totals(const TotalDesc *__restrict__ d, int n, long long *__restrict__ out, int64_t out_stride) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[(int64_t)k * out_stride] = d[k].rank_last ? (long long)*d[k].rank_last : 0ll;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -693,7 +798,10 @@ int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int3
     static SetDesc h_desc[BATCH_MAX_PAIRS];
     for (int k = 0; k < nsets; k++) {
         bxg_bits *b = sets[k];
-        if (!b) return set_error(BXG_ERR_ARG, "null bitset handle %d", k);
+        if (!b) {                                     // a chromosome this process holds no bitmap for: its ranges are skipped
+            h_desc[k] = SetDesc{nullptr, nullptr, 1, 1, 0};
+            continue;
+        }
         h_desc[k] = SetDesc{b->words, b->state, b->bin_size, b->flat ? 1 : 0, b->size};
     }
     Context &c = ctx();
@@ -706,8 +814,10 @@ int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int3
     BXG_TRY(stage_in(5, count, (size_t)n * 4, loc, &dc));
     BXG_LAUNCH(k_set_ranges_multi, grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets, (const int32_t *)dw,
                (const int32_t *)ds, (const int32_t *)dc, n);
-    for (int k = 0; k < nsets; k++) invalidate(sets[k]);
-    BXG_CUDA(cudaStreamSynchronize(c.stream));         // h_desc is static and the caller may reuse its arrays
+    for (int k = 0; k < nsets; k++)
+        if (sets[k]) invalidate(sets[k]);
+    // (h_desc is pageable: cudaMemcpyAsync has staged it before returning, so the static table may be reused at once)
+    if (loc == BXG_HOST) BXG_CUDA(cudaStreamSynchronize(c.stream));         // the caller may reuse its arrays on return
     return BXG_OK;
 }
 
@@ -860,15 +970,17 @@ int bxg_bits_count_all(const bxg_bits_t *b, int64_t *count) {
 static int build_rank(bxg_bits *b) {
     if (b->rank_valid) return BXG_OK;
     Context &c = ctx();
-    int64_t n = b->nwords_alloc + 1;
+    const int64_t nsec = b->nwords_alloc / 4, n = nsec + 1;
     if (!b->rank) BXG_CUDA(cudaMalloc(&b->rank, (size_t)n * 4));
     cub::CountingInputIterator<int64_t> idx(0);
-    cub::TransformInputIterator<uint32_t, PopcWord, cub::CountingInputIterator<int64_t>> it(idx, PopcWord{b->words, b->nwords_alloc});
+    cub::TransformInputIterator<uint32_t, PopcSector, cub::CountingInputIterator<int64_t>> it(idx, PopcSector{b->words, nsec});
     size_t tmp_bytes = 0;
     BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, b->rank, n, c.stream));
     void *tmp;
     BXG_TRY(scratch(7, tmp_bytes, &tmp));
+    prof_begin("cub::DeviceScan::ExclusiveSum(rank)");
     BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, b->rank, n, c.stream));
+    prof_end();
     c.launches += 2;   // CUB's single-pass scan: init + scan kernels
     b->rank_valid = true;
     return BXG_OK;
@@ -914,7 +1026,10 @@ int bxg_bits_count_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const in
     static CountDesc h_desc[BATCH_MAX_PAIRS];
     for (int k = 0; k < nsets; k++) {
         bxg_bits *b = sets[k];
-        if (!b) return set_error(BXG_ERR_ARG, "null bitset handle %d", k);
+        if (!b) {                                     // `fields[0] in bitsets` is false (bed_intersect.py:53): count 0
+            h_desc[k] = CountDesc{nullptr, nullptr, nullptr, 1, 0, 0};
+            continue;
+        }
         BXG_TRY(build_rank(b));
         h_desc[k] = CountDesc{b->words, b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0, b->size};
     }
@@ -936,6 +1051,76 @@ int bxg_bits_count_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const in
                (const int32_t *)dw, (const int32_t *)ds, (const int32_t *)dc, n, dout);
     if (loc == BXG_HOST) {
         BXG_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, c.stream));
+        BXG_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return BXG_OK;
+}
+
+int bxg_bits_clear(bxg_bits_t *b) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    Context &c = ctx();
+    BXG_CUDA(cudaMemsetAsync(b->words, 0, (size_t)b->nwords_alloc * 8, c.stream));
+    BXG_CUDA(cudaMemsetAsync(b->state, BZ, (size_t)b->nbins, c.stream));
+    invalidate(b);
+    return BXG_OK;
+}
+
+int bxg_bits_count_all_multi(bxg_bits_t *const *sets, int32_t nsets, int64_t *out, int64_t out_stride, int loc) {
+    BXG_TRY(ensure_init());
+    if (nsets <= 0) return BXG_OK;
+    if (nsets > BATCH_MAX_PAIRS) return set_error(BXG_ERR_ARG, "nsets must be in [1, %d]", BATCH_MAX_PAIRS);
+    if (!out || out_stride < 1 || (loc == BXG_HOST && out_stride != 1))
+        return set_error(BXG_ERR_ARG, "bad output (host output needs out_stride == 1)");
+    static TotalDesc h_desc[BATCH_MAX_PAIRS];
+    for (int k = 0; k < nsets; k++) {
+        bxg_bits *b = sets[k];
+        if (!b) {
+            h_desc[k] = TotalDesc{nullptr};
+            continue;
+        }
+        BXG_TRY(build_rank(b));
+        h_desc[k] = TotalDesc{b->rank + b->nwords_alloc / 4};
+    }
+    Context &c = ctx();
+    void *d_desc;
+    BXG_TRY(scratch(3, sizeof(TotalDesc) * (size_t)nsets, &d_desc));
+    BXG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(TotalDesc) * (size_t)nsets, cudaMemcpyHostToDevice, c.stream));
+    long long *dout = (long long *)out;
+    if (loc == BXG_HOST) {
+        void *t;
+        BXG_TRY(scratch(4, 8 * (size_t)nsets, &t));
+        dout = (long long *)t;
+    }
+    BXG_LAUNCH(k_gather_totals, (nsets + 127) / 128, 128, 0, (const TotalDesc *)d_desc, (int)nsets, dout,
+               loc == BXG_HOST ? (int64_t)1 : out_stride);
+    if (loc == BXG_HOST) {
+        BXG_CUDA(cudaMemcpyAsync(out, dout, 8 * (size_t)nsets, cudaMemcpyDeviceToHost, c.stream));
+        BXG_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return BXG_OK;
+}
+
+int bxg_group_stats_i32(const int32_t *key, const int32_t *val, int64_t n, int32_t nkeys, int32_t threshold, int64_t *stats,
+                        int loc) {
+    BXG_TRY(ensure_init());
+    if (nkeys <= 0 || nkeys > STATS_MAX_KEYS) return set_error(BXG_ERR_ARG, "nkeys must be in [1, %d]", STATS_MAX_KEYS);
+    if (!stats) return set_error(BXG_ERR_ARG, "stats is null");
+    if (n <= 0) return BXG_OK;
+    Context &c = ctx();
+    const void *dk, *dv;
+    BXG_TRY(stage_in(0, key, (size_t)n * 4, loc, &dk));
+    BXG_TRY(stage_in(1, val, (size_t)n * 4, loc, &dv));
+    unsigned long long *dst = (unsigned long long *)stats;
+    if (loc == BXG_HOST) {
+        void *t;
+        BXG_TRY(scratch(4, 16 * (size_t)nkeys, &t));
+        dst = (unsigned long long *)t;
+        BXG_CUDA(cudaMemcpyAsync(dst, stats, 16 * (size_t)nkeys, cudaMemcpyHostToDevice, c.stream));
+    }
+    BXG_LAUNCH(k_group_stats, grid_for(cdiv(n, 256 * 8), 4), 256, 0, (const int32_t *)dk, (const int32_t *)dv, n, (int)nkeys,
+               threshold, dst);
+    if (loc == BXG_HOST) {
+        BXG_CUDA(cudaMemcpyAsync(stats, dst, 16 * (size_t)nkeys, cudaMemcpyDeviceToHost, c.stream));
         BXG_CUDA(cudaStreamSynchronize(c.stream));
     }
     return BXG_OK;

@@ -197,6 +197,11 @@ int bxg_dev_free(void *dptr) {
     }
     return BXG_OK;
 }
+int bxg_dev_memset(void *dptr, int value, int64_t bytes) {
+    BXG_TRY(ensure_init());
+    BXG_CUDA(cudaMemsetAsync(dptr, value, (size_t)bytes, g_ctx.stream));
+    return BXG_OK;
+}
 int bxg_memcpy_h2d(void *dptr, const void *hptr, int64_t bytes) {
     BXG_TRY(ensure_init());
     BXG_CUDA(cudaMemcpyAsync(dptr, hptr, (size_t)bytes, cudaMemcpyHostToDevice, g_ctx.stream));
@@ -280,6 +285,73 @@ int bxg_profile_report(char *buf, int64_t cap) {
     if ((int64_t)out.size() + 1 > cap) return set_error(BXG_ERR_ARG, "profile buffer too small (%zu needed)", out.size() + 1);
     memcpy(buf, out.c_str(), out.size() + 1);
     return BXG_OK;
+}
+
+// Pinned-memory copy rates of this process's GPU: host-to-device alone, device-to-host alone, and both directions at once
+// (two streams).  bench.py calls it on every rank at the same time (after a barrier) to measure what the box's PCIe /
+// host-memory side can sustain when all GPUs copy together -- the ceiling of the end-to-end figure.
+int bxg_copy_probe(int64_t bytes, int reps, double *h2d_gbs, double *d2h_gbs, double *bidir_gbs) {
+    BXG_TRY(ensure_init());
+    if (bytes < 4096 || reps < 1) return set_error(BXG_ERR_ARG, "bad probe size");
+    void *h0 = nullptr, *h1 = nullptr, *d0 = nullptr, *d1 = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    int rc = BXG_OK;
+    auto fail = [&](cudaError_t err, const char *what) {
+        rc = set_error(BXG_ERR_CUDA, "copy probe: %s failed: %s", what, cudaGetErrorString(err));
+    };
+    cudaError_t err;
+    do {
+        if ((err = cudaMallocHost(&h0, (size_t)bytes)) != cudaSuccess) { fail(err, "cudaMallocHost"); break; }
+        if ((err = cudaMallocHost(&h1, (size_t)bytes)) != cudaSuccess) { fail(err, "cudaMallocHost"); break; }
+        if ((err = cudaMalloc(&d0, (size_t)bytes)) != cudaSuccess) { fail(err, "cudaMalloc"); break; }
+        if ((err = cudaMalloc(&d1, (size_t)bytes)) != cudaSuccess) { fail(err, "cudaMalloc"); break; }
+        memset(h0, 1, (size_t)bytes);                 // first touch on this process's node
+        memset(h1, 2, (size_t)bytes);
+        cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
+        for (auto &x : e) cudaEventCreate(&x);
+        cudaMemcpyAsync(d0, h0, (size_t)bytes, cudaMemcpyHostToDevice, s0);      // warm-up both directions
+        cudaMemcpyAsync(h1, d1, (size_t)bytes, cudaMemcpyDeviceToHost, s1);
+        cudaStreamSynchronize(s0);
+        cudaStreamSynchronize(s1);
+        float ms = 0.f;
+        cudaEventRecord(e[0], s0);
+        for (int r = 0; r < reps; r++) cudaMemcpyAsync(d0, h0, (size_t)bytes, cudaMemcpyHostToDevice, s0);
+        cudaEventRecord(e[1], s0);
+        cudaEventSynchronize(e[1]);
+        cudaEventElapsedTime(&ms, e[0], e[1]);
+        if (h2d_gbs) *h2d_gbs = (double)bytes * reps / (ms * 1e-3) / 1e9;
+        cudaEventRecord(e[0], s1);
+        for (int r = 0; r < reps; r++) cudaMemcpyAsync(h1, d1, (size_t)bytes, cudaMemcpyDeviceToHost, s1);
+        cudaEventRecord(e[1], s1);
+        cudaEventSynchronize(e[1]);
+        cudaEventElapsedTime(&ms, e[0], e[1]);
+        if (d2h_gbs) *d2h_gbs = (double)bytes * reps / (ms * 1e-3) / 1e9;
+        // both directions at once: wall time from the common start to the later finish
+        cudaEventRecord(e[0], s0);
+        cudaStreamWaitEvent(s1, e[0], 0);
+        for (int r = 0; r < reps; r++) {
+            cudaMemcpyAsync(d0, h0, (size_t)bytes, cudaMemcpyHostToDevice, s0);
+            cudaMemcpyAsync(h1, d1, (size_t)bytes, cudaMemcpyDeviceToHost, s1);
+        }
+        cudaEventRecord(e[1], s0);
+        cudaEventRecord(e[2], s1);
+        cudaEventSynchronize(e[1]);
+        cudaEventSynchronize(e[2]);
+        float m0 = 0.f, m1 = 0.f;
+        cudaEventElapsedTime(&m0, e[0], e[1]);
+        cudaEventElapsedTime(&m1, e[0], e[2]);
+        if (bidir_gbs) *bidir_gbs = 2.0 * (double)bytes * reps / ((m0 > m1 ? m0 : m1) * 1e-3) / 1e9;
+        if ((err = cudaGetLastError()) != cudaSuccess) fail(err, "copies");
+    } while (0);
+    for (auto &x : e) if (x) cudaEventDestroy(x);
+    if (s0) cudaStreamDestroy(s0);
+    if (s1) cudaStreamDestroy(s1);
+    cudaFree(d0); cudaFree(d1);
+    if (h0) cudaFreeHost(h0);
+    if (h1) cudaFreeHost(h1);
+    return rc;
 }
 
 int bxg_l2_flush(void) {
@@ -377,6 +449,17 @@ int bxg_comm_init(const char id[BXG_UNIQUE_ID_BYTES], int nranks, int rank) {
 
 int bxg_comm_allreduce_i64(int64_t *buf, int64_t n) { return allreduce(buf, (size_t)n, 8, ncclInt64, ncclSum); }
 int bxg_comm_allreduce_max_f64(double *buf, int64_t n) { return allreduce(buf, (size_t)n, 8, ncclFloat64, ncclMax); }
+// in place on a DEVICE buffer, enqueued on the library stream, no host synchronisation: the reduction of the
+// per-chromosome counters stays inside the device-timed step (single rank: identity)
+int bxg_comm_allreduce_i64_dev(int64_t *dbuf, int64_t n) {
+    if (!g_nccl.comm) {
+        if (g_nccl.nranks <= 1) return BXG_OK;
+        return set_error(BXG_ERR_STATE, "bxg_comm_init not called");
+    }
+    if (!dbuf || n <= 0) return set_error(BXG_ERR_ARG, "bad buffer");
+    BXG_NCCL(g_nccl.AllReduce(dbuf, dbuf, (size_t)n, ncclInt64, ncclSum, g_nccl.comm, ctx().stream));
+    return BXG_OK;
+}
 int bxg_comm_barrier(void) {
     int64_t x = 1;
     return bxg_comm_allreduce_i64(&x, 1);

@@ -54,6 +54,7 @@ int bxg_host_alloc(int64_t bytes, void **ptr);
 int bxg_host_free(void *ptr);
 int bxg_dev_alloc(int64_t bytes, void **dptr);
 int bxg_dev_free(void *dptr);
+int bxg_dev_memset(void *dptr, int value, int64_t bytes);           /* async on the library stream */
 int bxg_memcpy_h2d(void *dptr, const void *hptr, int64_t bytes);   /* async on the library stream */
 int bxg_memcpy_d2h(void *hptr, const void *dptr, int64_t bytes);   /* async; call bxg_sync() before reading */
 
@@ -65,6 +66,9 @@ int bxg_timer_start(bxg_timer_t *t);
 int bxg_timer_stop(bxg_timer_t *t);
 int bxg_timer_elapsed_ms(bxg_timer_t *t, float *ms);               /* synchronises on the stop event */
 int bxg_l2_flush(void);                            /* overwrite a buffer larger than L2 (timing hygiene) */
+/* pinned-memory copy rates of this process's GPU in GB/s: H2D alone, D2H alone, both directions at once (two streams);
+ * `bytes` per copy, `reps` copies per measurement.  bench.py runs it on all ranks at once: the box's e2e ceiling. */
+int bxg_copy_probe(int64_t bytes, int reps, double *h2d_gbs, double *d2h_gbs, double *bidir_gbs);
 /* per-kernel CUDA-event timing of every launch the library makes: enable(1) clears and starts recording,
  * report() synchronises and writes "<kernel>\t<launches>\t<total_ms>\n" lines (bench.py's roofline uses it) */
 int bxg_profile_enable(int on);
@@ -86,6 +90,7 @@ int bxg_bits_create(int32_t size, int32_t granularity, bxg_bits_t **out);
 int bxg_bits_free(bxg_bits_t *b);                                                   /* binBitsFree / bitFree   */
 int bxg_bits_geometry(const bxg_bits_t *b, int32_t *size, int32_t *bin_size, int32_t *nbins);
 int bxg_bits_clone(const bxg_bits_t *b, bxg_bits_t **out);                          /* bitClone (bits.c:58-66)  */
+int bxg_bits_clear(bxg_bits_t *b);        /* bitClear (bits.c:190-195) / a fresh binBitsAlloc: all bits 0, all bins ALL_ZERO */
 
 /* binBitsSetRange (binBits.c:98-128) / bitSetRange (bits.c:86-109), n ranges per call; ranges must satisfy
  * 0 <= start, 0 <= count, start+count <= size (the host shim raises the reference's IndexError first). */
@@ -117,11 +122,23 @@ int bxg_bits_binop_batch(int op, bxg_bits_t *const *a, const bxg_bits_t *const *
 int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *count, int64_t n,
                           int32_t *out, int strict, int loc);
 int bxg_bits_count_all(const bxg_bits_t *b, int64_t *count);                  /* count_range(0, size)          */
+/* count_range(0, size) of every set of a genome in one launch (read off the rank tables, built on demand):
+ * out[k * out_stride] = popcount(sets[k]) (0 for a NULL entry); device output (loc == BXG_DEVICE) is not synchronised. */
+int bxg_bits_count_all_multi(bxg_bits_t *const *sets, int32_t nsets, int64_t *out, int64_t out_stride, int loc);
 /* Genome-wide form of `bitsets[chrom].count_range(start, end-start)` per BED line (scripts/bed_intersect.py:46-53):
- * query i addresses sets[which[i]]; which outside [0,nsets) (chromosome without a bitset) or an out-of-range span
- * yields 0.  One launch. */
+ * query i addresses sets[which[i]]; which outside [0,nsets), a NULL sets[k] (chromosome without a bitset: `fields[0] in
+ * bitsets` is false, :53) or an out-of-range span yields 0.  One launch. */
 int bxg_bits_count_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int32_t *which, const int32_t *start,
                                 const int32_t *count, int64_t n, int32_t *out, int strict, int loc);
+
+/* Per-chromosome counters of a whole file -- what the multi-GPU runs reduce: for every key k in [0, nkeys)
+ *   stats[2k] += #(i : key[i] == k && val[i] >= threshold),   stats[2k+1] += sum(val[i] : key[i] == k).
+ * With val = the counts of bxg_bits_count_ranges_multi and threshold = mincols this is the number of lines
+ * scripts/bed_intersect.py:53 prints per chromosome; with val = the window counts of bxg_aggregate_multi and threshold 1
+ * the number of windows aggregate_scores_in_intervals.py:126 gives an average.  stats is ACCUMULATED into (zero it first);
+ * entries with a key outside [0, nkeys) are ignored.  nkeys <= 1024. */
+int bxg_group_stats_i32(const int32_t *key, const int32_t *val, int64_t n, int32_t nkeys, int32_t threshold,
+                        int64_t *stats /* 2 * nkeys */, int loc);
 
 /* binBitsFindSet / binBitsFindClear (binBits.c:180-228) ; bitFindSet/Clear with an end bound (bits.c:143-190).
  * first position p in [start, end) whose bit == val, else `end`; end <= size. */
@@ -226,7 +243,8 @@ int bxg_aggregate(const bxg_scores_t *s, const bxg_bits_t *mask /* or NULL */,
                   const int32_t *ws, const int32_t *we, int64_t nw, int loc,
                   float *sum, float *avg, int32_t *count, float *mn, float *mx);
 /* Genome-wide form: window w reads track tracks[wtrack[w]] (the script's `scores_by_chrom[chrom]`, :115; a track id
- * outside [0,ntracks) behaves like a chromosome without scores).  masks may be NULL, or hold NULL entries.  One launch. */
+ * outside [0,ntracks), or a NULL tracks[k], behaves like a chromosome without scores).  masks may be NULL, or hold NULL
+ * entries.  One launch. */
 int bxg_aggregate_multi(const bxg_scores_t *const *tracks, const bxg_bits_t *const *masks, int32_t ntracks,
                         const int32_t *wtrack, const int32_t *ws, const int32_t *we, int64_t nw, int loc,
                         float *sum, float *avg, int32_t *count, float *mn, float *mx);
@@ -272,6 +290,9 @@ int bxg_comm_unique_id(char id[BXG_UNIQUE_ID_BYTES]);                 /* rank 0;
 int bxg_comm_init(const char id[BXG_UNIQUE_ID_BYTES], int nranks, int rank);
 int bxg_comm_allreduce_i64(int64_t *buf, int64_t n);                   /* in-place sum over ranks (host buffer) */
 int bxg_comm_allreduce_max_f64(double *buf, int64_t n);                /* in-place max over ranks (timings)     */
+/* the same sum on a DEVICE buffer, enqueued on the library stream without a host synchronisation (the reduce of the
+ * per-chromosome counters inside a device-timed step) */
+int bxg_comm_allreduce_i64_dev(int64_t *dbuf, int64_t n);
 int bxg_comm_barrier(void);
 int bxg_comm_destroy(void);
 
