@@ -69,6 +69,8 @@ SIGNATURES = {
     "bxg_bits_next": [vp, i32, i32, cint, pi32],
     "bxg_bits_runs_count": [vp, pi64],
     "bxg_bits_runs_fetch": [vp, vp, vp, i64],
+    "bxg_bits_runs_in_ranges": [vp, vp, vp, i64, cint, cint, vp, pi64],
+    "bxg_bits_runs_in_ranges_fetch": [vp, vp, vp, i64],
     "bxg_bits_states": [vp, vp],
     "bxg_bits_export_words": [vp, vp],
     "bxg_bits_import_words": [vp, vp],
@@ -84,6 +86,7 @@ SIGNATURES = {
     "bxg_itree_find_host": [vp, vp, vp, vp, i64, pvp, pvp, pi64],
     "bxg_itree_find_host32": [vp, vp, vp, vp, i64, pvp, pvp, pi64],
     "bxg_itree_find_small": [vp, vp, vp, vp, i32, pvp, pvp, pi64],
+    "bxg_itree_find1": [vp, i32, i32, i32, pvp],
     "bxg_itree_result_dev": [vp, pvp, pvp, pi64, pi64],
     "bxg_itree_count": [vp, vp, vp, vp, i64, cint, vp, pi64],
     "bxg_itree_neighbors": [vp, vp, vp, vp, vp, i64, cint, cint, pi64],
@@ -110,7 +113,7 @@ SIGNATURES = {
     "bxg_comm_barrier": [],
     "bxg_comm_destroy": [],
 }
-_RESTYPE = {"bxg_last_error": C.c_char_p, "bxg_version": C.c_char_p}
+_RESTYPE = {"bxg_last_error": C.c_char_p, "bxg_version": C.c_char_p, "bxg_itree_find1": i64}
 
 _lib = None
 _initialised = False

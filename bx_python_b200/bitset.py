@@ -217,6 +217,22 @@ class _DeviceBits:
         check(_lib.lib().bxg_bits_runs_fetch(self._h, ptr(rs), ptr(re), n.value))
         return rs, re
 
+    def runs_in_ranges(self, starts, ends, val=1):
+        """For every range [starts[i], ends[i]) the maximal runs of bits == val inside it, clipped to the range: the
+        generators bits_set_in_range / bits_clear_in_range (lib/bx/intervals/operations/__init__.py:10-33) for a whole
+        file in two launches.  -> (offsets int64[n+1], run_starts int32[], run_ends int32[]) in CSR form."""
+        s, e = as_i32(starts), as_i32(ends)
+        if len(s) != len(e):
+            raise ValueError("starts and ends must have the same length")
+        self._flush()
+        off = np.zeros(len(s) + 1, np.int64)
+        total = C.c_int64()
+        L = _lib.lib()
+        check(L.bxg_bits_runs_in_ranges(self._h, ptr(s), ptr(e), len(s), 1 if val else 0, _lib.HOST, ptr(off), C.byref(total)))
+        rs, re = np.empty(total.value, np.int32), np.empty(total.value, np.int32)
+        check(L.bxg_bits_runs_in_ranges_fetch(self._h, ptr(rs), ptr(re), total.value))
+        return off, rs, re
+
     def _next(self, start, end, val):
         self._flush()
         out = C.c_int32()

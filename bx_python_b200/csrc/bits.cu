@@ -25,6 +25,8 @@ struct bxg_bits {
     bool rank_valid = false;
     int32_t *run_s = nullptr, *run_e = nullptr;  // run extraction output (device)
     int64_t run_cap = 0, nruns = -1;
+    int32_t *rr_s = nullptr, *rr_e = nullptr;    // runs-in-ranges output (device)
+    int64_t rr_cap = 0, rr_total = 0;
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -410,13 +412,23 @@ k_set_ranges_multi(const SetDesc *__restrict__ descs, int nsets, const int32_t *
     }
 }
 
+// `flag` (single-CTA launches of the scalar calls only, else null): completion word in mapped host memory, written after
+// the results with a system-scope fence -- the host spins on it instead of synchronising the stream (common.cuh zc_wait)
+__device__ __forceinline__ void zc_signal(volatile long long *flag, long long seq) {
+    if (flag == nullptr) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = seq;
+}
+
 __global__ void k_read_bits(const uint64_t *__restrict__ words, const int32_t *__restrict__ pos, int64_t n,
-                            uint8_t *__restrict__ out) {
+                            uint8_t *__restrict__ out, volatile long long *flag, long long seq) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int32_t p = pos[i];
         out[i] = (uint8_t)((words[p >> 6] >> (p & 63)) & 1ull);
     }
+    zc_signal(flag, seq);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -491,7 +503,7 @@ __device__ __forceinline__ int32_t count_span(const uint64_t *__restrict__ words
 __global__ void __launch_bounds__(256)
 k_count_ranges(const uint64_t *__restrict__ words, const uint32_t *__restrict__ rank, const uint8_t *__restrict__ state,
                int bin_size, int strict, const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n,
-               int32_t *__restrict__ out) {
+               int32_t *__restrict__ out, volatile long long *flag, long long seq) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int32_t s = __ldg(start + i), c = __ldg(count + i), r = 0;
@@ -502,6 +514,7 @@ k_count_ranges(const uint64_t *__restrict__ words, const uint32_t *__restrict__ 
         }
         out[i] = r;
     }
+    zc_signal(flag, seq);
 }
 
 // genome-wide form: query i addresses bit set which[i] (the dict lookup `bitsets[chrom]` of scripts/bed_intersect.py:46-53)
@@ -546,6 +559,38 @@ k_next(const uint64_t *__restrict__ words, int64_t start, int64_t end, int val, 
         if (w == w1 && (end & 63)) x &= (1ull << (end & 63)) - 1ull;
         if (x) atomicMin(result, (unsigned long long)((w << 6) + __ffsll((long long)x) - 1));
     }
+}
+
+// The scalar next_set / next_clear almost always finds its bit close by (the run-extraction idiom of the scripts walks
+// from run to run): one warp scans the first NEAR_WORDS words and writes the answer (or -1) straight into mapped host
+// memory, completion word last -- no copies, no stream synchronise.  Only a miss pays for the grid-wide kernel above.
+constexpr int NEAR_WORDS = 32 * 16;
+
+__global__ void __launch_bounds__(32)
+k_next_near(const uint64_t *__restrict__ words, int64_t start, int64_t end, int val, long long *__restrict__ out,
+            volatile long long *flag, long long seq) {
+    const int64_t w0 = start >> 6, w1 = (end - 1) >> 6;
+    long long found = -1;
+    for (int j = 0; j < NEAR_WORDS / 32 && found < 0; j++) {
+        const int64_t w = w0 + j * 32 + threadIdx.x;
+        unsigned long long x = 0;
+        if (w <= w1) {
+            x = words[w];
+            if (!val) x = ~x;
+            if (w == w0) x &= ~0ull << (start & 63);
+            if (w == w1 && (end & 63)) x &= (1ull << (end & 63)) - 1ull;
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, x != 0);
+        if (any) {
+            const int src = __ffs((int)any) - 1;
+            const unsigned long long xs = __shfl_sync(0xffffffffu, x, src);
+            found = ((w0 + j * 32 + src) << 6) + __ffsll((long long)xs) - 1;
+        } else if (w0 + (j + 1) * 32 > w1) {
+            found = end;                                   // scanned to the end of the range: nothing there
+        }
+    }
+    if (threadIdx.x == 0) *out = found;
+    zc_signal(flag, seq);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -615,6 +660,62 @@ k_runs_fill(const uint64_t *__restrict__ words, int64_t nwords_alloc, const uint
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Runs inside ranges: for range i the maximal runs of bits == val inside [start[i], end[i]), clipped to the range -- the
+// generators bits_set_in_range / bits_clear_in_range of lib/bx/intervals/operations/__init__.py:10-33 (the per-interval
+// `pieces` of operations/intersect.py:62-70 and subtract.py:66-72) for a whole file.  One thread per range walks its
+// words (BED intervals span a few dozen words); FILL = false counts the runs, FILL = true writes them at the CSR offsets.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_runs_in_ranges(const uint64_t *__restrict__ words, int32_t size, const int32_t *__restrict__ start,
+                 const int32_t *__restrict__ end, int64_t n, int val, int32_t *__restrict__ cnt,
+                 const int64_t *__restrict__ off, int32_t *__restrict__ out_s, int32_t *__restrict__ out_e) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int64_t s = start[i], e = end[i];
+        if (s < 0) s = 0;
+        if (e > size) e = size;
+        int32_t c = 0;
+        int64_t o = FILL ? off[i] : 0;
+        if (s < e) {
+            const int64_t w0 = s >> 6, w1 = (e - 1) >> 6;
+            unsigned long long prev = 0;                      // the bit in front of the range counts as "not val"
+            int64_t run_start = -1;
+            for (int64_t w = w0; w <= w1; w++) {
+                unsigned long long x = __ldg((const unsigned long long *)words + w);
+                if (!val) x = ~x;
+                if (w == w0) x &= ~0ull << (s & 63);
+                if (w == w1 && (e & 63)) x &= (1ull << (e & 63)) - 1ull;
+                unsigned long long rise = x & ~((x << 1) | prev);          // run starts in this word
+                if (!FILL) {
+                    c += __popcll(rise);
+                } else {
+                    unsigned long long fall = ~x & ((x << 1) | prev);      // first non-val bit after a run
+                    while (rise | fall) {
+                        const int br = rise ? __ffsll((long long)rise) - 1 : 64, bf = fall ? __ffsll((long long)fall) - 1 : 64;
+                        if (br < bf) {
+                            run_start = (w << 6) + br;
+                            rise &= rise - 1;
+                        } else {
+                            out_s[o] = (int32_t)run_start;
+                            out_e[o] = (int32_t)((w << 6) + bf);
+                            o++;
+                            fall &= fall - 1;
+                        }
+                    }
+                }
+                prev = x >> 63;
+            }
+            if (FILL && prev) {                                // the last run reaches the end of the range
+                out_s[o] = (int32_t)run_start;
+                out_e[o] = (int32_t)e;
+            }
+        }
+        if (!FILL) cnt[i] = c;
+    }
+}
+
 __global__ void k_fill_u8(uint8_t *p, int64_t n, uint8_t v) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
@@ -632,38 +733,58 @@ __global__ void k_mask_tail(uint64_t *words, int64_t nwords, int64_t nwords_allo
 // per key and CTA.  Bytes: 8 per entry.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int STATS_MAX_KEYS = 1024;
+constexpr int STATS_FLUSH = 256;          // tiles between flushes: 256 x 256 entries keep the 32-bit partial sums exact
 
 __global__ void __launch_bounds__(256)
 k_group_stats(const int32_t *__restrict__ key, const int32_t *__restrict__ val, int64_t n, int nkeys, int32_t threshold,
               unsigned long long *__restrict__ stats) {
-    __shared__ unsigned int s_cnt[STATS_MAX_KEYS];
-    __shared__ unsigned long long s_sum[STATS_MAX_KEYS];
-    for (int k = threadIdx.x; k < nkeys; k += blockDim.x) { s_cnt[k] = 0; s_sum[k] = 0; }
+    // per-CTA partial counters; a value is accumulated as (v >> 16, v & 0xffff) so that 32-bit shared atomics suffice
+    __shared__ unsigned int s_cnt[STATS_MAX_KEYS], s_lo[STATS_MAX_KEYS];
+    __shared__ int s_hi[STATS_MAX_KEYS];
+    auto flush = [&]() {
+        __syncthreads();
+        for (int k = threadIdx.x; k < nkeys; k += blockDim.x) {
+            const long long sum = (long long)s_hi[k] * 65536ll + (long long)s_lo[k];
+            if (s_cnt[k]) atomicAdd(stats + 2 * k, (unsigned long long)s_cnt[k]);
+            if (sum) atomicAdd(stats + 2 * k + 1, (unsigned long long)sum);
+            s_cnt[k] = 0; s_lo[k] = 0; s_hi[k] = 0;
+        }
+        __syncthreads();
+    };
+    for (int k = threadIdx.x; k < nkeys; k += blockDim.x) { s_cnt[k] = 0; s_lo[k] = 0; s_hi[k] = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {   // warp-uniform
-        const int64_t i = base + lane;
+    int tiles = 0;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {             // CTA-uniform
+        const int64_t i = base + threadIdx.x;
         int32_t k = -1, v = 0;
         if (i < n) { k = __ldcs(key + i); v = __ldcs(val + i); }
         if (k < 0 || k >= nkeys) k = -1;
-        const unsigned grp = __match_any_sync(0xffffffffu, k);
-        const unsigned ge = __ballot_sync(0xffffffffu, k >= 0 && v >= threshold);
-        // group sum of a signed 32-bit value without overflow: low and high halves separately
-        const unsigned lo16 = __reduce_add_sync(grp, (unsigned)v & 0xffffu);
-        const int hi16 = __reduce_add_sync(grp, v >> 16);
-        if (k >= 0 && lane == __ffs((int)grp) - 1) {
-            const unsigned c = (unsigned)__popc(ge & grp);
-            if (c) atomicAdd(&s_cnt[k], c);
-            const long long sum = (long long)hi16 * 65536ll + (long long)lo16;
-            if (sum) atomicAdd(&s_sum[k], (unsigned long long)sum);
+        const int k0 = __shfl_sync(0xffffffffu, k, 0);
+        if (__all_sync(0xffffffffu, k == k0)) {
+            // sorted input: the whole warp holds one key -- reduce in registers, one lane updates the counters
+            if (k0 >= 0) {
+                const unsigned c = (unsigned)__popc(__ballot_sync(0xffffffffu, v >= threshold));
+                const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xffffu);
+                const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+                if (lane == 0) {
+                    if (c) atomicAdd(&s_cnt[k0], c);
+                    if (lo) atomicAdd(&s_lo[k0], lo);
+                    if (hi) atomicAdd(&s_hi[k0], hi);
+                }
+            }
+        } else if (k >= 0) {
+            if (v >= threshold) atomicAdd(&s_cnt[k], 1u);
+            if (v & 0xffff) atomicAdd(&s_lo[k], (unsigned)v & 0xffffu);
+            if (v >> 16) atomicAdd(&s_hi[k], v >> 16);
+        }
+        if (++tiles == STATS_FLUSH) {
+            flush();
+            tiles = 0;
         }
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < nkeys; k += blockDim.x) {
-        if (s_cnt[k]) atomicAdd(stats + 2 * k, (unsigned long long)s_cnt[k]);
-        if (s_sum[k]) atomicAdd(stats + 2 * k + 1, s_sum[k]);
-    }
+    flush();
 }
 
 // out[k] = popcount of set k, read off the last entry of its rank table
@@ -752,6 +873,8 @@ int bxg_bits_free(bxg_bits_t *b) {
     cudaFree(b->rank);
     cudaFree(b->run_s);
     cudaFree(b->run_e);
+    cudaFree(b->rr_s);
+    cudaFree(b->rr_e);
     delete b;
     return BXG_OK;
 }
@@ -838,8 +961,9 @@ int bxg_bits_read(const bxg_bits_t *b, const int32_t *pos, int64_t n, uint8_t *o
     if (n <= 0) return BXG_OK;
     if (zc_small(loc, n)) {                 // __getitem__ of one position: no staging copies (common.cuh)
         memcpy(zc_host(0), pos, (size_t)n * 4);
-        BXG_LAUNCH(k_read_bits, 1, 64, 0, b->words, (const int32_t *)zc_device(0), n, (uint8_t *)zc_device(1));
-        BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+        const long long seq = zc_next_seq();
+        BXG_LAUNCH(k_read_bits, 1, 64, 0, b->words, (const int32_t *)zc_device(0), n, (uint8_t *)zc_device(1), zc_flag_device(), seq);
+        BXG_TRY(zc_wait(seq));
         memcpy(out, zc_host(1), (size_t)n);
         return BXG_OK;
     }
@@ -851,7 +975,8 @@ int bxg_bits_read(const bxg_bits_t *b, const int32_t *pos, int64_t n, uint8_t *o
         BXG_TRY(scratch(1, (size_t)n, &t));
         dout = (uint8_t *)t;
     }
-    BXG_LAUNCH(k_read_bits, grid_for(cdiv(n, 256), 8), 256, 0, b->words, (const int32_t *)dp, n, dout);
+    BXG_LAUNCH(k_read_bits, grid_for(cdiv(n, 256), 8), 256, 0, b->words, (const int32_t *)dp, n, dout,
+               (volatile long long *)nullptr, 0ll);
     if (loc == BXG_HOST) {
         BXG_CUDA(cudaMemcpyAsync(out, dout, (size_t)n, cudaMemcpyDeviceToHost, ctx().stream));
         BXG_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -994,9 +1119,10 @@ int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *co
     if (zc_small(loc, n)) {                 // the scalar count_range(start, count): no staging copies (common.cuh)
         memcpy(zc_host(0), start, (size_t)n * 4);
         memcpy(zc_host(1), count, (size_t)n * 4);
-        BXG_LAUNCH(k_count_ranges, 1, 256, 0, b->words, b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0,
-                   (const int32_t *)zc_device(0), (const int32_t *)zc_device(1), n, (int32_t *)zc_device(2));
-        BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+        const long long seq = zc_next_seq();
+        BXG_LAUNCH(k_count_ranges, 1, 64, 0, b->words, b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0,
+                   (const int32_t *)zc_device(0), (const int32_t *)zc_device(1), n, (int32_t *)zc_device(2), zc_flag_device(), seq);
+        BXG_TRY(zc_wait(seq));
         memcpy(out, zc_host(2), (size_t)n * 4);
         return BXG_OK;
     }
@@ -1010,7 +1136,7 @@ int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *co
         dout = (int32_t *)t;
     }
     BXG_LAUNCH(k_count_ranges, grid_for(cdiv(n, 256), 8), 256, 0, b->words, b->rank, b->state, b->bin_size,
-               (strict && !b->flat) ? 1 : 0, (const int32_t *)ds, (const int32_t *)dc, n, dout);
+               (strict && !b->flat) ? 1 : 0, (const int32_t *)ds, (const int32_t *)dc, n, dout, (volatile long long *)nullptr, 0ll);
     if (loc == BXG_HOST) {
         BXG_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx().stream));
         BXG_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -1134,6 +1260,17 @@ int bxg_bits_next(const bxg_bits_t *b, int32_t start, int32_t end, int val, int3
         return BXG_OK;
     }
     Context &c = ctx();
+    if (c.zc) {
+        const long long seq = zc_next_seq();
+        BXG_LAUNCH(k_next_near, 1, 32, 0, b->words, (int64_t)start, (int64_t)end, val, (long long *)zc_device(3), zc_flag_device(), seq);
+        BXG_TRY(zc_wait(seq));
+        const long long r = *(volatile long long *)zc_host(3);
+        if (r >= 0) {
+            *out = (int32_t)r;
+            return BXG_OK;
+        }
+        start = (int32_t)((((int64_t)start >> 6) + NEAR_WORDS) << 6);     // continue behind the scanned words
+    }
     c.mailbox[1] = end;
     BXG_CUDA(cudaMemcpyAsync(c.d_mailbox + 1, c.mailbox + 1, 8, cudaMemcpyHostToDevice, c.stream));
     int64_t nw = ((int64_t)(end - 1) >> 6) - (start >> 6) + 1;
@@ -1197,6 +1334,64 @@ int bxg_bits_runs_fetch(bxg_bits_t *b, int32_t *starts, int32_t *ends, int64_t n
     if (nruns == 0) return BXG_OK;
     BXG_CUDA(cudaMemcpyAsync(starts, b->run_s, (size_t)nruns * 4, cudaMemcpyDeviceToHost, ctx().stream));
     BXG_CUDA(cudaMemcpyAsync(ends, b->run_e, (size_t)nruns * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    return BXG_OK;
+}
+
+struct CastI32ToI64 {
+    __device__ __forceinline__ int64_t operator()(int32_t v) const { return (int64_t)v; }
+};
+
+int bxg_bits_runs_in_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *end, int64_t n, int val, int loc,
+                            int64_t *offsets, int64_t *total) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (n < 0 || !offsets) return set_error(BXG_ERR_ARG, "bad arguments");
+    Context &c = ctx();
+    offsets[0] = 0;
+    b->rr_total = 0;
+    if (total) *total = 0;
+    if (n == 0) return BXG_OK;
+    const void *ds, *de;
+    BXG_TRY(stage_in(0, start, (size_t)n * 4, loc, &ds));
+    BXG_TRY(stage_in(1, end, (size_t)n * 4, loc, &de));
+    void *d_cnt, *d_off, *tmp;
+    BXG_TRY(scratch(2, (size_t)(n + 1) * 4, &d_cnt));
+    BXG_TRY(scratch(4, (size_t)(n + 1) * 8, &d_off));
+    BXG_CUDA(cudaMemsetAsync((int32_t *)d_cnt + n, 0, 4, c.stream));
+    const int grid = grid_for(cdiv(n, 256), 8);
+    BXG_LAUNCH((k_runs_in_ranges<false>), grid, 256, 0, b->words, b->size, (const int32_t *)ds, (const int32_t *)de, n,
+               val ? 1 : 0, (int32_t *)d_cnt, (const int64_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr);
+    cub::TransformInputIterator<int64_t, CastI32ToI64, const int32_t *> it((const int32_t *)d_cnt, CastI32ToI64());
+    size_t tmp_bytes = 0;
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, (int64_t *)d_off, n + 1, c.stream));
+    BXG_TRY(scratch(7, tmp_bytes, &tmp));
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, (int64_t *)d_off, n + 1, c.stream));
+    c.launches += 2;
+    BXG_CUDA(cudaMemcpyAsync(offsets, d_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    const int64_t nr = offsets[n];
+    if (nr > b->rr_cap) {
+        cudaFree(b->rr_s);
+        cudaFree(b->rr_e);
+        b->rr_s = b->rr_e = nullptr;
+        b->rr_cap = nr + nr / 4 + 16;
+        BXG_CUDA(cudaMalloc(&b->rr_s, (size_t)b->rr_cap * 4));
+        BXG_CUDA(cudaMalloc(&b->rr_e, (size_t)b->rr_cap * 4));
+    }
+    if (nr > 0)
+        BXG_LAUNCH((k_runs_in_ranges<true>), grid, 256, 0, b->words, b->size, (const int32_t *)ds, (const int32_t *)de, n,
+                   val ? 1 : 0, (int32_t *)nullptr, (const int64_t *)d_off, b->rr_s, b->rr_e);
+    b->rr_total = nr;
+    if (total) *total = nr;
+    return BXG_OK;
+}
+
+int bxg_bits_runs_in_ranges_fetch(bxg_bits_t *b, int32_t *starts, int32_t *ends, int64_t total) {
+    if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
+    if (total != b->rr_total) return set_error(BXG_ERR_ARG, "total mismatch (%lld vs %lld)", (long long)total, (long long)b->rr_total);
+    if (total == 0) return BXG_OK;
+    BXG_CUDA(cudaMemcpyAsync(starts, b->rr_s, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    BXG_CUDA(cudaMemcpyAsync(ends, b->rr_e, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx().stream));
     BXG_CUDA(cudaStreamSynchronize(ctx().stream));
     return BXG_OK;
 }

@@ -24,6 +24,7 @@ struct Context {
     // 4 KB of mapped pinned memory: tiny host arrays of scalar-style calls are read / written by the kernel in place
     // (no staging copies) -- see zc_small()
     char *zc = nullptr, *zc_dev = nullptr;
+    long long zc_seq = 0;
     void *l2_flush_buf = nullptr;
     size_t l2_flush_bytes = 0;
 };
@@ -77,6 +78,13 @@ constexpr int64_t ZC_MAX_ITEMS = 64;          // per array; the page holds 4 arr
 static inline bool zc_small(int loc, int64_t n) { return loc == BXG_HOST && n <= ZC_MAX_ITEMS && ctx().zc != nullptr; }
 static inline void *zc_host(int k) { return ctx().zc + (size_t)k * 512; }
 static inline void *zc_device(int k) { return ctx().zc_dev + (size_t)k * 512; }
+// completion word of the scalar-style launches (last 8 bytes of the page): the kernel stores the call's sequence number
+// there after its results (system-scope fence), the host spins on it -- a few hundred nanoseconds after the kernel's
+// last write instead of the several microseconds a cudaStreamSynchronize adds
+constexpr size_t ZC_FLAG_OFFSET = 4096 - 8;
+static inline volatile long long *zc_flag_device() { return (volatile long long *)(ctx().zc_dev + ZC_FLAG_OFFSET); }
+static inline long long zc_next_seq() { return ++ctx().zc_seq; }
+int zc_wait(long long seq);
 
 // Stage a caller array onto the device if it lives on the host; returns the device pointer to use.
 int stage_in(int slot, const void *src, size_t bytes, int loc, const void **dptr);

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "itree_search.cuh"
@@ -46,6 +47,9 @@ struct IndexView {
                                                   // [a x16 | b x16] layout, pitch 2, measured slower -- profiles/r01k)
     const int32_t *M[MAX_LEVELS];
     const int64_t *toff;
+    const bxs::GridRec *G;       // direct-address grid records (all trees, see itree_search.cuh: search_walk_grid)
+    const unsigned char *dir;    // tree directory: toff[ntrees+1] (int64), padded to 16 B, then GridDir[ntrees]
+    uint32_t dir_bytes, dir_grid_off;
     const int32_t *spS, *spPM;   // contiguous: spS[nsplit_pad] then spPM[nsplit_pad]
     uint32_t n;
     int32_t ntrees, nlev, nsplit, nsplit_pad, shift;   // stride = 1 << shift
@@ -60,6 +64,10 @@ struct bxg_itree {
     int64_t mlen[MAX_LEVELS] = {0, 0, 0, 0, 0, 0};
     int nlev = 0;
     int64_t *toff = nullptr;
+    bxs::GridRec *G = nullptr;            // grid records of all trees
+    unsigned char *dir = nullptr;         // [toff | pad | GridDir x ntrees], one TMA bulk copy per CTA
+    uint32_t dir_bytes = 0, dir_grid_off = 0;
+    int64_t ncells_total = 0;
     int32_t *split = nullptr;
     int nsplit = 0, nsplit_pad = 0, shift = 0;
     int32_t *KS[MAX_KLEV] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] aliases S
@@ -90,8 +98,11 @@ struct bxg_itree {
     long long *d_result = nullptr;          // 2 x (MAX_CHUNKS + 1)
     long long *h_result = nullptr;          // pinned mirror
     // small-batch path (bxg_itree_find_small): results land in mapped pinned memory, written by the kernel itself
-    long long *m_off = nullptr;             // SMALL_Q + 1 offsets, then an overflow flag
+    long long *m_off = nullptr;             // SMALL_Q + 1 offsets, an overflow flag, the completion sequence number
     int32_t *m_hits = nullptr;              // SMALL_CAP hit ids
+    long long *md_off = nullptr;            // their device addresses
+    int32_t *md_hits = nullptr;
+    long long m_seq = 0;
     // the staged query arrays of the last find (device pointers valid until the next call)
     IndexView view() const {
         IndexView v;
@@ -103,6 +114,7 @@ struct bxg_itree {
         v.QS[0] = S; v.QP[0] = PM; v.n8 = n8;
         v.KS[0] = S; v.KP[0] = PM; v.WE = E; v.WI = I; v.mul = 1;
         v.toff = toff; v.spS = split; v.spPM = split + nsplit_pad;
+        v.G = G; v.dir = dir; v.dir_bytes = dir_bytes; v.dir_grid_off = dir_grid_off;
         v.n = (uint32_t)n; v.ntrees = ntrees; v.nlev = nlev; v.nsplit = nsplit; v.nsplit_pad = nsplit_pad; v.shift = shift;
         return v;
     }
@@ -199,6 +211,46 @@ __global__ void k_sample(const int32_t *__restrict__ S, const int32_t *__restric
     split[nsplit_pad + k] = (k < nsplit && p < n) ? PM[p] : INT32_MAX;
 }
 
+// per tree: {smallest start, largest start} (S is sorted inside a tree)
+__global__ void k_tree_extent(const int32_t *__restrict__ S, const int64_t *__restrict__ toff, int ntrees, int32_t *__restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntrees) return;
+    const int64_t a = toff[t], b = toff[t + 1];
+    out[2 * t] = a < b ? S[a] : 0;
+    out[2 * t + 1] = a < b ? S[b - 1] : 0;
+}
+
+// grid records: one thread per record (tree t, cell c in 0..ncells): x = lower_bound(S, cell_start), y = upper_bound(PM, cell_start)
+// inside the tree's segment; cell_start = base + (c << shift) in 64 bits (the sentinel cell may lie beyond INT32_MAX)
+__global__ void k_build_grid(const int32_t *__restrict__ S, const int32_t *__restrict__ PM, const int64_t *__restrict__ toff,
+                             const bxs::GridDir *__restrict__ gd, int ntrees, int64_t nrec, bxs::GridRec *__restrict__ G) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrec; r += stride) {
+        int lo = 0, hi = ntrees - 1;                     // tree of record r: largest t with coff[t] <= r
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int64_t)gd[mid].coff <= r) lo = mid; else hi = mid - 1;
+        }
+        const bxs::GridDir d = gd[lo];
+        const int64_t c = r - d.coff;
+        const int64_t v = (int64_t)d.base + (c << d.shift);
+        const int64_t a = toff[lo], b = toff[lo + 1];
+        int64_t l = a, h = b;
+        while (l < h) {                                  // first k with S[k] >= v
+            const int64_t m = (l + h) >> 1;
+            if ((int64_t)S[m] < v) l = m + 1; else h = m;
+        }
+        const uint32_t x = (uint32_t)l;
+        l = a;
+        h = b;
+        while (l < h) {                                  // first k with PM[k] > v
+            const int64_t m = (l + h) >> 1;
+            if ((int64_t)PM[m] <= v) l = m + 1; else h = m;
+        }
+        G[r] = bxs::GridRec{x, (uint32_t)l};
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS)
 // ------------------------------------------------------------------------------------------------------------------
@@ -235,6 +287,7 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
 struct SmemIndex {
     const int32_t *spS, *spPM;   // shared
     const int64_t *toff;         // shared (ntrees <= SMEM_TREES) or global
+    const bxs::GridDir *gdir;    // likewise (PROBE 3 only)
 };
 
 // The search (dual_search) and walk (walk_hits) arithmetic lives in itree_search.cuh so that the CPU fuzz harness
@@ -333,10 +386,34 @@ __device__ __forceinline__ void st_stream_q(unsigned long long *p, unsigned long
 // PROBE selects the search: 2 = search_walk_probe8 (one search over 8-ary levels + backward probe of QP[1], half-group
 // walk: ~8 sectors per query), 1 = search_walk_probe (the same over the 16-ary levels: ~10), 0 = search_walk (two
 // lock-step searches: ~13); identical results, kept switchable (BXB200_FIND_PROBE) for A/B runs
+// one 8-byte grid record; the records of neighbouring cells share sectors (the qs and qe cells of a BED-sized query are
+// 0-2 cells apart), so they may stay in L1; L2 keeps them with the rest of the index
+#if FIND_L2_HINTS
+struct LdRec {
+    uint64_t pol;
+    __device__ __forceinline__ LdRec() : pol(l2_keep_policy()) {}
+    __device__ __forceinline__ bxs::GridRec operator()(const bxs::GridRec *p) const {
+        bxs::GridRec r;
+        asm("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+        return r;
+    }
+};
+#else
+struct LdRec {
+    __device__ __forceinline__ bxs::GridRec operator()(const bxs::GridRec *p) const {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        return bxs::GridRec{v.x, v.y};
+    }
+};
+#endif
+
 template <int PROBE, typename SP, typename F>
-__device__ __forceinline__ void query_search_walk(const IndexView &ix, const SP &spS, const SP &spPM, uint32_t seg_lo,
-                                                  uint32_t seg_hi, int32_t qe, int32_t qs, uint32_t &hi, uint32_t &lo, F &&f) {
-    if (PROBE == 2)
+__device__ __forceinline__ void query_search_walk(const IndexView &ix, const SP &spS, const SP &spPM, const bxs::GridDir *gd,
+                                                  uint32_t seg_lo, uint32_t seg_hi, int32_t qe, int32_t qs, uint32_t &hi,
+                                                  uint32_t &lo, F &&f) {
+    if (PROBE == 3)
+        bxs::search_walk_grid(ix.G, *gd, ix.S, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdRec(), LdK8(), Ld1(), hi, lo, f);
+    else if (PROBE == 2)
         bxs::search_walk_probe8(ix.QS, ix.QP, ix.n8, spS, spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdTop8(),
                                 LdK8(), Ld1(), hi, lo, f);
     else if (PROBE == 1)
@@ -368,6 +445,32 @@ __device__ __forceinline__ const SmemIndex stage_index(const IndexView &ix, unsi
     s.spS = sp;
     s.spPM = sp + ix.nsplit_pad;
     s.toff = toff_smem ? stoff : ix.toff;
+    s.gdir = nullptr;
+    return s;
+}
+
+// PROBE 3 (direct addressing) needs no splitter table: the only per-CTA state is the tree directory -- segment offsets and
+// grid geometry of every tree, 24 bytes per chromosome -- staged by ONE 1-D TMA bulk copy (it is laid out for that:
+// [toff | pad to 16 B | GridDir x ntrees], csrc/itree.cu build).  Forests with more than SMEM_TREES trees read it from L2.
+__device__ __forceinline__ const SmemIndex stage_dir(const IndexView &ix, unsigned char *smem_raw) {
+    SmemIndex s;
+    s.spS = s.spPM = nullptr;
+    if (ix.ntrees > SMEM_TREES || ix.dir_bytes == 0) {
+        s.toff = ix.toff;
+        s.gdir = reinterpret_cast<const bxs::GridDir *>(ix.dir + ix.dir_grid_off);
+        return s;
+    }
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    unsigned char *dst = smem_raw + 16;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, ix.dir_bytes);
+        tma_load_1d(dst, ix.dir, ix.dir_bytes, bar);
+    }
+    __syncthreads();                       // barrier init visible to every thread
+    mbar_wait(bar, 0);
+    s.toff = reinterpret_cast<const int64_t *>(dst);
+    s.gdir = reinterpret_cast<const bxs::GridDir *>(dst + ix.dir_grid_off);
     return s;
 }
 
@@ -398,7 +501,7 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
        unsigned long long *total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemIndex sm;
-    if (!FILL) sm = stage_index(ix, smem_raw);
+    if (!FILL) sm = PROBE == 3 ? stage_dir(ix, smem_raw) : stage_index(ix, smem_raw);
     unsigned long long local = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // Fill only: the inputs of the next grid-stride iteration are loaded at the top of the current one (0.350 -> 0.338 ms).
@@ -420,7 +523,7 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
                 // hi: candidates (start < qe) end here; lo: coarse start of the walk (running max end > qs from here on)
-                query_search_walk<PROBE>(ix, sm.spS, sm.spPM, seg_lo, seg_hi, qe, qs, hi, lo, st);
+                query_search_walk<PROBE>(ix, sm.spS, sm.spPM, PROBE == 3 ? sm.gdir + t : nullptr, seg_lo, seg_hi, qe, qs, hi, lo, st);
             }
             cnt[q] = st.c;                                 // read again right away by the scan: keep it cached
             st_stream_q(lo_ + q, (int32_t)((st.c ? st.base : lo) | (st.overflow ? WALK_AGAIN : 0u)));
@@ -589,7 +692,7 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
     __shared__ typename BS::TempStorage scan_tmp;
     __shared__ unsigned int s_tile;
     __shared__ long long s_base;
-    const SmemIndex sm = stage_index(ix, smem_raw);
+    const SmemIndex sm = PROBE == 3 ? stage_dir(ix, smem_raw) : stage_index(ix, smem_raw);
     const unsigned int ntiles = (unsigned int)((nq + FUSED_THREADS - 1) / FUSED_THREADS);
     const int lane = threadIdx.x & 31;
     while (true) {
@@ -608,7 +711,7 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
             const int32_t t = qtree ? __ldg(qtree + q) : 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
-                query_search_walk<PROBE>(ix, sm.spS, sm.spPM, seg_lo, seg_hi, qe, qs, hi, lo, st);
+                query_search_walk<PROBE>(ix, sm.spS, sm.spPM, PROBE == 3 ? sm.gdir + t : nullptr, seg_lo, seg_hi, qe, qs, hi, lo, st);
                 c = st.c;
             }
         }
@@ -667,6 +770,8 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
 // ------------------------------------------------------------------------------------------------------------------
 static void free_index(bxg_itree *t) {
     cudaFree(t->S); cudaFree(t->E); cudaFree(t->I); cudaFree(t->PM); cudaFree(t->toff); cudaFree(t->split);
+    cudaFree(t->G); cudaFree(t->dir);
+    t->G = nullptr; t->dir = nullptr; t->dir_bytes = t->dir_grid_off = 0; t->ncells_total = 0;
     for (int l = 0; l < MAX_LEVELS; l++) { cudaFree(t->M[l]); t->M[l] = nullptr; t->mlen[l] = 0; }
     for (int j = 1; j < MAX_KLEV; j++) { cudaFree(t->KS[j]); cudaFree(t->KP[j]); }
     for (int j = 0; j < MAX_KLEV; j++) t->KS[j] = t->KP[j] = nullptr;
@@ -684,7 +789,8 @@ static void free_index(bxg_itree *t) {
     t->built = false;
 }
 
-static size_t find_smem_bytes(const bxg_itree *t) {
+static size_t find_smem_bytes(const bxg_itree *t, int probe) {
+    if (probe == 3) return 16 + (t->ntrees <= SMEM_TREES ? (size_t)t->dir_bytes : 0);
     return 16 + (size_t)t->nsplit_pad * 8 + (t->ntrees <= SMEM_TREES ? (size_t)(t->ntrees + 1) * 8 : 0);
 }
 
@@ -706,11 +812,12 @@ static int ensure_query_buffers(bxg_itree *t, int64_t nq) {
     return BXG_OK;
 }
 
-static int find_probe() {      // 2 (default): 8-ary levels + probe; 1: 16-ary levels + probe; 0: two lock-step searches
+// 3 (default): direct-address grid; 2: 8-ary levels + probe; 1: 16-ary levels + probe; 0: two lock-step searches
+static int find_probe() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("BXB200_FIND_PROBE");
-        v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+        v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
     }
     return v;
 }
@@ -719,7 +826,7 @@ static int find_probe() {      // 2 (default): 8-ary levels + probe; 1: 16-ary l
 template <int PROBE>
 static int launch_count_as(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, const int32_t *dqe, int64_t nq,
                            unsigned long long *d_total, int64_t q0) {
-    size_t smem = find_smem_bytes(t);
+    size_t smem = find_smem_bytes(t, PROBE);
     static bool attr_set = false;
     if (!attr_set) {
         BXG_CUDA(cudaFuncSetAttribute(k_find<false, PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -740,7 +847,8 @@ static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
     switch (find_probe()) {
         case 0: return launch_count_as<0>(t, dqt, dqs, dqe, nq, d_total, q0);
         case 1: return launch_count_as<1>(t, dqt, dqs, dqe, nq, d_total, q0);
-        default: return launch_count_as<2>(t, dqt, dqs, dqe, nq, d_total, q0);
+        case 2: return launch_count_as<2>(t, dqt, dqs, dqe, nq, d_total, q0);
+        default: return launch_count_as<3>(t, dqt, dqs, dqe, nq, d_total, q0);
     }
 }
 
@@ -977,6 +1085,51 @@ int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, c
         BXG_LAUNCH(k_sample_level, gk, 256, 0, t->PM, n, ss, t->QP[j], nout, nout_pad);
     }
 
+    // direct-address grid (search_walk_grid): per tree a uniform grid over its start coordinates with 2-4 items per cell
+    {
+        void *d_ext;
+        {
+            int r = scratch(6, (size_t)ntrees * 8 + 16, &d_ext);
+            if (r != BXG_OK) { cleanup(); return r; }
+        }
+        BXG_LAUNCH(k_tree_extent, (ntrees + 127) / 128, 128, 0, t->S, t->toff, ntrees, (int32_t *)d_ext);
+        std::vector<int32_t> ext((size_t)ntrees * 2);
+        std::vector<int64_t> h_toff((size_t)ntrees + 1);
+        BUILD_CUDA(cudaMemcpyAsync(ext.data(), d_ext, (size_t)ntrees * 8, cudaMemcpyDeviceToHost, c.stream));
+        BUILD_CUDA(cudaMemcpyAsync(h_toff.data(), t->toff, (size_t)(ntrees + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
+        BUILD_CUDA(cudaStreamSynchronize(c.stream));
+        static const int dens = [] {                     // log2 of the target items per cell (lower bound); default 1 -> 2-4 items
+            const char *e = getenv("BXB200_GRID_LOG2");
+            return e ? std::max(0, std::min(8, atoi(e))) : 1;
+        }();
+        const size_t toff_bytes = (((size_t)ntrees + 1) * 8 + 15) & ~(size_t)15;
+        std::vector<unsigned char> h_dir(toff_bytes + (size_t)ntrees * sizeof(bxs::GridDir), 0);
+        memcpy(h_dir.data(), h_toff.data(), ((size_t)ntrees + 1) * 8);
+        bxs::GridDir *gd = reinterpret_cast<bxs::GridDir *>(h_dir.data() + toff_bytes);
+        int64_t nrec = 0;
+        for (int k = 0; k < ntrees; k++) {
+            const int64_t nt = h_toff[k + 1] - h_toff[k];
+            const uint64_t span = nt > 0 ? (uint64_t)((int64_t)ext[2 * k + 1] - (int64_t)ext[2 * k]) : 0;
+            const uint64_t limit = (uint64_t)std::max<int64_t>(1, nt >> dens);
+            int shift = 0;
+            while ((span >> shift) + 1 > limit) shift++;
+            gd[k].base = ext[2 * k];
+            gd[k].shift = shift;
+            gd[k].ncells = nt > 0 ? (uint32_t)((span >> shift) + 1) : 0u;
+            gd[k].coff = (uint32_t)nrec;
+            nrec += (int64_t)gd[k].ncells + 1;
+        }
+        t->dir_grid_off = (uint32_t)toff_bytes;
+        t->dir_bytes = (uint32_t)h_dir.size();
+        t->ncells_total = nrec;
+        BUILD_CUDA(cudaMalloc(&t->dir, h_dir.size()));
+        BUILD_CUDA(cudaMalloc(&t->G, (size_t)nrec * sizeof(bxs::GridRec)));
+        BUILD_CUDA(cudaMemcpyAsync(t->dir, h_dir.data(), h_dir.size(), cudaMemcpyHostToDevice, c.stream));
+        BXG_LAUNCH(k_build_grid, grid_for(cdiv(nrec, 256), 8), 256, 0, t->S, t->PM, t->toff,
+                   (const bxs::GridDir *)(t->dir + toff_bytes), (int)ntrees, nrec, t->G);
+        BUILD_CUDA(cudaStreamSynchronize(c.stream));     // h_dir is a local
+    }
+
     BUILD_CUDA(cudaMemcpyAsync(c.mailbox + 4, c.d_mailbox + 4, 8, cudaMemcpyDeviceToHost, c.stream));
     BUILD_CUDA(cudaStreamSynchronize(c.stream));
     cleanup();
@@ -1206,7 +1359,7 @@ static int launch_fused_as(bxg_itree *t, const int32_t *dqt, const int32_t *dqs,
     BXG_CUDA(cudaMemsetAsync(t->d_tiles + tile0, 0, (size_t)ntiles * 8, c.stream));
     BXG_CUDA(cudaMemsetAsync(t->d_ticket + slot, 0, sizeof(unsigned int), c.stream));
     BXG_CUDA(cudaMemsetAsync(t->d_result + 2 * slot, 0, 2 * sizeof(long long), c.stream));
-    size_t smem = find_smem_bytes(t);
+    size_t smem = find_smem_bytes(t, PROBE);
     static bool attr_set = false;
     if (!attr_set) {
         BXG_CUDA(cudaFuncSetAttribute(k_find_fused<PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -1227,7 +1380,8 @@ static int launch_fused(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
     switch (find_probe()) {
         case 0: return launch_fused_as<0>(t, dqt, dqs, dqe, n, q0, slot, tile0);
         case 1: return launch_fused_as<1>(t, dqt, dqs, dqe, n, q0, slot, tile0);
-        default: return launch_fused_as<2>(t, dqt, dqs, dqe, n, q0, slot, tile0);
+        case 2: return launch_fused_as<2>(t, dqt, dqs, dqe, n, q0, slot, tile0);
+        default: return launch_fused_as<3>(t, dqt, dqs, dqe, n, q0, slot, tile0);
     }
 }
 
@@ -1408,19 +1562,15 @@ struct SmallQueries {
     int32_t t[SMALL_Q], qs[SMALL_Q], qe[SMALL_Q];
 };
 
+// out_off layout (mapped pinned host memory): [0..SMALL_Q] offsets, [SMALL_Q+1] overflow flag, [SMALL_Q+2] completion
+// sequence number -- written LAST, after a system-scope fence, so the host can spin on it instead of paying a
+// cudaStreamSynchronize (the kernel's few PCIe writes are the whole result).
 __global__ void __launch_bounds__(32)
-k_find_small(IndexView ix, SmallQueries a, int nq, long long *__restrict__ out_off, int32_t *__restrict__ out_hits) {
-    // the S splitters go to shared memory first (one coalesced sweep by the warp): the 12 dependent steps of the
-    // splitter search then cost shared-memory latency instead of 12 L2 round trips.  PM splitters are only needed by
-    // the rare fallback of the probe search and are read from global memory there.
-    __shared__ __align__(16) int32_t s_sp[MAX_SPLIT];
+k_find_small(IndexView ix, SmallQueries a, int nq, long long seq, long long *__restrict__ out_off,
+             int32_t *__restrict__ out_hits) {
+    // direct addressing (search_walk_grid): cell record -> S sector -> E sectors, no shared-memory staging at all; the
+    // tree directory entries come straight from L2 (one lane per query, up to 32 queries)
     const int q = threadIdx.x;
-    {
-        const int4 *src = reinterpret_cast<const int4 *>(ix.spS);
-        int4 *dst = reinterpret_cast<int4 *>(s_sp);
-        for (int i = q; i < ix.nsplit_pad / 4; i += 32) dst[i] = __ldg(src + i);
-        __syncwarp();
-    }
     uint32_t lo = 0, hi = 0;
     int32_t qs = 0;
     int c = 0;
@@ -1429,8 +1579,10 @@ k_find_small(IndexView ix, SmallQueries a, int nq, long long *__restrict__ out_o
         qs = a.qs[q];
         if (t >= 0 && t < ix.ntrees) {
             const uint32_t seg_lo = (uint32_t)ix.toff[t], seg_hi = (uint32_t)ix.toff[t + 1];
-            bxs::search_walk_probe8(ix.QS, ix.QP, ix.n8, (const int32_t *)s_sp, ix.spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E,
-                                    ix.M, ix.nlev, Ld8(), Ld8(), Ld1(), hi, lo, [&](uint32_t, unsigned m) { c += __popc(m); });
+            const bxs::GridDir gd = reinterpret_cast<const bxs::GridDir *>(ix.dir + ix.dir_grid_off)[t];
+            bxs::search_walk_grid(ix.G, gd, ix.S, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev,
+                                  [](const bxs::GridRec *p) { return *p; }, Ld8(), Ld1(), hi, lo,
+                                  [&](uint32_t, unsigned m) { c += __popc(m); });
         }
     }
     int incl = c;
@@ -1444,23 +1596,45 @@ k_find_small(IndexView ix, SmallQueries a, int nq, long long *__restrict__ out_o
         out_off[nq] = total;
         out_off[SMALL_Q + 1] = total > SMALL_CAP;             // overflow: the host re-runs the general path
     }
-    if (total > SMALL_CAP || c == 0) return;
-    int32_t *dst = out_hits + (incl - c);
-    bxs::walk_hits_halves(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld8(), Ld1(), [&](uint32_t k0, unsigned m) {
-        bxs::PtrSink out{dst};
-        bxs::emit_group_halves_to(ix.I, k0, m, out, Ld8());
-        dst = out.p;
-    });
+    if (total <= SMALL_CAP && c > 0) {
+        int32_t *dst = out_hits + (incl - c);
+        bxs::walk_hits_halves(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld8(), Ld1(), [&](uint32_t k0, unsigned m) {
+            bxs::PtrSink out{dst};
+            bxs::emit_group_halves_to(ix.I, k0, m, out, Ld8());
+            dst = out.p;
+        });
+    }
+    __threadfence_system();                                   // every lane's result writes before the completion word
+    __syncwarp();
+    if (q == 0) *(volatile long long *)(out_off + SMALL_Q + 2) = seq;
+}
+
+// wait for the completion word of a small launch: spin on the mapped host word (the kernel finishes in a few
+// microseconds); if it does not show up quickly fall back to a stream synchronise, which also surfaces launch errors
+static int wait_small(bxg_itree *t, long long seq) {
+    volatile long long *flag = (volatile long long *)(t->m_off + SMALL_Q + 2);
+    for (int spin = 0; spin < 200000; spin++) {
+        if (*flag == seq) return BXG_OK;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    BXG_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (*flag != seq) return set_error(BXG_ERR_CUDA, "small find kernel did not complete");
+    return BXG_OK;
 }
 
 int bxg_itree_find_small(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int32_t nq,
                          const int64_t **offsets, const int32_t **hits, int64_t *total) {
     if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
     if (nq < 0 || nq > SMALL_Q) return set_error(BXG_ERR_ARG, "bxg_itree_find_small takes 0..%d queries", SMALL_Q);
-    Context &c = ctx();
     if (!t->m_off) {
-        BXG_CUDA(cudaHostAlloc((void **)&t->m_off, (SMALL_Q + 2) * sizeof(long long), cudaHostAllocMapped));
+        BXG_CUDA(cudaHostAlloc((void **)&t->m_off, (SMALL_Q + 3) * sizeof(long long), cudaHostAllocMapped));
         BXG_CUDA(cudaHostAlloc((void **)&t->m_hits, (size_t)SMALL_CAP * 4, cudaHostAllocMapped));
+        BXG_CUDA(cudaHostGetDevicePointer((void **)&t->md_off, t->m_off, 0));
+        BXG_CUDA(cudaHostGetDevicePointer((void **)&t->md_hits, t->m_hits, 0));
+        t->m_off[SMALL_Q + 2] = 0;
+        t->m_seq = 0;
     }
     if (nq == 0 || t->n == 0) {
         for (int q = 0; q <= nq; q++) t->m_off[q] = 0;
@@ -1471,12 +1645,9 @@ int bxg_itree_find_small(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs
             a.qs[q] = qs[q];
             a.qe[q] = qe[q];
         }
-        long long *d_off;
-        int32_t *d_hits;
-        BXG_CUDA(cudaHostGetDevicePointer((void **)&d_off, t->m_off, 0));
-        BXG_CUDA(cudaHostGetDevicePointer((void **)&d_hits, t->m_hits, 0));
-        BXG_LAUNCH(k_find_small, 1, 32, 0, t->view(), a, (int)nq, d_off, d_hits);
-        BXG_CUDA(cudaStreamSynchronize(c.stream));
+        const long long seq = ++t->m_seq;
+        BXG_LAUNCH(k_find_small, 1, 32, 0, t->view(), a, (int)nq, seq, t->md_off, t->md_hits);
+        BXG_TRY(wait_small(t, seq));
         if (t->m_off[SMALL_Q + 1])                   // more than SMALL_CAP hits: the general path has no such limit
             return bxg_itree_find_host(t, qtree, qs, qe, nq, offsets, hits, total);
     }
@@ -1485,6 +1656,15 @@ int bxg_itree_find_small(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs
     if (hits) *hits = t->m_hits;
     if (total) *total = t->m_off[nq];
     return BXG_OK;
+}
+
+// The scalar IntervalTree.find(start, end) (intersection.pyx:400-406) with the thinnest possible call: plain integers in,
+// the number of hits (>= 0) or a negative status out; *hits points into the index's mapped result buffer.
+int64_t bxg_itree_find1(bxg_itree_t *t, int32_t tree, int32_t start, int32_t end, const int32_t **hits) {
+    const int64_t *off = nullptr;
+    int64_t total = 0;
+    const int rc = bxg_itree_find_small(t, &tree, &start, &end, 1, &off, hits, &total);
+    return rc == BXG_OK ? total : (int64_t)rc;
 }
 
 int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq, int loc,

@@ -567,6 +567,78 @@ BXG_HD void search_walk_probe8(const int32_t *const *QS, const int32_t *const *Q
     walk_hits_halves(E, M, nlev, lo, hi, qs, ld8, ld, f);
 }
 
+// ---- fourth form: direct addressing ------------------------------------------------------------------------------
+//
+// The three forms above SEARCH for hi: splitters in shared memory, then 3-4 dependent single-sector rounds.  A count
+// kernel bound by dependent sector reads wants neither.  Here every tree carries a uniform grid over its start
+// coordinates -- cell c covers [base + (c << shift), base + ((c + 1) << shift)), 2-4 items per cell on average -- and per
+// cell one 8-byte record
+//     G[c].x = first k with S[k]  >= cell_start(c)          (where the candidates of a query ENDING in this cell stop)
+//     G[c].y = first k with PM[k] >  cell_start(c)          (where the hits of a query STARTING in this cell can begin)
+// so that     hi in [G[ce].x, G[ce + 1].x]   for ce = cell(qe)   -- resolved by the one or two S sectors of that cell,
+//             lo >= G[cs].y                  for cs = cell(qs)   -- a coarse start, the walk masks the rest (E <= qs).
+// Dependent chain per query: cell record(s) -> S sector -> E sectors: 3 rounds instead of 5, ~5.5 sectors instead of
+// 7.4, and no shared-memory table at all.  Any distribution stays correct: a crowded cell falls back to a binary search
+// inside [G[ce].x, G[ce+1].x], a long interval in front only lengthens the walk (which skips through M[]).
+struct GridDir {
+    int32_t base;        // smallest start of the tree
+    int32_t shift;       // cell width = 1 << shift
+    uint32_t ncells;     // cells 0 .. ncells (ncells + 1 records; record ncells is the end sentinel)
+    uint32_t coff;       // index of the tree's record 0 in G
+};
+struct GridRec {
+    uint32_t x, y;
+};
+
+// cell of coordinate q (q > base), clamped to ncells
+BXG_HD uint32_t grid_cell(const GridDir &d, int32_t q) {
+    const uint32_t c = ((uint32_t)q - (uint32_t)d.base) >> d.shift;
+    return c < d.ncells ? c : d.ncells;
+}
+
+template <typename LDR, typename LD8, typename LD, typename F>
+BXG_HD void search_walk_grid(const GridRec *G, const GridDir &d, const int32_t *S, uint32_t seg_lo, uint32_t seg_hi,
+                             int32_t qe, int32_t qs, const int32_t *E, const int32_t *const *M, int nlev, const LDR &ldr,
+                             const LD8 &ld8, const LD &ld, uint32_t &hi_out, uint32_t &lo_out, F &&f) {
+    hi_out = lo_out = seg_hi;
+    if (seg_lo >= seg_hi) return;
+    if (qe <= d.base) {                                // nothing starts before qe
+        hi_out = lo_out = seg_lo;
+        return;
+    }
+    const GridRec *g = G + d.coff;
+    const uint32_t ce = grid_cell(d, qe);
+    uint32_t a, b, lo_c = seg_lo;
+    {
+        const GridRec r0 = ldr(g + ce);
+        a = r0.x;
+        b = ce < d.ncells ? ldr(g + ce + 1).x : seg_hi;
+        if (qs >= d.base) {
+            const uint32_t cs = grid_cell(d, qs);
+            lo_c = cs == ce ? r0.y : ldr(g + cs).y;
+        }
+    }
+    // hi = a + #{k in [a,b) : S[k] < qe}; S is sorted inside the segment, so those form a prefix of [a,b)
+    uint32_t hi = a;
+    if (b > a) {
+        const uint32_t s0 = a & ~7u, s1 = (b - 1u) & ~7u;
+        if (s1 - s0 <= 8u) {
+            unsigned m = sector_mask<false>(S + s0, qe, ld8);
+            if (s1 != s0) m |= sector_mask<false>(S + s1, qe, ld8) << 8;
+            m &= ~0u << (a - s0);
+            if (b - s0 < 32u) m &= (1u << (b - s0)) - 1u;
+            hi = a + (uint32_t)popc32(m);
+        } else {
+            Win w{a, b};
+            hi = finish_binary<false>(S, w, qe, ld);
+        }
+    }
+    hi_out = hi;
+    const uint32_t lo = lo_c < hi ? lo_c : hi;
+    lo_out = lo;
+    walk_hits_halves(E, M, nlev, lo, hi, qs, ld8, ld, f);
+}
+
 // Write the item ids of the hits of one 16-item group: the whole aligned group of I is fetched with four 16-byte
 // loads issued back to back (one 64-byte line), THEN the selected ids are stored -- a load per hit interleaved with
 // the stores would serialise on every store (the compiler must assume hits[] may alias I[]).

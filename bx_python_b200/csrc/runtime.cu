@@ -58,6 +58,20 @@ int stage_in(int slot, const void *src, size_t bytes, int loc, const void **dptr
     return BXG_OK;
 }
 
+int zc_wait(long long seq) {
+    Context &c = ctx();
+    volatile long long *flag = (volatile long long *)(c.zc + ZC_FLAG_OFFSET);
+    for (int spin = 0; spin < 200000; spin++) {
+        if (*flag == seq) return BXG_OK;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    BXG_CUDA(cudaStreamSynchronize(c.stream));          // slow kernel or a launch error: let the runtime tell
+    if (*flag != seq) return set_error(BXG_ERR_CUDA, "scalar-call kernel did not complete");
+    return BXG_OK;
+}
+
 // ---- per-kernel event profiler ------------------------------------------------------------------------------------
 struct ProfRec {
     const char *name;
@@ -134,6 +148,7 @@ int bxg_init(int device) {
         cudaGetLastError();                    // no mapped memory on this platform: scalar calls use the staged path
         c.zc = c.zc_dev = nullptr;
     }
+    if (c.zc) memset(c.zc, 0, 4096);
     c.device = device;
     c.launches = 0;
     return BXG_OK;

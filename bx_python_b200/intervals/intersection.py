@@ -142,12 +142,14 @@ class _DeviceIndex:
         """One query through the low-latency path (bxg_itree_find_small): -> list of item indices."""
         a = self._one
         if a is None:
-            a = self._one = ((C.c_int32 * 1)(), (C.c_int32 * 1)(), (C.c_int32 * 1)(), C.c_void_p(), C.c_void_p(), C.c_int64())
-            self._one_fn = _lib.lib().bxg_itree_find_small
-        a[0][0], a[1][0], a[2][0] = tree, start, end
-        check(self._one_fn(self._h, a[0], a[1], a[2], 1, C.byref(a[3]), C.byref(a[4]), C.byref(a[5])))
-        n = a[5].value
-        return (C.c_int32 * n).from_address(a[4].value)[:] if n else []
+            p = C.c_void_p()
+            a = self._one = (p, C.byref(p), _lib.lib().bxg_itree_find1)
+        n = a[2](self._h, tree, start, end, a[1])
+        if n <= 0:
+            if n < 0:
+                check(int(n))
+            return []
+        return (C.c_int32 * n).from_address(a[0].value)[:]
 
     def count(self, qtree, qs, qe):
         out = np.empty(len(qs), np.int32)
@@ -174,10 +176,17 @@ class _DeviceIndex:
 class IntervalTree:
     """intersection.pyx:325-485 -- same methods, device-resident index."""
 
+    # Items inserted since the last device build stay in a small host-side tail: the scalar `find` answers them by a
+    # direct scan and merges them into the device hits at their in-order position, so the reference idiom of interleaved
+    # insert / find (scripts/maf_drop_overlapping-style loops: `if not tree.find(s, e): tree.insert(s, e)`) costs one small
+    # launch per find and one index build per TAIL_MAX inserts instead of one build per find.
+    TAIL_MAX = 1024
+
     def __init__(self):
         self._starts, self._ends, self._values = [], [], []
         self._index = None
         self._dirty = False
+        self._built = 0                    # items the device index holds (a prefix of the lists)
 
     # ---- position based interface --------------------------------------------------------------------------
     def insert(self, start, end, value=None):
@@ -198,22 +207,39 @@ class IntervalTree:
         self._values.extend(values if values is not None else range(base, base + len(s)))
         self._dirty = True
 
-    def _ensure(self):
+    def _ensure(self, allow_tail=False):
+        """The device index over all items -- or, with allow_tail, over all but a tail of at most TAIL_MAX recent ones."""
         if self._index is None:
             self._index = _DeviceIndex()
             self._dirty = True
-        if self._dirty:
+            self._built = 0
+        if self._dirty and not (allow_tail and self._built and len(self._starts) - self._built <= self.TAIL_MAX):
             self._s = np.asarray(self._starts, np.int32)
             self._e = np.asarray(self._ends, np.int32)
             self._index.build(None, self._s, self._e, 1)
+            self._built = len(self._starts)
             self._dirty = False
         return self._index
+
+    def _order_key(self, i):
+        """Position of item i in the reference treap's in-order sequence (intersection.pyx:110-116): by start, items
+        with end <= start first and in reverse insertion order, the others in insertion order."""
+        s = self._starts[i]
+        return (s, 1, i) if self._ends[i] > s else (s, 0, -i)
 
     def find(self, start, end):
         """Return a sorted list of all intervals overlapping [start,end)."""
         if not self._starts:
             return []
-        hits = self._ensure().find_one(_c_int(start), _c_int(end))
+        start, end = _c_int(start), _c_int(end)
+        hits = self._ensure(allow_tail=True).find_one(start, end)
+        built, n = self._built, len(self._starts)
+        if built < n:                      # recent inserts the device index does not hold yet
+            ss, ee = self._starts, self._ends
+            tail = [i for i in range(built, n) if ee[i] > start and ss[i] < end]
+            if tail:
+                key = self._order_key
+                hits = sorted(list(hits) + tail, key=key) if hits else sorted(tail, key=key)
         v = self._values
         return [v[i] for i in hits]
 

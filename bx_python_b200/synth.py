@@ -203,6 +203,37 @@ def exon_lists(seed):
     return one(), one()
 
 
+def ops_case(seed, n=300):
+    """Three BED line lists + a lens dict for the interval operations (intersect / subtract / merge / complement /
+    coverage / base_coverage): overlapping intervals, zero-length ones, a few with end < start (dropped by the readers), a
+    few beyond the chromosome length (dropped by BitsetSafeReaderWrapper), a chromosome without a length (MAX-sized bit
+    set) and one that only the primary file has."""
+    rng = np.random.default_rng(6500 + seed)
+    lens = {"chr1": 30000, "chr2": 12000}
+
+    def bed(m, names, tag, at_end=False):
+        out = ["# a comment line"]
+        for i in range(m):
+            c = names[int(rng.integers(0, len(names)))]
+            L = lens.get(c, 20000)
+            s = int(rng.integers(0, L - 200))
+            e = s + int(rng.integers(0, 200))
+            r = rng.random()
+            if r < 0.03:
+                s, e = e + 5, s                       # end < start
+            elif r < 0.06:
+                e = L + int(rng.integers(1, 50))      # runs past the chromosome
+            elif r < 0.08 and at_end:
+                s = e = L                             # empty interval exactly at the end: fine as a primary line, but as a
+                                                      # bit-set line the reference dies with set_range's IndexError
+            out.append(f"{c}\t{s}\t{e}\t{tag}{i}\t0\t{'+-'[int(rng.integers(0, 2))]}")
+        return out
+    primary = bed(n, ["chr1", "chr2", "chrX", "chrOnlyPrimary"], "p", at_end=True)
+    second = bed(n, ["chr1", "chr2", "chrX"], "s")
+    third = bed(n // 2, ["chr1", "chrX", "chrOnlyThird"], "t")
+    return primary, second, third, lens
+
+
 # ---- score sources / summary / join (SURVEY 8f-4) -------------------------------------------------------------------
 def wiggle_text(seed, n=6000, chroms=("chr1", "chr2")):
     """A wiggle file mixing fixedStep / variableStep blocks (with and without span), a leading bedGraph-style

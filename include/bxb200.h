@@ -148,6 +148,14 @@ int bxg_bits_next(const bxg_bits_t *b, int32_t start, int32_t end, int val, int3
 int bxg_bits_runs_count(bxg_bits_t *b, int64_t *nruns);
 int bxg_bits_runs_fetch(bxg_bits_t *b, int32_t *starts, int32_t *ends, int64_t nruns);
 
+/* The generators bits_set_in_range / bits_clear_in_range (lib/bx/intervals/operations/__init__.py:10-33) for n ranges at
+ * once: the maximal runs of bits == val inside [start[i], end[i]) (clipped to [0, size)), in order -- the `pieces` that
+ * operations/intersect.py:62-70 / subtract.py:66-72 emit per interval.  offsets (HOST, n+1 entries) receives the CSR
+ * offsets of the runs of each range; the runs stay on the device until ..._fetch copies them to host arrays. */
+int bxg_bits_runs_in_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *end, int64_t n, int val, int loc,
+                            int64_t *offsets, int64_t *total);
+int bxg_bits_runs_in_ranges_fetch(bxg_bits_t *b, int32_t *starts, int32_t *ends, int64_t total);
+
 /* test / interchange helpers */
 int bxg_bits_states(const bxg_bits_t *b, uint8_t *out /* nbins */);
 int bxg_bits_export_words(const bxg_bits_t *b, uint64_t *out /* ceil(size/64) */);
@@ -206,10 +214,14 @@ int bxg_itree_find_host32(bxg_itree_t *t, const int32_t *qtree, const int32_t *q
  * back to bxg_itree_find_host when the queries have more than 65536 hits in total. */
 int bxg_itree_find_small(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int32_t nq,
                          const int64_t **offsets, const int32_t **hits, int64_t *total);
+/* One query, plain integers in: returns the number of hits (>= 0) or a negative status; *hits points into the index's
+ * mapped result buffer (valid until its next find).  The thinnest form of IntervalTree.find (intersection.pyx:400-406). */
+int64_t bxg_itree_find1(bxg_itree_t *t, int32_t tree, int32_t start, int32_t end, const int32_t **hits);
 int bxg_itree_result_dev(const bxg_itree_t *t, const int64_t **d_offsets, const int32_t **d_hits, int64_t *nq,
                          int64_t *total);
 /* len(find(...)) only (scripts/bed_count_overlapping.py:27-33): int32 counts[nq] written to `counts` (host or device
- * per loc); *total (may be NULL) receives the sum. */
+ * per loc); *total (may be NULL) receives the sum.  Host arrays of two or more pipeline chunks are copied in, counted and
+ * copied out chunk by chunk on three streams (16 bytes per query over PCIe instead of the ~42 of the full CSR). */
 int bxg_itree_count(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe,
                     int64_t nq, int loc, int32_t *counts, int64_t *total);
 

@@ -316,8 +316,83 @@ def golden_join():
     print("join.json:", len(cases), "cases;", sum(len(c["rows"]) for c in cases), "rows")
 
 
+def golden_operations():
+    """The reference's own interval operations (lib/bx/intervals/operations/*.py over NiceReaderWrapper readers) on
+    synth.ops_case inputs -- what bx_python_b200.intervals.operations.arrays must reproduce row for row."""
+    _ref_pure_python()
+    from bx.intervals.io import GenomicInterval, NiceReaderWrapper
+    from bx.intervals.operations.base_coverage import base_coverage
+    from bx.intervals.operations.complement import complement
+    from bx.intervals.operations.coverage import coverage
+    from bx.intervals.operations.intersect import intersect
+    from bx.intervals.operations.merge import merge
+    from bx.intervals.operations.subtract import subtract
+
+    def rd(lines):
+        return NiceReaderWrapper(iter([ln + "\n" for ln in lines]), chrom_col=0, start_col=1, end_col=2, strand_col=5,
+                                 fix_strand=True)
+
+    def rows(gen):
+        out = []
+        for r in gen:
+            if isinstance(r, GenomicInterval):
+                out.append([str(f).rstrip("\n") for f in r.fields])
+            elif isinstance(r, list):
+                out.append([str(f) for f in r])
+        return out
+    cases = []
+    for seed in range(4):
+        p, s2, s3, lens = synth.ops_case(seed)
+        c = {"seed": seed}
+        for pieces in (True, False):
+            for mincols in (1, 40):
+                key = f"pieces{int(pieces)}_min{mincols}"
+                c["intersect_" + key] = rows(intersect([rd(p), rd(s2)], mincols=mincols, pieces=pieces, lens=lens))
+                c["subtract_" + key] = rows(subtract([rd(p), rd(s2)], mincols=mincols, pieces=pieces, lens=lens))
+        c["intersect3"] = rows(intersect([rd(p), rd(s2), rd(s3)], lens=lens))
+        c["subtract3"] = rows(subtract([rd(p), rd(s2), rd(s3)], lens=lens))
+        c["merge"] = rows(merge(rd(p)))
+        c["complement"] = rows(complement(rd(s2), lens))
+        c["coverage"] = rows(coverage([rd(p), rd(s2)]))
+        c["coverage3"] = rows(coverage([rd(p), rd(s2), rd(s3)]))
+        c["base_coverage"] = int(base_coverage(rd(p)))
+        cases.append(c)
+    json.dump(cases, open(os.path.join(HERE, "operations.json"), "w"))
+    print("operations.json:", {k: (len(v) if isinstance(v, list) else v) for k, v in cases[0].items()})
+
+
+def golden_scripts():
+    """stdout of the reference's scripts (staged unmodified in oracle/_ref/scripts) run on the compiled reference over
+    the inputs of tests/dropin.py:make_inputs -- what the drop-in tests compare the shadowed runs with."""
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import dropin
+    out = {"inputs_seed": 0, "runs": []}
+    with tempfile.TemporaryDirectory() as d:
+        dropin.make_inputs(d, 0)
+        for name, argv, _ in dropin.SCRIPT_RUNS:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin.py"), "--impl", "reference", "script",
+                                name, d] + argv, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, (name, argv, r.stderr[-2000:])
+            out["runs"].append({"script": name, "argv": argv, "stdout": r.stdout.splitlines()})
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin.py"), "--impl", "reference", "unittests"],
+                           capture_output=True, text=True, timeout=600)
+        res = json.loads(r.stdout.strip().splitlines()[-1])
+        assert res["rc"] == 0 and res["failed"] == 0
+        out["unittests_passed"] = res["passed"]
+    json.dump(out, open(os.path.join(HERE, "scripts.json"), "w"), indent=0)
+    print("scripts.json:", [(r["script"], len(r["stdout"])) for r in out["runs"]], "unit tests:", out["unittests_passed"])
+
+
 if __name__ == "__main__":
     orc.build_ref(REFERENCE)
+    if sys.argv[1:] == ["scripts"]:
+        golden_scripts()
+        sys.exit(0)
+    if sys.argv[1:] == ["operations"]:
+        orc.ref_modules()
+        golden_operations()
+        sys.exit(0)
     bs, ix = orc.ref_modules()
     golden_find(ix)
     golden_neighbors(ix)
@@ -327,3 +402,5 @@ if __name__ == "__main__":
     golden_scores()
     golden_summarize()
     golden_join()
+    golden_scripts()
+    golden_operations()

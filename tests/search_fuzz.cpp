@@ -132,6 +132,30 @@ int main(int argc, char **argv) {
             KS[0] = SPi.data();
             KP[0] = SPi.data() + 16;
         }
+        // direct-address grid, built exactly as csrc/itree.cu does (k_tree_extent / host geometry / k_build_grid)
+        const int dens = trial % 3;                       // 1, 2-4 or 4-8 items per cell
+        std::vector<bxs::GridDir> gd(ntrees);
+        std::vector<bxs::GridRec> G;
+        for (int t = 0; t < ntrees; t++) {
+            const long nt = (long)toff[t + 1] - (long)toff[t];
+            const unsigned long long span = nt > 0 ? (unsigned long long)((long long)S[toff[t + 1] - 1] - (long long)S[toff[t]]) : 0ull;
+            const unsigned long long limit = (unsigned long long)std::max<long>(1, nt >> dens);
+            int gshift = 0;
+            while ((span >> gshift) + 1 > limit) gshift++;
+            gd[t].base = nt > 0 ? S[toff[t]] : 0;
+            gd[t].shift = gshift;
+            gd[t].ncells = nt > 0 ? (uint32_t)((span >> gshift) + 1) : 0u;
+            gd[t].coff = (uint32_t)G.size();
+            for (uint32_t c = 0; c <= gd[t].ncells; c++) {
+                const long long v = (long long)gd[t].base + ((long long)c << gshift);
+                const auto less = [](int32_t e, long long key) { return (long long)e < key; };
+                const auto leq = [](long long key, int32_t e) { return key < (long long)e; };
+                const uint32_t x = (uint32_t)(std::lower_bound(S.begin() + toff[t], S.begin() + toff[t + 1], v, less) - S.begin());
+                const uint32_t y = (uint32_t)(std::upper_bound(PM.begin() + toff[t], PM.begin() + toff[t + 1], v, leq) - PM.begin());
+                G.push_back(bxs::GridRec{x, y});
+            }
+        }
+        auto ldr = [](const bxs::GridRec *p) { return *p; };
         for (int q = 0; q < 150; q++) {
             const int t = (int)(rnd() % (uint32_t)ntrees);
             const int32_t qs = shifted((long long)(rnd() % (uint32_t)(range + 40)) - 70);
@@ -216,6 +240,21 @@ int main(int argc, char **argv) {
                 if (hi4 != ehi || lo4 > std::min(elo, ehi) || lo4 < toff[t] || got4 != want3) {
                     printf("SEARCH_WALK_PROBE8 MISMATCH trial %d n=%d n8=%d shift=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u got=%zu want=%zu\n",
                            trial, n, n8, shift, toff[t], toff[t + 1], qs, qe, hi4, ehi, lo4, elo, got4.size(), want3.size());
+                    return 1;
+                }
+                std::vector<uint32_t> got5;
+                uint32_t hi5, lo5;
+                bxs::search_walk_grid(G.data(), gd[t], S.data(), toff[t], toff[t + 1], qe, qs, E.data(), Mp.data(),
+                                      (int)Mp.size(), ldr, ld8, ld, hi5, lo5, [&](uint32_t k0, unsigned mask) {
+                                          while (mask) {
+                                              int b = bxs::ffs32(mask) - 1;
+                                              mask &= mask - 1;
+                                              got5.push_back(k0 + b);
+                                          }
+                                      });
+                if (hi5 != ehi || lo5 > std::min(elo, ehi) || lo5 < toff[t] || got5 != want3) {
+                    printf("SEARCH_WALK_GRID MISMATCH trial %d n=%d dens=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u got=%zu want=%zu\n",
+                           trial, n, dens, toff[t], toff[t + 1], qs, qe, hi5, ehi, lo5, elo, got5.size(), want3.size());
                     return 1;
                 }
                 if (hi2 != ehi || lo2 > std::min(elo, ehi) || got2 != want) {
