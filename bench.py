@@ -971,12 +971,12 @@ def leg_bed_intersect(comm, peak, args):
         ok &= all(int(per[c, 0]) == gold[c]["overlapping"] and int(per[c, 1]) == gold[c]["sum_counts"] and
                   int(covered[c]) == gold[c]["covered"] for c in range(N_CHROM))
     ok = all_ok(comm, ok)
-    # ---- per-kernel device times on rank 0 (separate pass)
-    prof = None
+    # ---- per-kernel device times on rank 0 (separate pass; every rank runs it -- the step contains a collective)
     if rank == 0:
         _lib.profile_enable(True)
-        step()
-        prof = _lib.profile_report()
+    step()
+    prof = _lib.profile_report() if rank == 0 else None
+    if rank == 0:
         _lib.profile_enable(False)
     words_written = int(comm.allreduce_sum_i64(np.array(
         [sum(int(np.sum((f2[c][1] - 1) // 64 - f2[c][0] // 64 + 1)) for c in mine)]))[0])
@@ -1071,11 +1071,11 @@ def leg_aggregate(comm, peak, args):
     ok = all_ok(comm, ok)
     bases = int(comm.allreduce_sum_i64(np.array([int(np.sum(we.astype(np.int64) - ws))]))[0])
     nw_all = int(comm.allreduce_sum_i64(np.array([nw]))[0])
-    prof = None
-    if rank == 0:
+    if rank == 0:                                   # (every rank runs the profiled step: it contains a collective)
         _lib.profile_enable(True)
-        step()
-        prof = _lib.profile_report()
+    step()
+    prof = _lib.profile_report() if rank == 0 else None
+    if rank == 0:
         _lib.profile_enable(False)
     for h in handles.values():
         L.bxg_scores_free(h)
@@ -1109,14 +1109,29 @@ def bench_scalar_api(db):
     for k in range(n):
         t.find(100000 * k, 100000 * k + 1500)
     find_us = (time.perf_counter() - t0) / n * 1e6
+    # the same calls without the Python class around them: ctypes -> bxg_itree_find1 (launch + completion word) only
+    import ctypes as C
+
+    from bx_python_b200 import _lib
+    fn, h, p = _lib.lib().bxg_itree_find1, t._index._h, C.c_void_p()
+    ref = C.byref(p)
+    t0 = time.perf_counter()
+    for k in range(n):
+        fn(h, 0, 100000 * k, 100000 * k + 1500, ref)
+    find_raw_us = (time.perf_counter() - t0) / n * 1e6
     b = BinnedBitSet(int(synth.HG38_LENS[20]))
-    b.set_range(10, 1000)
+    b.set_ranges(np.arange(0, 40_000_000, 5000), np.full(8000, 700))       # a 700-base run every 5000 bases
     b.count_range(0, 5000)
     t0 = time.perf_counter()
     for k in range(n):
         b.count_range(1000 * k, 1500)
     count_us = (time.perf_counter() - t0) / n * 1e6
-    return {"find_us_per_call": find_us, "count_range_us_per_call": count_us,
+    t0 = time.perf_counter()
+    for k in range(n):
+        b.next_set(1000 * k + 900)                  # the run-extraction idiom: the next run is a few thousand bits away
+    next_us = (time.perf_counter() - t0) / n * 1e6
+    return {"find_us_per_call": find_us, "find1_ctypes_us_per_call": find_raw_us, "count_range_us_per_call": count_us,
+            "next_set_us_per_call": next_us,
             "note": "scalar IntervalTree.find / BinnedBitSet.count_range = one launch + one synchronise each (arguments by value / "
                     "mapped pinned memory, results written by the kernel into mapped pinned memory: no copies); the reference's "
                     "Cython calls take ~1-4 us -- bulk callers should still use the batched methods"}

@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
-        if force or _stale(o, [s] + HEADERS) or (extra and src == "itree.cu"):
+        if force or _stale(o, [s] + HEADERS) or (extra and src in ("itree.cu", "bits.cu")):
             cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             subprocess.check_call(cmd)
         objs.append(o)

@@ -449,10 +449,36 @@ struct PopcSector {
     }
 };
 
+// Random single-sector reads from a working set far larger than L2 (a genome of bitmaps + rank tables): ncu (r02b) shows
+// 264 B of DRAM reads per count_range query for ~4 missed sectors, i.e. 64-byte fetches.  Neither
+// cudaLimitMaxL2FetchGranularity = 32 (no change, r02c) nor loads carrying an L2 evict_first policy (COUNT_L2_HINT=1:
+// 2.69 -> 3.57 ms per 50 M queries, r02d) help, so plain loads stay the default; the switch is kept for A/B runs.
+#ifndef COUNT_L2_HINT
+#define COUNT_L2_HINT 0
+#endif
+#if COUNT_L2_HINT
+__device__ __forceinline__ uint64_t count_policy() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void ld_sector(const uint64_t *p, unsigned long long &a, unsigned long long &b,
+                                          unsigned long long &c, unsigned long long &d) {
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(count_policy()));
+}
+__device__ __forceinline__ uint32_t ld_rank(const uint32_t *p) {
+    uint32_t r;
+    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(count_policy()));
+    return r;
+}
+#else
 __device__ __forceinline__ void ld_sector(const uint64_t *p, unsigned long long &a, unsigned long long &b,
                                           unsigned long long &c, unsigned long long &d) {
     asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
+__device__ __forceinline__ uint32_t ld_rank(const uint32_t *p) { return __ldg(p); }
+#endif
 
 // bits of the 256-bit sector (a,b,c,d) strictly below bit offset o in [1,255]
 __device__ __forceinline__ uint32_t popc_below(unsigned long long a, unsigned long long b, unsigned long long c,
@@ -468,7 +494,7 @@ __device__ __forceinline__ uint32_t popc_below(unsigned long long a, unsigned lo
 
 __device__ __forceinline__ uint32_t rank_at(const uint64_t *__restrict__ words, const uint32_t *__restrict__ rank, uint32_t p) {
     const uint32_t sec = p >> 8, o = p & 255u;
-    uint32_t r = __ldg(rank + sec);
+    uint32_t r = ld_rank(rank + sec);
     if (o) {
         unsigned long long a, b, c, d;
         ld_sector(words + 4 * (size_t)sec, a, b, c, d);

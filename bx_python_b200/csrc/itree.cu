@@ -26,7 +26,9 @@ constexpr int MAX_SPLIT = 4096;        // splitter entries per array (16 KB each
 constexpr int SMEM_TREES = 256;        // toff entries cached in shared memory
 constexpr int FIND_THREADS = 256;
 #ifndef FIND_MIN_CTAS
-#define FIND_MIN_CTAS 6            // co-resident CTAs per SM the find kernels are compiled for (register budget 40):
+#define FIND_MIN_CTAS 7            // co-resident CTAs per SM the find kernels are compiled for (register budget 36; the
+                                   // direct-address search needs 38-40 without a cap and no shared-memory table, so occupancy is
+                                   // the registers' to give: 6 / 7 / 8 CTAs -> count 0.312 / 0.302 / 0.302 ms, profiles/r02c).  History:
                                    // since the 8-ary probe search (7.4 sectors per query) the count kernel is bound by
                                    // latency, not by L1 wavefronts, and occupancy pays even with a few spills:
                                    // 4 / 5 / 6 CTAs -> 0.507 / 0.457 / 0.431 ms (profiles/r01s, r01t); shared memory
@@ -48,6 +50,7 @@ struct IndexView {
     const int32_t *M[MAX_LEVELS];
     const int64_t *toff;
     const bxs::GridRec *G;       // direct-address grid records (all trees, see itree_search.cuh: search_walk_grid)
+    const bxs::GridRec16 *G16;   // the same with the cell's starts packed in (search_walk_grid16)
     const unsigned char *dir;    // tree directory: toff[ntrees+1] (int64), padded to 16 B, then GridDir[ntrees]
     uint32_t dir_bytes, dir_grid_off;
     const int32_t *spS, *spPM;   // contiguous: spS[nsplit_pad] then spPM[nsplit_pad]
@@ -65,6 +68,7 @@ struct bxg_itree {
     int nlev = 0;
     int64_t *toff = nullptr;
     bxs::GridRec *G = nullptr;            // grid records of all trees
+    bxs::GridRec16 *G16 = nullptr;
     unsigned char *dir = nullptr;         // [toff | pad | GridDir x ntrees], one TMA bulk copy per CTA
     uint32_t dir_bytes = 0, dir_grid_off = 0;
     int64_t ncells_total = 0;
@@ -114,7 +118,7 @@ struct bxg_itree {
         v.QS[0] = S; v.QP[0] = PM; v.n8 = n8;
         v.KS[0] = S; v.KP[0] = PM; v.WE = E; v.WI = I; v.mul = 1;
         v.toff = toff; v.spS = split; v.spPM = split + nsplit_pad;
-        v.G = G; v.dir = dir; v.dir_bytes = dir_bytes; v.dir_grid_off = dir_grid_off;
+        v.G = G; v.G16 = G16; v.dir = dir; v.dir_bytes = dir_bytes; v.dir_grid_off = dir_grid_off;
         v.n = (uint32_t)n; v.ntrees = ntrees; v.nlev = nlev; v.nsplit = nsplit; v.nsplit_pad = nsplit_pad; v.shift = shift;
         return v;
     }
@@ -248,6 +252,32 @@ __global__ void k_build_grid(const int32_t *__restrict__ S, const int32_t *__res
             if ((int64_t)PM[m] <= v) l = m + 1; else h = m;
         }
         G[r] = bxs::GridRec{x, (uint32_t)l};
+    }
+}
+
+// 16-byte records: (x, y) of G plus the cell's item count and the offsets of its first 56 / shift items (search_walk_grid16)
+__global__ void k_build_grid16(const int32_t *__restrict__ S, const bxs::GridRec *__restrict__ G, const bxs::GridDir *__restrict__ gd,
+                               int ntrees, int64_t nrec, bxs::GridRec16 *__restrict__ G16) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrec; r += stride) {
+        int lo = 0, hi = ntrees - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int64_t)gd[mid].coff <= r) lo = mid; else hi = mid - 1;
+        }
+        const bxs::GridDir d = gd[lo];
+        const int64_t c = r - d.coff;
+        const bxs::GridRec g = G[r];
+        unsigned long long p = 0;
+        if (c < (int64_t)d.ncells) {
+            const uint32_t cnt = G[r + 1].x - g.x;
+            p = cnt < 255u ? cnt : 255u;
+            const uint32_t kmax = (uint32_t)bxs::grid16_fields(d.shift), stored = cnt < kmax ? cnt : kmax;
+            const int64_t v = (int64_t)d.base + (c << d.shift);
+            for (uint32_t i = 0; i < stored; i++)
+                p |= (unsigned long long)((int64_t)S[g.x + i] - v) << (8 + i * d.shift);
+        }
+        G16[r] = bxs::GridRec16{g.x, g.y, (uint32_t)p, (uint32_t)(p >> 32)};
     }
 }
 
@@ -398,11 +428,26 @@ struct LdRec {
         return r;
     }
 };
+struct LdRec16 {
+    uint64_t pol;
+    __device__ __forceinline__ LdRec16() : pol(l2_keep_policy()) {}
+    __device__ __forceinline__ bxs::GridRec16 operator()(const bxs::GridRec16 *p) const {
+        bxs::GridRec16 r;
+        asm("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.p0), "=r"(r.p1) : "l"(p), "l"(pol));
+        return r;
+    }
+};
 #else
 struct LdRec {
     __device__ __forceinline__ bxs::GridRec operator()(const bxs::GridRec *p) const {
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
         return bxs::GridRec{v.x, v.y};
+    }
+};
+struct LdRec16 {
+    __device__ __forceinline__ bxs::GridRec16 operator()(const bxs::GridRec16 *p) const {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+        return bxs::GridRec16{v.x, v.y, v.z, v.w};
     }
 };
 #endif
@@ -411,7 +456,9 @@ template <int PROBE, typename SP, typename F>
 __device__ __forceinline__ void query_search_walk(const IndexView &ix, const SP &spS, const SP &spPM, const bxs::GridDir *gd,
                                                   uint32_t seg_lo, uint32_t seg_hi, int32_t qe, int32_t qs, uint32_t &hi,
                                                   uint32_t &lo, F &&f) {
-    if (PROBE == 3)
+    if (PROBE == 4)
+        bxs::search_walk_grid16(ix.G16, *gd, ix.S, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdRec16(), LdK8(), Ld1(), hi, lo, f);
+    else if (PROBE == 3)
         bxs::search_walk_grid(ix.G, *gd, ix.S, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdRec(), LdK8(), Ld1(), hi, lo, f);
     else if (PROBE == 2)
         bxs::search_walk_probe8(ix.QS, ix.QP, ix.n8, spS, spPM, ix.shift, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev, LdTop8(),
@@ -501,7 +548,7 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
        unsigned long long *total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemIndex sm;
-    if (!FILL) sm = PROBE == 3 ? stage_dir(ix, smem_raw) : stage_index(ix, smem_raw);
+    if (!FILL) sm = PROBE >= 3 ? stage_dir(ix, smem_raw) : stage_index(ix, smem_raw);
     unsigned long long local = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // Fill only: the inputs of the next grid-stride iteration are loaded at the top of the current one (0.350 -> 0.338 ms).
@@ -523,7 +570,7 @@ k_find(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qtree, 
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
                 // hi: candidates (start < qe) end here; lo: coarse start of the walk (running max end > qs from here on)
-                query_search_walk<PROBE>(ix, sm.spS, sm.spPM, PROBE == 3 ? sm.gdir + t : nullptr, seg_lo, seg_hi, qe, qs, hi, lo, st);
+                query_search_walk<PROBE>(ix, sm.spS, sm.spPM, PROBE >= 3 ? sm.gdir + t : nullptr, seg_lo, seg_hi, qe, qs, hi, lo, st);
             }
             cnt[q] = st.c;                                 // read again right away by the scan: keep it cached
             st_stream_q(lo_ + q, (int32_t)((st.c ? st.base : lo) | (st.overflow ? WALK_AGAIN : 0u)));
@@ -692,7 +739,7 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
     __shared__ typename BS::TempStorage scan_tmp;
     __shared__ unsigned int s_tile;
     __shared__ long long s_base;
-    const SmemIndex sm = PROBE == 3 ? stage_dir(ix, smem_raw) : stage_index(ix, smem_raw);
+    const SmemIndex sm = PROBE >= 3 ? stage_dir(ix, smem_raw) : stage_index(ix, smem_raw);
     const unsigned int ntiles = (unsigned int)((nq + FUSED_THREADS - 1) / FUSED_THREADS);
     const int lane = threadIdx.x & 31;
     while (true) {
@@ -711,7 +758,7 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
             const int32_t t = qtree ? __ldg(qtree + q) : 0;
             if (t >= 0 && t < ix.ntrees) {
                 const uint32_t seg_lo = (uint32_t)sm.toff[t], seg_hi = (uint32_t)sm.toff[t + 1];
-                query_search_walk<PROBE>(ix, sm.spS, sm.spPM, PROBE == 3 ? sm.gdir + t : nullptr, seg_lo, seg_hi, qe, qs, hi, lo, st);
+                query_search_walk<PROBE>(ix, sm.spS, sm.spPM, PROBE >= 3 ? sm.gdir + t : nullptr, seg_lo, seg_hi, qe, qs, hi, lo, st);
                 c = st.c;
             }
         }
@@ -770,8 +817,8 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
 // ------------------------------------------------------------------------------------------------------------------
 static void free_index(bxg_itree *t) {
     cudaFree(t->S); cudaFree(t->E); cudaFree(t->I); cudaFree(t->PM); cudaFree(t->toff); cudaFree(t->split);
-    cudaFree(t->G); cudaFree(t->dir);
-    t->G = nullptr; t->dir = nullptr; t->dir_bytes = t->dir_grid_off = 0; t->ncells_total = 0;
+    cudaFree(t->G); cudaFree(t->G16); cudaFree(t->dir);
+    t->G = nullptr; t->G16 = nullptr; t->dir = nullptr; t->dir_bytes = t->dir_grid_off = 0; t->ncells_total = 0;
     for (int l = 0; l < MAX_LEVELS; l++) { cudaFree(t->M[l]); t->M[l] = nullptr; t->mlen[l] = 0; }
     for (int j = 1; j < MAX_KLEV; j++) { cudaFree(t->KS[j]); cudaFree(t->KP[j]); }
     for (int j = 0; j < MAX_KLEV; j++) t->KS[j] = t->KP[j] = nullptr;
@@ -790,7 +837,7 @@ static void free_index(bxg_itree *t) {
 }
 
 static size_t find_smem_bytes(const bxg_itree *t, int probe) {
-    if (probe == 3) return 16 + (t->ntrees <= SMEM_TREES ? (size_t)t->dir_bytes : 0);
+    if (probe >= 3) return 16 + (t->ntrees <= SMEM_TREES ? (size_t)t->dir_bytes : 0);
     return 16 + (size_t)t->nsplit_pad * 8 + (t->ntrees <= SMEM_TREES ? (size_t)(t->ntrees + 1) * 8 : 0);
 }
 
@@ -812,12 +859,13 @@ static int ensure_query_buffers(bxg_itree *t, int64_t nq) {
     return BXG_OK;
 }
 
-// 3 (default): direct-address grid; 2: 8-ary levels + probe; 1: 16-ary levels + probe; 0: two lock-step searches
+// 4 (default): direct-address grid with packed 16-byte records; 3: 8-byte records + S; 2: 8-ary levels + probe;
+// 1: 16-ary levels + probe; 0: two lock-step searches
 static int find_probe() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("BXB200_FIND_PROBE");
-        v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+        v = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 4;
     }
     return v;
 }
@@ -848,7 +896,8 @@ static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
         case 0: return launch_count_as<0>(t, dqt, dqs, dqe, nq, d_total, q0);
         case 1: return launch_count_as<1>(t, dqt, dqs, dqe, nq, d_total, q0);
         case 2: return launch_count_as<2>(t, dqt, dqs, dqe, nq, d_total, q0);
-        default: return launch_count_as<3>(t, dqt, dqs, dqe, nq, d_total, q0);
+        case 3: return launch_count_as<3>(t, dqt, dqs, dqe, nq, d_total, q0);
+        default: return launch_count_as<4>(t, dqt, dqs, dqe, nq, d_total, q0);
     }
 }
 
@@ -1125,8 +1174,11 @@ int bxg_itree_build(bxg_itree_t *t, const int32_t *tree, const int32_t *start, c
         BUILD_CUDA(cudaMalloc(&t->dir, h_dir.size()));
         BUILD_CUDA(cudaMalloc(&t->G, (size_t)nrec * sizeof(bxs::GridRec)));
         BUILD_CUDA(cudaMemcpyAsync(t->dir, h_dir.data(), h_dir.size(), cudaMemcpyHostToDevice, c.stream));
+        BUILD_CUDA(cudaMalloc(&t->G16, (size_t)nrec * sizeof(bxs::GridRec16)));
         BXG_LAUNCH(k_build_grid, grid_for(cdiv(nrec, 256), 8), 256, 0, t->S, t->PM, t->toff,
                    (const bxs::GridDir *)(t->dir + toff_bytes), (int)ntrees, nrec, t->G);
+        BXG_LAUNCH(k_build_grid16, grid_for(cdiv(nrec, 256), 8), 256, 0, t->S, (const bxs::GridRec *)t->G,
+                   (const bxs::GridDir *)(t->dir + toff_bytes), (int)ntrees, nrec, t->G16);
         BUILD_CUDA(cudaStreamSynchronize(c.stream));     // h_dir is a local
     }
 
@@ -1381,7 +1433,8 @@ static int launch_fused(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
         case 0: return launch_fused_as<0>(t, dqt, dqs, dqe, n, q0, slot, tile0);
         case 1: return launch_fused_as<1>(t, dqt, dqs, dqe, n, q0, slot, tile0);
         case 2: return launch_fused_as<2>(t, dqt, dqs, dqe, n, q0, slot, tile0);
-        default: return launch_fused_as<3>(t, dqt, dqs, dqe, n, q0, slot, tile0);
+        case 3: return launch_fused_as<3>(t, dqt, dqs, dqe, n, q0, slot, tile0);
+        default: return launch_fused_as<4>(t, dqt, dqs, dqe, n, q0, slot, tile0);
     }
 }
 
@@ -1580,9 +1633,9 @@ k_find_small(IndexView ix, SmallQueries a, int nq, long long seq, long long *__r
         if (t >= 0 && t < ix.ntrees) {
             const uint32_t seg_lo = (uint32_t)ix.toff[t], seg_hi = (uint32_t)ix.toff[t + 1];
             const bxs::GridDir gd = reinterpret_cast<const bxs::GridDir *>(ix.dir + ix.dir_grid_off)[t];
-            bxs::search_walk_grid(ix.G, gd, ix.S, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev,
-                                  [](const bxs::GridRec *p) { return *p; }, Ld8(), Ld1(), hi, lo,
-                                  [&](uint32_t, unsigned m) { c += __popc(m); });
+            bxs::search_walk_grid16(ix.G16, gd, ix.S, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev,
+                                    [](const bxs::GridRec16 *p) { return *p; }, Ld8(), Ld1(), hi, lo,
+                                    [&](uint32_t, unsigned m) { c += __popc(m); });
         }
     }
     int incl = c;

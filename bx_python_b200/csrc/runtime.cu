@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <map>
 #include <string>
@@ -139,6 +140,16 @@ int bxg_init(int device) {
         return set_error(BXG_ERR_CUDA, "device %d is sm_%d%d; libbxb200 is built for sm_100a only", device, p.major, p.minor);
     c.sm_count = p.multiProcessorCount;
     c.l2_bytes = p.l2CacheSize;
+    {
+        // The query kernels of this library (find, count_range, set_range) read single 32-byte sectors at random from
+        // working sets larger than L2; the default 64-byte L2 fetch granularity doubles their DRAM traffic (ncu,
+        // profiles/r02b).  BXB200_L2_FETCH=64|128 restores a larger granularity for A/B runs.
+        const char *e = getenv("BXB200_L2_FETCH");
+        const size_t g = e ? (size_t)atoi(e) : 32;
+        if (g == 32 || g == 64 || g == 128) {
+            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g) != cudaSuccess) cudaGetLastError();
+        }
+    }
     BXG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     BXG_CUDA(cudaMallocHost(&c.mailbox, 64 * sizeof(int64_t)));
     BXG_CUDA(cudaMalloc(&c.d_mailbox, 64 * sizeof(int64_t)));

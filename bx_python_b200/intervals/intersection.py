@@ -93,6 +93,9 @@ class IntervalNode:
         self._root().traverse(func)
 
 
+_SMALL_CAP = 1 << 16       # hit capacity of the low-latency path's mapped buffer (csrc/itree.cu SMALL_CAP)
+
+
 class _DeviceIndex:
     """Owner of one bxg_itree handle (ntrees trees)."""
 
@@ -143,13 +146,16 @@ class _DeviceIndex:
         a = self._one
         if a is None:
             p = C.c_void_p()
-            a = self._one = (p, C.byref(p), _lib.lib().bxg_itree_find1)
+            a = self._one = [p, C.byref(p), _lib.lib().bxg_itree_find1, None, None]
         n = a[2](self._h, tree, start, end, a[1])
         if n <= 0:
             if n < 0:
                 check(int(n))
             return []
-        return (C.c_int32 * n).from_address(a[0].value)[:]
+        addr = a[0].value
+        if addr != a[3]:                   # the index's mapped result buffer: one ctypes view for all calls
+            a[3], a[4] = addr, (C.c_int32 * _SMALL_CAP).from_address(addr)
+        return a[4][:n] if n <= _SMALL_CAP else (C.c_int32 * n).from_address(addr)[:]
 
     def count(self, qtree, qs, qe):
         out = np.empty(len(qs), np.int32)

@@ -109,14 +109,15 @@ def subtract(primary, others, mincols=1, pieces=True, lens=None):
     """operations/subtract.py:22-79.  -> dict(src, start, end, skipped)."""
     bitsets = _secondary_bitsets(list(others), lens or {}, lambda a, b: _or_into(a, b, True))
     which, ok, bad, counts, sets = _primary_counts(primary, bitsets)
-    untouched = np.nonzero(which < 0)[0]                               # chromosome without a bit set: yielded as is
+    # chromosome without a bit set: yielded as is (a line with end < start never leaves the reader: ParseError, io.py:66-67)
+    untouched = np.nonzero((which < 0) & (primary.start <= primary.end))[0]
     below = np.nonzero(ok & (counts < mincols))[0]                     # not enough overlap: the whole interval
     parts = [(untouched, primary.start[untouched], primary.end[untouched]),
              (below, primary.start[below], primary.end[below])]
     if pieces:
         parts.append(_pieces(sets, which, np.nonzero(ok & (counts >= mincols))[0], primary.start, primary.end, 0))
     src, rs, re = _merge_rows(parts)
-    return {"src": src, "start": rs, "end": re, "skipped": np.nonzero(bad)[0]}
+    return {"src": src, "start": rs, "end": re, "skipped": np.nonzero(bad | ((which < 0) & (primary.start > primary.end)))[0]}
 
 
 def merge(table, mincols=1):

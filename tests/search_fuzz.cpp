@@ -35,7 +35,7 @@ int main(int argc, char **argv) {
     auto ld8 = [](const int4 *p, int4 &a, int4 &b) { a = p[0]; b = p[1]; };
     long checks = 0;
     for (int trial = 0; trial < trials; trial++) {
-        const int n = 1 + (int)(rnd() % (trial % 4 == 0 ? 200000 : 3000));
+        const int n = 1 + (int)(rnd() % (trial % 4 == 0 ? 200000 : (trial % 7 == 3 ? 40 : 3000)));
         const int maxsplit = (trial % 2) ? 4096 : 8;      // a tiny splitter budget exercises the deep levels
         const int ntrees = 1 + (int)(rnd() % 6);
         std::vector<uint32_t> toff(ntrees + 1);
@@ -43,7 +43,8 @@ int main(int argc, char **argv) {
         toff[0] = 0;
         toff[ntrees] = (uint32_t)n;
         std::sort(toff.begin(), toff.end());
-        const int range = 1 + (int)(rnd() % 100000);
+        // every 7th trial spreads few items over 16 M positions: wide grid cells (shift > 20, one or two packed offsets)
+        const int range = (trial % 7 == 3) ? 16000000 : 1 + (int)(rnd() % 100000);
         const long npad = ((n + 15) & ~15l) + 16;
         std::vector<int32_t> S(npad, INT_MAX), PM(npad, INT_MAX), E(npad, INT_MIN);
         for (int t = 0; t < ntrees; t++) {
@@ -156,6 +157,23 @@ int main(int argc, char **argv) {
             }
         }
         auto ldr = [](const bxs::GridRec *p) { return *p; };
+        // 16-byte records, packed as k_build_grid16 does
+        std::vector<bxs::GridRec16> G16(G.size());
+        for (int t = 0; t < ntrees; t++)
+            for (uint32_t c = 0; c <= gd[t].ncells; c++) {
+                const size_t r = gd[t].coff + c;
+                unsigned long long p = 0;
+                if (c < gd[t].ncells) {
+                    const uint32_t cnt = G[r + 1].x - G[r].x;
+                    p = cnt < 255u ? cnt : 255u;
+                    const uint32_t kmax = (uint32_t)bxs::grid16_fields(gd[t].shift), stored = std::min(cnt, kmax);
+                    const long long v = (long long)gd[t].base + ((long long)c << gd[t].shift);
+                    for (uint32_t i = 0; i < stored; i++)
+                        p |= (unsigned long long)((long long)S[G[r].x + i] - v) << (8 + i * gd[t].shift);
+                }
+                G16[r] = bxs::GridRec16{G[r].x, G[r].y, (uint32_t)p, (uint32_t)(p >> 32)};
+            }
+        auto ldr16 = [](const bxs::GridRec16 *p) { return *p; };
         for (int q = 0; q < 150; q++) {
             const int t = (int)(rnd() % (uint32_t)ntrees);
             const int32_t qs = shifted((long long)(rnd() % (uint32_t)(range + 40)) - 70);
@@ -255,6 +273,21 @@ int main(int argc, char **argv) {
                 if (hi5 != ehi || lo5 > std::min(elo, ehi) || lo5 < toff[t] || got5 != want3) {
                     printf("SEARCH_WALK_GRID MISMATCH trial %d n=%d dens=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u got=%zu want=%zu\n",
                            trial, n, dens, toff[t], toff[t + 1], qs, qe, hi5, ehi, lo5, elo, got5.size(), want3.size());
+                    return 1;
+                }
+                std::vector<uint32_t> got6;
+                uint32_t hi6, lo6;
+                bxs::search_walk_grid16(G16.data(), gd[t], S.data(), toff[t], toff[t + 1], qe, qs, E.data(), Mp.data(),
+                                        (int)Mp.size(), ldr16, ld8, ld, hi6, lo6, [&](uint32_t k0, unsigned mask) {
+                                            while (mask) {
+                                                int b = bxs::ffs32(mask) - 1;
+                                                mask &= mask - 1;
+                                                got6.push_back(k0 + b);
+                                            }
+                                        });
+                if (hi6 != ehi || lo6 > std::min(elo, ehi) || lo6 < toff[t] || got6 != want3) {
+                    printf("SEARCH_WALK_GRID16 MISMATCH trial %d n=%d dens=%d shift=%d seg=[%u,%u) qs=%d qe=%d hi=%u/%u lo=%u/%u got=%zu want=%zu\n",
+                           trial, n, dens, gd[t].shift, toff[t], toff[t + 1], qs, qe, hi6, ehi, lo6, elo, got6.size(), want3.size());
                     return 1;
                 }
                 if (hi2 != ehi || lo2 > std::min(elo, ehi) || got2 != want) {
