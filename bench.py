@@ -531,7 +531,7 @@ def run_ours(args):
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except (OSError, ValueError):
         pass
-    traffic = tj.get(dom, tj.get(dom.replace("PROBE", os.environ.get("BXB200_FIND_PROBE", "2"))))
+    traffic = tj.get(dom, tj.get(dom.replace("PROBE", os.environ.get("BXB200_FIND_PROBE", "4"))))
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dom_ms,

@@ -6,6 +6,7 @@
 // only feeds the strict count_range correction (binBits.c:155,161).
 #include <cub/cub.cuh>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -21,7 +22,8 @@ struct bxg_bits {
     int64_t nwords_alloc = 0;  // nwords rounded up to a multiple of 4 (32 B)
     uint64_t *words = nullptr;
     uint8_t *state = nullptr;
-    uint32_t *rank = nullptr;  // exclusive prefix popcount per 256-bit sector (4 words), nwords_alloc/4+1 entries (lazy)
+    uint64_t *rank = nullptr;  // rank lines: 64-byte lines {rank, 7 bitmap words}, nlines + 1 of them (lazy; see count_range)
+    int64_t nlines = 0;
     bool rank_valid = false;
     int32_t *run_s = nullptr, *run_e = nullptr;  // run extraction output (device)
     int64_t run_cap = 0, nruns = -1;
@@ -344,8 +346,35 @@ struct SetDesc {
     uint64_t *words;
     uint8_t *state;
     int32_t bin_size, flat, size;
+    int32_t cellbase;      // first locality bucket of this set (bucketed form only)
+};
+struct RangeTriple {
+    int32_t w, s, c;
 };
 
+// Locality bucket of every range: (set, start >> kshift) flattened over the genome, at most 256 buckets of a few MB of
+// bitmap each.  A file in random order touches the whole genome's bitmaps (386 MB for hg38, three times L2) at random:
+// every edge word's atomicOr pulls its sector from DRAM and every rewritten line goes back to DRAM (ncu r02b: 6.0 GB read +
+// 7.6 GB written for 50 M ranges).  Processed bucket by bucket -- one 8-bit radix pass over 13-byte records -- the same
+// atomics and stores hit lines that are still in L2.
+__global__ void __launch_bounds__(256)
+k_range_buckets(const SetDesc *__restrict__ descs, int nsets, int kshift, int group, const int32_t *__restrict__ which,
+                const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n, uint8_t *__restrict__ keys,
+                RangeTriple *__restrict__ vals) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t w = __ldcs(which + i), s = __ldcs(start + i), c = __ldcs(count + i);
+        int k = 255;
+        if (w >= 0 && w < nsets) {
+            k = group > 0 ? w / group : descs[w].cellbase + (int)((uint32_t)(s < 0 ? 0 : s) >> kshift);
+            k = k < 0 ? 0 : (k > 255 ? 255 : k);
+        }
+        keys[i] = (uint8_t)k;
+        vals[i] = RangeTriple{w, s, c};
+    }
+}
+
+template <bool AOS>
 __global__ void __launch_bounds__(256)
 k_set_ranges_multi(const SetDesc *__restrict__ descs, int nsets, const int32_t *__restrict__ which,
                    const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n) {
@@ -360,7 +389,13 @@ k_set_ranges_multi(const SetDesc *__restrict__ descs, int nsets, const int32_t *
         int64_t mb = 0, me = 0;
         uint64_t *words = nullptr;
         if (i < n) {
-            const int32_t t = __ldg(which + i), s = __ldg(start + i), c = __ldg(count + i);
+            int32_t t, s, c;
+            if (AOS) {                                  // bucketed records (k_range_buckets + radix pass): `which` points at them
+                const RangeTriple r = reinterpret_cast<const RangeTriple *>(which)[i];
+                t = r.w; s = r.s; c = r.c;
+            } else {
+                t = __ldg(which + i); s = __ldg(start + i); c = __ldg(count + i);
+            }
             if (t >= 0 && t < nsets && c > 0 && s >= 0) {
                 const SetDesc d = descs[t];
                 if ((int64_t)s + c <= d.size) {
@@ -434,107 +469,102 @@ __global__ void k_read_bits(const uint64_t *__restrict__ words, const int32_t *_
 // ------------------------------------------------------------------------------------------------------------------
 // count_range x n  (binBits.c:130-178): rank table lookup, O(1) per query
 // ------------------------------------------------------------------------------------------------------------------
-// The rank table holds one exclusive prefix popcount per 256-bit SECTOR (4 words = one 32-byte DRAM sector): an eighth of
-// the bitmap's size (48 MB for a whole hg38 genome -- it stays in the 126 MB L2, where a per-word table of 193 MB did
-// not), built by one scan that reads the bitmap once.  rank(p) = table[p >> 8] + popcount of the sector's bits below
-// p & 255: one table sector + one bitmap sector (a single 256-bit load) per position.
-struct PopcSector {
+// Rank lines.  A count_range query reads at two random positions of a genome of bitmaps (386 MB for hg38: three times
+// L2), so what it costs is DRAM lines.  A separate rank table (one entry per word or per sector) means two lines per
+// position -- the table's and the bitmap's -- and ncu (r02b) showed 264 B of DRAM reads per query.  Here the rank is
+// stored NEXT TO the bits it belongs to: the count structure is a copy of the bitmap cut into 64-byte lines
+//     line i = { rank_i : number of set bits before bit 448 i ; words 7 i .. 7 i + 6 of the bitmap }        (8 x uint64)
+// so rank(p) = line[p / 448].rank + popcount of that line's bits below p % 448: ONE 64-byte line per position, which is
+// also exactly what one L2 miss fetches.  Built lazily (one scan over 7-word popcounts + one interleaving pass, both
+// streaming) and invalidated by every mutation, like the table it replaces; costs 8/7 of the bitmap in HBM.
+constexpr int RL_WORDS = 7;                    // bitmap words per rank line
+constexpr uint32_t RL_BITS = 64u * RL_WORDS;   // 448
+
+struct PopcLine {                              // popcount of line i's words (scan input)
     const uint64_t *w;
-    int64_t nsec;
+    int64_t nwords, nlines;
     __device__ __forceinline__ uint32_t operator()(int64_t i) const {
-        if (i >= nsec) return 0u;
-        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(w + 4 * i);
-        const ulonglong2 a = __ldg(p), b = __ldg(p + 1);
-        return (uint32_t)(__popcll(a.x) + __popcll(a.y) + __popcll(b.x) + __popcll(b.y));
+        uint32_t c = 0;
+        if (i < nlines) {
+#pragma unroll
+            for (int k = 0; k < RL_WORDS; k++) {
+                const int64_t j = i * RL_WORDS + k;
+                if (j < nwords) c += (uint32_t)__popcll(__ldg((const unsigned long long *)w + j));
+            }
+        }
+        return c;
     }
 };
 
-// Random single-sector reads from a working set far larger than L2 (a genome of bitmaps + rank tables): ncu (r02b) shows
-// 264 B of DRAM reads per count_range query for ~4 missed sectors, i.e. 64-byte fetches.  Neither
-// cudaLimitMaxL2FetchGranularity = 32 (no change, r02c) nor loads carrying an L2 evict_first policy (COUNT_L2_HINT=1:
-// 2.69 -> 3.57 ms per 50 M queries, r02d) help, so plain loads stay the default; the switch is kept for A/B runs.
-#ifndef COUNT_L2_HINT
-#define COUNT_L2_HINT 0
-#endif
-#if COUNT_L2_HINT
-__device__ __forceinline__ uint64_t count_policy() {
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
+__global__ void __launch_bounds__(256)
+k_rank_lines(const uint64_t *__restrict__ words, int64_t nwords, const uint32_t *__restrict__ prefix, int64_t nlines,
+             ulonglong2 *__restrict__ lines) {
+    // one thread per 16-byte quarter of a line: coalesced 128-bit stores, the bitmap read with plain 8-byte loads
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < (nlines + 1) * 4; q += stride) {
+        const int64_t i = q >> 2;
+        const int part = (int)(q & 3);                      // words 2*part, 2*part+1 of the line
+        unsigned long long v[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int k = 2 * part + h;                     // 0 = rank, 1..7 = bitmap words 7i .. 7i+6
+            if (k == 0) {
+                v[h] = prefix[i];
+            } else {
+                const int64_t j = i * RL_WORDS + (k - 1);
+                v[h] = (i < nlines && j < nwords) ? __ldg((const unsigned long long *)words + j) : 0ull;
+            }
+        }
+        st_stream(lines + q, make_ulonglong2(v[0], v[1]));
+    }
 }
-__device__ __forceinline__ void ld_sector(const uint64_t *p, unsigned long long &a, unsigned long long &b,
-                                          unsigned long long &c, unsigned long long &d) {
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
-        : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(count_policy()));
-}
-__device__ __forceinline__ uint32_t ld_rank(const uint32_t *p) {
-    uint32_t r;
-    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(count_policy()));
-    return r;
-}
-#else
+
 __device__ __forceinline__ void ld_sector(const uint64_t *p, unsigned long long &a, unsigned long long &b,
                                           unsigned long long &c, unsigned long long &d) {
     asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
-__device__ __forceinline__ uint32_t ld_rank(const uint32_t *p) { return __ldg(p); }
-#endif
 
-// bits of the 256-bit sector (a,b,c,d) strictly below bit offset o in [1,255]
-__device__ __forceinline__ uint32_t popc_below(unsigned long long a, unsigned long long b, unsigned long long c,
-                                               unsigned long long d, uint32_t o) {
-    const uint32_t k = o >> 6;                                   // words fully below
-    const unsigned long long part = k == 0 ? a : k == 1 ? b : k == 2 ? c : d;
-    uint32_t r = (uint32_t)__popcll(part & ((1ull << (o & 63)) - 1ull));
-    if (k > 0) r += (uint32_t)__popcll(a);
-    if (k > 1) r += (uint32_t)__popcll(b);
-    if (k > 2) r += (uint32_t)__popcll(c);
-    return r;
-}
-
-__device__ __forceinline__ uint32_t rank_at(const uint64_t *__restrict__ words, const uint32_t *__restrict__ rank, uint32_t p) {
-    const uint32_t sec = p >> 8, o = p & 255u;
-    uint32_t r = ld_rank(rank + sec);
+// rank(p): set bits in [0, p)
+__device__ __forceinline__ uint32_t rank_at(const uint64_t *__restrict__ lines, uint32_t p) {
+    const uint32_t i = p / RL_BITS, o = p - i * RL_BITS;
+    const uint64_t *L = lines + 8 * (size_t)i;
+    unsigned long long r, d0, d1, d2;
+    ld_sector(L, r, d0, d1, d2);                            // rank + the line's first 192 bits
+    uint32_t c = (uint32_t)r;
     if (o) {
-        unsigned long long a, b, c, d;
-        ld_sector(words + 4 * (size_t)sec, a, b, c, d);
-        r += popc_below(a, b, c, d, o);
+        const uint32_t k = o >> 6;
+        const unsigned long long m = (1ull << (o & 63)) - 1ull;
+        if (k < 3) {
+            c += (uint32_t)__popcll((k == 0 ? d0 : k == 1 ? d1 : d2) & m);
+            if (k > 0) c += (uint32_t)__popcll(d0);
+            if (k > 1) c += (uint32_t)__popcll(d1);
+        } else {
+            unsigned long long d3, d4, d5, d6;
+            ld_sector(L + 4, d3, d4, d5, d6);               // the other half of the same 64-byte line
+            c += (uint32_t)(__popcll(d0) + __popcll(d1) + __popcll(d2));
+            c += (uint32_t)__popcll((k == 3 ? d3 : k == 4 ? d4 : k == 5 ? d5 : d6) & m);
+            if (k > 3) c += (uint32_t)__popcll(d3);
+            if (k > 4) c += (uint32_t)__popcll(d4);
+            if (k > 5) c += (uint32_t)__popcll(d5);
+        }
     }
-    return r;
+    return c;
 }
 
-// popcount of [s, s + c), c > 0: when both ends fall into one sector a single sector load answers it without the table
-__device__ __forceinline__ int32_t count_span(const uint64_t *__restrict__ words, const uint32_t *__restrict__ rank, uint32_t s,
-                                              uint32_t c) {
-    const uint32_t e = s + c;
-    if ((s >> 8) == ((e - 1) >> 8)) {
-        unsigned long long w[4];
-        ld_sector(words + 4 * (size_t)(s >> 8), w[0], w[1], w[2], w[3]);
-        const uint32_t o0 = s & 255u, o1 = ((e - 1) & 255u) + 1u;   // bits [o0, o1) of the sector, o1 in [1,256]
-        uint32_t r = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t lo = o0 > 64u * k ? o0 - 64u * k : 0u, hi = o1 > 64u * k ? o1 - 64u * k : 0u;
-            if (lo < 64u && hi > lo) {
-                unsigned long long m = hi >= 64u ? ~0ull : ((1ull << hi) - 1ull);
-                m &= ~0ull << lo;
-                r += (uint32_t)__popcll(w[k] & m);
-            }
-        }
-        return (int32_t)r;
-    }
-    return (int32_t)(rank_at(words, rank, e) - rank_at(words, rank, s));
+// popcount of [s, s + c), c > 0
+__device__ __forceinline__ int32_t count_span(const uint64_t *__restrict__ lines, uint32_t s, uint32_t c) {
+    return (int32_t)(rank_at(lines, s + c) - rank_at(lines, s));
 }
 
 __global__ void __launch_bounds__(256)
-k_count_ranges(const uint64_t *__restrict__ words, const uint32_t *__restrict__ rank, const uint8_t *__restrict__ state,
+k_count_ranges(const uint64_t *__restrict__ lines, const uint8_t *__restrict__ state,
                int bin_size, int strict, const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n,
                int32_t *__restrict__ out, volatile long long *flag, long long seq) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int32_t s = __ldg(start + i), c = __ldg(count + i), r = 0;
         if (c > 0) {
-            r = count_span(words, rank, (uint32_t)s, (uint32_t)c);
+            r = count_span(lines, (uint32_t)s, (uint32_t)c);
             // binBits.c:155,161: an ALL_ONE *sentinel* first bin contributes (k - offset) instead of k
             if (strict && state[s / bin_size] == BO) r -= s % bin_size;
         }
@@ -545,8 +575,7 @@ k_count_ranges(const uint64_t *__restrict__ words, const uint32_t *__restrict__ 
 
 // genome-wide form: query i addresses bit set which[i] (the dict lookup `bitsets[chrom]` of scripts/bed_intersect.py:46-53)
 struct CountDesc {
-    const uint64_t *words;
-    const uint32_t *rank;
+    const uint64_t *lines;       // rank lines (see above)
     const uint8_t *state;
     int32_t bin_size, strict, size;
 };
@@ -562,7 +591,7 @@ k_count_ranges_multi(const CountDesc *__restrict__ descs, int nsets, const int32
         if (w >= 0 && w < nsets && c > 0) {
             const CountDesc d = descs[w];
             if (s >= 0 && (int64_t)s + c <= d.size) {          // out-of-range queries are the host shim's IndexError
-                r = count_span(d.words, d.rank, (uint32_t)s, (uint32_t)c);
+                r = count_span(d.lines, (uint32_t)s, (uint32_t)c);
                 if (d.strict && d.state[s / d.bin_size] == BO) r -= s % d.bin_size;
             }
         }
@@ -815,7 +844,7 @@ k_group_stats(const int32_t *__restrict__ key, const int32_t *__restrict__ val, 
 
 // out[k] = popcount of set k, read off the last entry of its rank table
 struct TotalDesc {
-    const uint32_t *rank_last;
+    const uint64_t *rank_last;       // rank word of the sentinel line = popcount of the whole bitmap
 };
 __global__ void k_gather_totals(const TotalDesc *__restrict__ d, int n, long long *__restrict__ out, int64_t out_stride) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -945,15 +974,41 @@ int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int3
     if (nsets <= 0 || nsets > BATCH_MAX_PAIRS) return set_error(BXG_ERR_ARG, "nsets must be in [1, %d]", BATCH_MAX_PAIRS);
     if (n <= 0) return BXG_OK;
     static SetDesc h_desc[BATCH_MAX_PAIRS];
+    int64_t total_bits = 0;
     for (int k = 0; k < nsets; k++) {
         bxg_bits *b = sets[k];
         if (!b) {                                     // a chromosome this process holds no bitmap for: its ranges are skipped
-            h_desc[k] = SetDesc{nullptr, nullptr, 1, 1, 0};
+            h_desc[k] = SetDesc{nullptr, nullptr, 1, 1, 0, 0};
             continue;
         }
-        h_desc[k] = SetDesc{b->words, b->state, b->bin_size, b->flat ? 1 : 0, b->size};
+        h_desc[k] = SetDesc{b->words, b->state, b->bin_size, b->flat ? 1 : 0, b->size, 0};
+        total_bits += b->size;
     }
     Context &c = ctx();
+    // bucket the ranges by position first when the bitmaps do not fit L2 and there is enough work to pay for the pass
+    static const int bucket_mode = [] {
+        const char *e = getenv("BXB200_SET_BUCKETS");      // 0: never, 1: always, unset: by size
+        return e ? atoi(e) : -1;
+    }();
+    const bool bucketed = bucket_mode == 1 || (bucket_mode != 0 && n >= (1 << 20) && total_bits / 8 > c.l2_bytes / 2);
+    int kshift = 0, group = 0;
+    if (bucketed) {
+        if (nsets > 128) {
+            group = (nsets + 255) / 256;               // many small sets: neighbouring sets share a bucket
+        } else {
+            for (kshift = 16;; kshift++) {             // the coarsest split that still gives every set its own buckets
+                int64_t cells = 0;
+                for (int k = 0; k < nsets; k++)
+                    if (sets[k]) cells += ((int64_t)sets[k]->size >> kshift) + 1;
+                if (cells <= 256) break;
+            }
+            int32_t base = 0;
+            for (int k = 0; k < nsets; k++) {
+                h_desc[k].cellbase = base;
+                if (sets[k]) base += (int32_t)(((int64_t)sets[k]->size >> kshift) + 1);
+            }
+        }
+    }
     void *d_desc;
     BXG_TRY(scratch(3, sizeof(SetDesc) * (size_t)nsets, &d_desc));
     BXG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(SetDesc) * (size_t)nsets, cudaMemcpyHostToDevice, c.stream));
@@ -961,8 +1016,37 @@ int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int3
     BXG_TRY(stage_in(0, which, (size_t)n * 4, loc, &dw));
     BXG_TRY(stage_in(1, start, (size_t)n * 4, loc, &ds));
     BXG_TRY(stage_in(5, count, (size_t)n * 4, loc, &dc));
-    BXG_LAUNCH(k_set_ranges_multi, grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets, (const int32_t *)dw,
-               (const int32_t *)ds, (const int32_t *)dc, n);
+    if (bucketed) {
+        void *d_k0, *d_k1, *d_v0, *d_v1, *tmp;
+        BXG_TRY(scratch(2, (size_t)n, &d_k0));
+        BXG_TRY(scratch(4, (size_t)n, &d_k1));
+        BXG_TRY(scratch(6, (size_t)n * sizeof(RangeTriple), &d_v0));
+        if ((size_t)n * sizeof(RangeTriple) > c.bucket_cap) {            // second value buffer: its own grow-only slot
+            BXG_CUDA(cudaStreamSynchronize(c.stream));
+            cudaFree(c.bucket_buf);
+            c.bucket_buf = nullptr;
+            c.bucket_cap = 0;
+            BXG_CUDA(cudaMalloc(&c.bucket_buf, (size_t)n * sizeof(RangeTriple) + 256));
+            c.bucket_cap = (size_t)n * sizeof(RangeTriple) + 256;
+        }
+        d_v1 = c.bucket_buf;
+        BXG_LAUNCH(k_range_buckets, grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets, kshift, group,
+                   (const int32_t *)dw, (const int32_t *)ds, (const int32_t *)dc, n, (uint8_t *)d_k0, (RangeTriple *)d_v0);
+        size_t tmp_bytes = 0;
+        BXG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint8_t *)d_k0, (uint8_t *)d_k1,
+                                                 (const RangeTriple *)d_v0, (RangeTriple *)d_v1, n, 0, 8, c.stream));
+        BXG_TRY(scratch(7, tmp_bytes, &tmp));
+        prof_begin("cub::DeviceRadixSort(range buckets)");
+        BXG_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint8_t *)d_k0, (uint8_t *)d_k1,
+                                                 (const RangeTriple *)d_v0, (RangeTriple *)d_v1, n, 0, 8, c.stream));
+        prof_end();
+        c.launches += 3;
+        BXG_LAUNCH((k_set_ranges_multi<true>), grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets,
+                   (const int32_t *)d_v1, (const int32_t *)nullptr, (const int32_t *)nullptr, n);
+    } else {
+        BXG_LAUNCH((k_set_ranges_multi<false>), grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets,
+                   (const int32_t *)dw, (const int32_t *)ds, (const int32_t *)dc, n);
+    }
     for (int k = 0; k < nsets; k++)
         if (sets[k]) invalidate(sets[k]);
     // (h_desc is pageable: cudaMemcpyAsync has staged it before returning, so the static table may be reused at once)
@@ -1121,18 +1205,22 @@ int bxg_bits_count_all(const bxg_bits_t *b, int64_t *count) {
 static int build_rank(bxg_bits *b) {
     if (b->rank_valid) return BXG_OK;
     Context &c = ctx();
-    const int64_t nsec = b->nwords_alloc / 4, n = nsec + 1;
-    if (!b->rank) BXG_CUDA(cudaMalloc(&b->rank, (size_t)n * 4));
+    const int64_t nlines = cdiv(b->nwords, RL_WORDS), n = nlines + 1;
+    if (!b->rank) BXG_CUDA(cudaMalloc(&b->rank, (size_t)n * 64));
+    b->nlines = nlines;
+    void *d_prefix, *tmp;
+    BXG_TRY(scratch(6, (size_t)n * 4, &d_prefix));
     cub::CountingInputIterator<int64_t> idx(0);
-    cub::TransformInputIterator<uint32_t, PopcSector, cub::CountingInputIterator<int64_t>> it(idx, PopcSector{b->words, nsec});
+    cub::TransformInputIterator<uint32_t, PopcLine, cub::CountingInputIterator<int64_t>> it(idx, PopcLine{b->words, b->nwords, nlines});
     size_t tmp_bytes = 0;
-    BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, b->rank, n, c.stream));
-    void *tmp;
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, (uint32_t *)d_prefix, n, c.stream));
     BXG_TRY(scratch(7, tmp_bytes, &tmp));
     prof_begin("cub::DeviceScan::ExclusiveSum(rank)");
-    BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, b->rank, n, c.stream));
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, (uint32_t *)d_prefix, n, c.stream));
     prof_end();
     c.launches += 2;   // CUB's single-pass scan: init + scan kernels
+    BXG_LAUNCH(k_rank_lines, grid_for(cdiv(n * 4, 256), 8), 256, 0, b->words, b->nwords, (const uint32_t *)d_prefix, nlines,
+               (ulonglong2 *)b->rank);
     b->rank_valid = true;
     return BXG_OK;
 }
@@ -1146,7 +1234,7 @@ int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *co
         memcpy(zc_host(0), start, (size_t)n * 4);
         memcpy(zc_host(1), count, (size_t)n * 4);
         const long long seq = zc_next_seq();
-        BXG_LAUNCH(k_count_ranges, 1, 64, 0, b->words, b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0,
+        BXG_LAUNCH(k_count_ranges, 1, 64, 0, b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0,
                    (const int32_t *)zc_device(0), (const int32_t *)zc_device(1), n, (int32_t *)zc_device(2), zc_flag_device(), seq);
         BXG_TRY(zc_wait(seq));
         memcpy(out, zc_host(2), (size_t)n * 4);
@@ -1161,7 +1249,7 @@ int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *co
         BXG_TRY(scratch(2, (size_t)n * 4, &t));
         dout = (int32_t *)t;
     }
-    BXG_LAUNCH(k_count_ranges, grid_for(cdiv(n, 256), 8), 256, 0, b->words, b->rank, b->state, b->bin_size,
+    BXG_LAUNCH(k_count_ranges, grid_for(cdiv(n, 256), 8), 256, 0, b->rank, b->state, b->bin_size,
                (strict && !b->flat) ? 1 : 0, (const int32_t *)ds, (const int32_t *)dc, n, dout, (volatile long long *)nullptr, 0ll);
     if (loc == BXG_HOST) {
         BXG_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx().stream));
@@ -1179,11 +1267,11 @@ int bxg_bits_count_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const in
     for (int k = 0; k < nsets; k++) {
         bxg_bits *b = sets[k];
         if (!b) {                                     // `fields[0] in bitsets` is false (bed_intersect.py:53): count 0
-            h_desc[k] = CountDesc{nullptr, nullptr, nullptr, 1, 0, 0};
+            h_desc[k] = CountDesc{nullptr, nullptr, 1, 0, 0};
             continue;
         }
         BXG_TRY(build_rank(b));
-        h_desc[k] = CountDesc{b->words, b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0, b->size};
+        h_desc[k] = CountDesc{b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0, b->size};
     }
     Context &c = ctx();
     void *d_desc;
@@ -1231,7 +1319,7 @@ int bxg_bits_count_all_multi(bxg_bits_t *const *sets, int32_t nsets, int64_t *ou
             continue;
         }
         BXG_TRY(build_rank(b));
-        h_desc[k] = TotalDesc{b->rank + b->nwords_alloc / 4};
+        h_desc[k] = TotalDesc{b->rank + 8 * (size_t)b->nlines};
     }
     Context &c = ctx();
     void *d_desc;

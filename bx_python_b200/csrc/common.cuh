@@ -27,6 +27,8 @@ struct Context {
     long long zc_seq = 0;
     void *l2_flush_buf = nullptr;
     size_t l2_flush_bytes = 0;
+    void *bucket_buf = nullptr;     // second record buffer of the bucketed set_ranges_multi (grow-only)
+    size_t bucket_cap = 0;
 };
 
 Context &ctx();

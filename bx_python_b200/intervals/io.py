@@ -6,9 +6,9 @@ The reference walks a reader line by line and calls ``BinnedBitSet.set_range`` p
 ``bx.bitset_builders`` (which raises on out-of-range lines): the interval is CLAMPED -- ``start = max(start, 0)``,
 ``end = min(end, bitset.size)`` (:212-213); a line with ``end < start`` never gets that far (the reader raises ParseError,
 :66-67; ``NiceReaderWrapper`` skips it, :233-245), and ``BitsetSafeReaderWrapper`` (:262-289) also skips lines with
-``end > lens.get(chrom, MAX)``.  Both behaviours are available here: ``safe=False`` raises like the plain reader,
-``safe=True`` skips like the wrappers and reports what it skipped.  Text parsing (``read_bed``) is a plain host loop, as
-in the reference.
+``end > lens.get(chrom, MAX)``.  Here lines with ``end < start`` are always skipped (there is no parse step to refuse
+them); ``safe=True`` adds the BitsetSafeReaderWrapper filter and reports what it skipped.  Text parsing (``read_bed``) is
+a plain host loop, as in the reference.
 """
 from __future__ import annotations
 
@@ -50,22 +50,19 @@ class IntervalTable:
         """io.py:190-216 for the whole table in one launch -> {chrom: BinnedBitSet} (chromosomes in the order of their
         first interval).  The reference accepts the pad arguments and ignores them (:190); so does this.
 
-        safe=False: the plain reader -- a line with end < start is the reader's ParseError (:66-67; ValueError here), and
-        whatever ``set_range`` refuses after the clamping raises its IndexError.
-        safe=True : NiceReaderWrapper + BitsetSafeReaderWrapper (:218-289) -- lines with end < start, or with
-        end > lens.get(chrom, MAX), are skipped; returns (bitsets, skipped line indices)."""
+        A line with end < start never reaches the bit sets: GenomicInterval refuses it (:66-67) and NiceReaderWrapper --
+        the reader the operations are fed with -- skips it (:233-245); such lines are skipped here in both modes.
+        safe=False: whatever ``set_range`` refuses after the clamping raises its IndexError.
+        safe=True : BitsetSafeReaderWrapper (:262-289) as well -- lines with end > lens.get(chrom, MAX) are skipped too;
+        returns (bitsets, skipped line indices)."""
         lens = lens or {}
         s, e = self.start, self.end
         n = len(s)
         limit = np.asarray([lens.get(c, MAX) for c in self.names] or [MAX], np.int64)
         lim_of = limit[self.chrom] if n else np.zeros(0, np.int64)
-        inverted = e < s
+        keep = ~(e < s)
         if safe:
-            keep = ~inverted & ~(e > lim_of)
-        else:
-            if inverted.any():
-                raise ValueError("Start is greater than End. Interval length is < 1.")
-            keep = np.ones(n, bool)
+            keep &= ~(e > lim_of)
         sel = np.nonzero(keep)[0]
         # a chromosome gets its bit set when its first surviving interval is read (:199-211)
         order = []

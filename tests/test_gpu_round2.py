@@ -345,3 +345,40 @@ def test_scalar_next_far_and_near(lib, orc):
         assert b.next_clear(7) == size                         # nothing clear: scans to the end
         if cls is BitSet:
             assert b.next_clear(7, 1000) == 1000 and b.next_set(7, 7) == 7
+
+
+BUCKET_SNIPPET = r"""
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+from bx_python_b200.bitset import BinnedBitSet, set_ranges_many
+from oracle import oracle as orc
+rng = np.random.default_rng(5)
+for nsets, size in ((5, 3_000_000), (300, 40_000)):
+    sets = [BinnedBitSet(size + 17 * k) for k in range(nsets)]
+    n = 200_000
+    w = rng.integers(0, nsets, n).astype(np.int32)
+    s = rng.integers(0, size - 3000, n).astype(np.int32)
+    c = rng.integers(0, 3000, n).astype(np.int32)
+    c[:50] = size // 2                                    # a few very long ranges (CTA-wide interior sweep)
+    s[:50] = rng.integers(0, size // 2 - 10, 50)
+    set_ranges_many(sets, w, s, c)
+    for k in range(0, nsets, max(1, nsets // 7)):
+        o = orc.OracleBinnedBitSet(size + 17 * k)
+        o.set_ranges(s[w == k], c[w == k])
+        assert np.array_equal(sets[k].to_words(), o.words()), (nsets, k)
+        assert np.array_equal(sets[k].bin_states(), o.states()), (nsets, k)
+print("bucketed ok")
+"""
+
+
+def test_set_ranges_bucketed_path(lib):
+    """BXB200_SET_BUCKETS=1 forces the locality-bucketed form of bxg_bits_set_ranges_multi (radix pass on (set, position)
+    buckets, then the same kernel over the bucketed records) -- few large sets and > 128 small sets (grouped buckets)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", BUCKET_SNIPPET % root], capture_output=True, text=True, timeout=600,
+                       env={**os.environ, "BXB200_SET_BUCKETS": "1"})
+    assert r.returncode == 0 and "bucketed ok" in r.stdout, r.stderr[-3000:]
