@@ -22,8 +22,9 @@ struct bxg_bits {
     int64_t nwords_alloc = 0;  // nwords rounded up to a multiple of 4 (32 B)
     uint64_t *words = nullptr;
     uint8_t *state = nullptr;
-    uint64_t *rank = nullptr;  // rank lines: 64-byte lines {rank, 7 bitmap words}, nlines + 1 of them (lazy; see count_range)
+    uint32_t *rank = nullptr;  // rank lines: 32-byte lines {rank, 7 x 32 bitmap bits}, nlines + 1 of them (lazy; see count_range)
     int64_t nlines = 0;
+    bool maybe_one = false;    // an ALL_ONE sentinel bin may exist (only then does strict count_range need the bin states)
     bool rank_valid = false;
     int32_t *run_s = nullptr, *run_e = nullptr;  // run extraction output (device)
     int64_t run_cap = 0, nruns = -1;
@@ -374,7 +375,26 @@ k_range_buckets(const SetDesc *__restrict__ descs, int nsets, int kshift, int gr
     }
 }
 
-template <bool AOS>
+__device__ __forceinline__ void st_ones256(uint64_t *p) {          // one full 32-byte sector of ones (p 32-byte aligned)
+    asm volatile("st.global.v4.u64 [%0], {%1, %1, %1, %1};" ::"l"(p), "l"(~0ull) : "memory");
+}
+
+// interior words [b, e) of one range := ~0, by the lane that owns the range: single words up to the first 32-byte boundary,
+// whole sectors (one 256-bit store each), single words after the last boundary.  A BED-sized interior is ~16 words: four
+// full-sector stores per lane, no shuffles, no per-range loop over the warp.
+__device__ __forceinline__ void fill_interior(uint64_t *__restrict__ w, int64_t b, int64_t e) {
+    while (b < e && (b & 3)) w[b++] = ~0ull;
+    for (; b + 4 <= e; b += 4) st_ones256(w + b);
+    while (b < e) w[b++] = ~0ull;
+}
+constexpr int64_t LANE_WORDS = 64;               // interiors up to 512 bytes are written by their own lane
+
+// DEFER_STATE: the bin states are not touched here; the caller runs k_mark_touched_bins afterwards.  (The per-range form
+// needs two integer divisions by the run-time bin size; on a whole file those were most of the kernel's instructions.)
+// AOS (bucketed, L2-resident targets): every lane writes its own interior -- the kernel is instruction-bound there and this
+// form needs no per-range loop over the warp (4.1 -> 3.2 ms per 50 M ranges, r02g).  Unbucketed (DRAM-bound) input keeps
+// the warp-wide coalesced sweep: scattered sector stores cost it more DRAM traffic than they save instructions (5.1 -> 6.3 ms).
+template <bool AOS, bool DEFER_STATE>
 __global__ void __launch_bounds__(256)
 k_set_ranges_multi(const SetDesc *__restrict__ descs, int nsets, const int32_t *__restrict__ which,
                    const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n) {
@@ -409,13 +429,17 @@ k_set_ranges_multi(const SetDesc *__restrict__ descs, int nsets, const int32_t *
                         atomicOr((unsigned long long *)words + w0, m0);
                         atomicOr((unsigned long long *)words + w1, m1);
                     }
-                    if (!d.flat) {
+                    if (!DEFER_STATE && !d.flat) {
                         int b1 = last / d.bin_size;
                         for (int b = s / d.bin_size; b <= b1; b++)
                             if (d.state[b] == BZ) d.state[b] = BA;     // benign race: every writer stores BA
                     }
                     mb = w0 + 1;
                     me = w1;
+                    if (AOS && me - mb <= LANE_WORDS) {     // the usual case: this lane writes its own interior
+                        fill_interior(words, mb, me);
+                        me = mb;
+                    }
                 }
             }
         }
@@ -428,6 +452,7 @@ k_set_ranges_multi(const SetDesc *__restrict__ descs, int nsets, const int32_t *
                 me = mb;
             }
         }
+        // medium interiors (512 B .. 32 KB): the warp sweeps them one after the other with coalesced stores
         unsigned has = __ballot_sync(0xffffffffu, me > mb);
         while (has) {
             int src = __ffs(has) - 1;
@@ -444,6 +469,42 @@ k_set_ranges_multi(const SetDesc *__restrict__ descs, int nsets, const int32_t *
             for (int64_t k = b + threadIdx.x; k < e; k += blockDim.x) w[k] = ~0ull;
         }
         __syncthreads();
+    }
+}
+
+// Deferred form of binBitsSetRange's bin allocation (binBits.c:104-126) after a batch of set_range calls: an ALL_ZERO bin
+// becomes allocated iff one of the ranges touched it, and -- since set_range only ever sets bits and an ALL_ZERO bin had
+// none -- iff it now holds a set bit.  One warp per bin ORs the bin's words (edges masked to the bin); the whole genome is
+// read once, streaming.  Bins in any other state are left alone (an ALL_ONE sentinel stays a sentinel, binBits.c:112-113).
+struct MarkDesc {
+    const uint64_t *words;
+    uint8_t *state;
+    int32_t bin_size, size, nbins, bin0;      // bin0: index of this set's first bin in the launch's global bin numbering
+};
+__global__ void __launch_bounds__(256)
+k_mark_touched_bins(const MarkDesc *__restrict__ descs, int nsets, int64_t nbins_total) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < nbins_total; g += nwarps) {
+        int lo = 0, hi = nsets - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int64_t)descs[mid].bin0 <= g) lo = mid; else hi = mid - 1;
+        }
+        const MarkDesc d = descs[lo];
+        const int b = (int)(g - d.bin0);
+        if (b >= d.nbins || d.state[b] != BZ) continue;
+        const int64_t p0 = (int64_t)b * d.bin_size, p1 = min(p0 + d.bin_size, (int64_t)d.size);
+        if (p0 >= p1) continue;
+        const int64_t w0 = p0 >> 6, w1 = (p1 - 1) >> 6;
+        unsigned long long any = 0;
+        for (int64_t w = w0 + lane; w <= w1; w += 32) {
+            unsigned long long x = __ldg((const unsigned long long *)d.words + w);
+            if (w == w0) x &= ~0ull << (p0 & 63);
+            if (w == w1 && (p1 & 63)) x &= (1ull << (p1 & 63)) - 1ull;
+            any |= x;
+        }
+        if (__ballot_sync(0xffffffffu, any != 0) && lane == 0) d.state[b] = BA;
     }
 }
 
@@ -470,94 +531,104 @@ __global__ void k_read_bits(const uint64_t *__restrict__ words, const int32_t *_
 // count_range x n  (binBits.c:130-178): rank table lookup, O(1) per query
 // ------------------------------------------------------------------------------------------------------------------
 // Rank lines.  A count_range query reads at two random positions of a genome of bitmaps (386 MB for hg38: three times
-// L2), so what it costs is DRAM lines.  A separate rank table (one entry per word or per sector) means two lines per
-// position -- the table's and the bitmap's -- and ncu (r02b) showed 264 B of DRAM reads per query.  Here the rank is
-// stored NEXT TO the bits it belongs to: the count structure is a copy of the bitmap cut into 64-byte lines
-//     line i = { rank_i : number of set bits before bit 448 i ; words 7 i .. 7 i + 6 of the bitmap }        (8 x uint64)
-// so rank(p) = line[p / 448].rank + popcount of that line's bits below p % 448: ONE 64-byte line per position, which is
-// also exactly what one L2 miss fetches.  Built lazily (one scan over 7-word popcounts + one interleaving pass, both
-// streaming) and invalidated by every mutation, like the table it replaces; costs 8/7 of the bitmap in HBM.
-constexpr int RL_WORDS = 7;                    // bitmap words per rank line
-constexpr uint32_t RL_BITS = 64u * RL_WORDS;   // 448
+// L2), so what it costs is DRAM sectors and the latency of fetching them.  A separate rank table (one entry per word or
+// per 256-bit block) means two sectors per position -- the table's and the bitmap's.  Here the rank is stored NEXT TO the
+// bits it belongs to: the count structure is a copy of the bitmap cut into 32-byte lines, one DRAM sector each,
+//     line i = { rank_i : set bits before bit 224 i ;  the bitmap's 32-bit pieces 7 i .. 7 i + 6 }          (8 x uint32)
+// (the bitmap is LSB-first, so as a uint32 array piece j holds bits 32 j .. 32 j + 31 and 224 = 7 x 32 keeps lines piece-
+// aligned).  rank(p) = line[p / 224].rank + popcount of that line's bits below p % 224: ONE sector and ONE independent
+// 256-bit load per position, two per query.  Built lazily (line popcounts -> one scan -> one interleaving pass, all
+// streaming; a whole genome in three launches) and invalidated by every mutation; costs 8/7 of the bitmap in HBM.
+// [r02f/r02g: 64-byte lines {rank, 7 x uint64} lost to the table they replaced -- 3.2 / 4.1 ms against 2.69 ms per 50 M
+//  queries -- because half the positions needed the line's second sector: a dependent load, or twice the DRAM sectors.]
+constexpr int RL_PIECES = 7;                   // 32-bit bitmap pieces per rank line
+constexpr uint32_t RL_BITS = 32u * RL_PIECES;  // 224
 
-struct PopcLine {                              // popcount of line i's words (scan input)
-    const uint64_t *w;
-    int64_t nwords, nlines;
-    __device__ __forceinline__ uint32_t operator()(int64_t i) const {
-        uint32_t c = 0;
-        if (i < nlines) {
+// popcount of line i's pieces (scan input); the bitmap is read as uint32 pieces, npieces = 2 * nwords_alloc
+__device__ __forceinline__ uint32_t line_popc(const uint32_t *__restrict__ pieces, int64_t npieces, int64_t nlines, int64_t i) {
+    uint32_t c = 0;
+    if (i < nlines) {
 #pragma unroll
-            for (int k = 0; k < RL_WORDS; k++) {
-                const int64_t j = i * RL_WORDS + k;
-                if (j < nwords) c += (uint32_t)__popcll(__ldg((const unsigned long long *)w + j));
-            }
-        }
-        return c;
-    }
-};
-
-__global__ void __launch_bounds__(256)
-k_rank_lines(const uint64_t *__restrict__ words, int64_t nwords, const uint32_t *__restrict__ prefix, int64_t nlines,
-             ulonglong2 *__restrict__ lines) {
-    // one thread per 16-byte quarter of a line: coalesced 128-bit stores, the bitmap read with plain 8-byte loads
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < (nlines + 1) * 4; q += stride) {
-        const int64_t i = q >> 2;
-        const int part = (int)(q & 3);                      // words 2*part, 2*part+1 of the line
-        unsigned long long v[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int k = 2 * part + h;                     // 0 = rank, 1..7 = bitmap words 7i .. 7i+6
-            if (k == 0) {
-                v[h] = prefix[i];
-            } else {
-                const int64_t j = i * RL_WORDS + (k - 1);
-                v[h] = (i < nlines && j < nwords) ? __ldg((const unsigned long long *)words + j) : 0ull;
-            }
-        }
-        st_stream(lines + q, make_ulonglong2(v[0], v[1]));
-    }
-}
-
-__device__ __forceinline__ void ld_sector(const uint64_t *p, unsigned long long &a, unsigned long long &b,
-                                          unsigned long long &c, unsigned long long &d) {
-    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-}
-
-// rank(p): set bits in [0, p)
-__device__ __forceinline__ uint32_t rank_at(const uint64_t *__restrict__ lines, uint32_t p) {
-    const uint32_t i = p / RL_BITS, o = p - i * RL_BITS;
-    const uint64_t *L = lines + 8 * (size_t)i;
-    unsigned long long r, d0, d1, d2;
-    ld_sector(L, r, d0, d1, d2);                            // rank + the line's first 192 bits
-    uint32_t c = (uint32_t)r;
-    if (o) {
-        const uint32_t k = o >> 6;
-        const unsigned long long m = (1ull << (o & 63)) - 1ull;
-        if (k < 3) {
-            c += (uint32_t)__popcll((k == 0 ? d0 : k == 1 ? d1 : d2) & m);
-            if (k > 0) c += (uint32_t)__popcll(d0);
-            if (k > 1) c += (uint32_t)__popcll(d1);
-        } else {
-            unsigned long long d3, d4, d5, d6;
-            ld_sector(L + 4, d3, d4, d5, d6);               // the other half of the same 64-byte line
-            c += (uint32_t)(__popcll(d0) + __popcll(d1) + __popcll(d2));
-            c += (uint32_t)__popcll((k == 3 ? d3 : k == 4 ? d4 : k == 5 ? d5 : d6) & m);
-            if (k > 3) c += (uint32_t)__popcll(d3);
-            if (k > 4) c += (uint32_t)__popcll(d4);
-            if (k > 5) c += (uint32_t)__popcll(d5);
+        for (int k = 0; k < RL_PIECES; k++) {
+            const int64_t j = i * RL_PIECES + k;
+            if (j < npieces) c += (uint32_t)__popc(__ldg(pieces + j));
         }
     }
     return c;
 }
 
+// every set's lines (its nlines + 1, sentinel included) are numbered consecutively across the call's sets: line popcounts
+// -> ONE 64-bit exclusive scan over all of them -> lines, with each set's own first prefix subtracted.  Three launches for
+// a whole genome (three per chromosome were launch-bound: 0.93 ms for hg38, r02f; 0.30 ms now).
+struct LineDesc {
+    const uint32_t *pieces;
+    uint32_t *lines;
+    int64_t npieces, nlines, line0;          // line0: global number of this set's line 0
+};
+__device__ __forceinline__ int line_owner(const LineDesc *__restrict__ d, int nsets, int64_t g) {
+    int lo = 0, hi = nsets - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (d[mid].line0 <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(256)
+k_line_popc_multi(const LineDesc *__restrict__ descs, int nsets, int64_t total, uint32_t *__restrict__ pc) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        const LineDesc d = descs[line_owner(descs, nsets, g)];
+        pc[g] = line_popc(d.pieces, d.npieces, d.nlines, g - d.line0);
+    }
+}
+__global__ void __launch_bounds__(256)
+k_rank_lines_multi(const LineDesc *__restrict__ descs, int nsets, int64_t total, const unsigned long long *__restrict__ prefix) {
+    // one thread per 16-byte half of a line: coalesced 128-bit stores
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total * 2; q += stride) {
+        const int64_t g = q >> 1;
+        const LineDesc d = descs[line_owner(descs, nsets, g)];
+        const int64_t i = g - d.line0;
+        const int half = (int)(q & 1);
+        uint32_t v[4];
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+            const int k = 4 * half + h;                     // 0 = rank, 1..7 = pieces 7i .. 7i+6
+            if (k == 0) {
+                v[h] = (uint32_t)(prefix[g] - prefix[d.line0]);
+            } else {
+                const int64_t j = i * RL_PIECES + (k - 1);
+                v[h] = (i < d.nlines && j < d.npieces) ? __ldg(d.pieces + j) : 0u;
+            }
+        }
+        reinterpret_cast<uint4 *>(d.lines)[i * 2 + half] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// rank(p): set bits in [0, p) -- one sector, one load
+__device__ __forceinline__ uint32_t rank_at(const uint32_t *__restrict__ lines, uint32_t p) {
+    const uint32_t i = p / RL_BITS, o = p - i * RL_BITS;
+    uint32_t d[8];
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+        : "l"(lines + 8 * (size_t)i));
+    uint32_t c = d[0];
+#pragma unroll
+    for (int k = 0; k < RL_PIECES; k++) {
+        const uint32_t lo = 32u * k;
+        const uint32_t m = o >= lo + 32u ? ~0u : (o > lo ? (1u << (o - lo)) - 1u : 0u);
+        c += (uint32_t)__popc(d[k + 1] & m);
+    }
+    return c;
+}
+
 // popcount of [s, s + c), c > 0
-__device__ __forceinline__ int32_t count_span(const uint64_t *__restrict__ lines, uint32_t s, uint32_t c) {
+__device__ __forceinline__ int32_t count_span(const uint32_t *__restrict__ lines, uint32_t s, uint32_t c) {
     return (int32_t)(rank_at(lines, s + c) - rank_at(lines, s));
 }
 
 __global__ void __launch_bounds__(256)
-k_count_ranges(const uint64_t *__restrict__ lines, const uint8_t *__restrict__ state,
+k_count_ranges(const uint32_t *__restrict__ lines, const uint8_t *__restrict__ state,
                int bin_size, int strict, const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n,
                int32_t *__restrict__ out, volatile long long *flag, long long seq) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -575,12 +646,12 @@ k_count_ranges(const uint64_t *__restrict__ lines, const uint8_t *__restrict__ s
 
 // genome-wide form: query i addresses bit set which[i] (the dict lookup `bitsets[chrom]` of scripts/bed_intersect.py:46-53)
 struct CountDesc {
-    const uint64_t *lines;       // rank lines (see above)
+    const uint32_t *lines;       // rank lines (see above)
     const uint8_t *state;
     int32_t bin_size, strict, size;
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 k_count_ranges_multi(const CountDesc *__restrict__ descs, int nsets, const int32_t *__restrict__ which,
                      const int32_t *__restrict__ start, const int32_t *__restrict__ count, int64_t n,
                      int32_t *__restrict__ out) {
@@ -844,7 +915,7 @@ k_group_stats(const int32_t *__restrict__ key, const int32_t *__restrict__ val, 
 
 // out[k] = popcount of set k, read off the last entry of its rank table
 struct TotalDesc {
-    const uint64_t *rank_last;       // rank word of the sentinel line = popcount of the whole bitmap
+    const uint32_t *rank_last;       // rank of the sentinel line = popcount of the whole bitmap
 };
 __global__ void k_gather_totals(const TotalDesc *__restrict__ d, int n, long long *__restrict__ out, int64_t out_stride) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -946,7 +1017,7 @@ int bxg_bits_clone(const bxg_bits_t *b, bxg_bits_t **out) {
     if (!b) return set_error(BXG_ERR_ARG, "null bitset handle");
     bxg_bits *n = new bxg_bits();
     n->size = b->size; n->bin_size = b->bin_size; n->nbins = b->nbins; n->flat = b->flat;
-    n->nwords = b->nwords; n->nwords_alloc = b->nwords_alloc;
+    n->nwords = b->nwords; n->nwords_alloc = b->nwords_alloc; n->maybe_one = b->maybe_one;
     BXG_CUDA(cudaMalloc(&n->words, (size_t)n->nwords_alloc * 8));
     BXG_CUDA(cudaMalloc(&n->state, (size_t)n->nbins));
     BXG_CUDA(cudaMemcpyAsync(n->words, b->words, (size_t)n->nwords_alloc * 8, cudaMemcpyDeviceToDevice, ctx().stream));
@@ -991,6 +1062,8 @@ int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int3
         return e ? atoi(e) : -1;
     }();
     const bool bucketed = bucket_mode == 1 || (bucket_mode != 0 && n >= (1 << 20) && total_bits / 8 > c.l2_bytes / 2);
+    // a whole file at once: mark the touched bins afterwards from the bitmaps (one streaming pass) instead of per range
+    const bool defer = bucketed || (int64_t)n * 64 >= total_bits / 64;
     int kshift = 0, group = 0;
     if (bucketed) {
         if (nsets > 128) {
@@ -1010,7 +1083,7 @@ int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int3
         }
     }
     void *d_desc;
-    BXG_TRY(scratch(3, sizeof(SetDesc) * (size_t)nsets, &d_desc));
+    BXG_TRY(scratch(3, (sizeof(SetDesc) + sizeof(MarkDesc)) * (size_t)nsets, &d_desc));      // [SetDesc x nsets | MarkDesc x <= nsets]
     BXG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(SetDesc) * (size_t)nsets, cudaMemcpyHostToDevice, c.stream));
     const void *dw, *ds, *dc;
     BXG_TRY(stage_in(0, which, (size_t)n * 4, loc, &dw));
@@ -1041,11 +1114,30 @@ int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int3
                                                  (const RangeTriple *)d_v0, (RangeTriple *)d_v1, n, 0, 8, c.stream));
         prof_end();
         c.launches += 3;
-        BXG_LAUNCH((k_set_ranges_multi<true>), grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets,
+        BXG_LAUNCH((k_set_ranges_multi<true, true>), grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets,
                    (const int32_t *)d_v1, (const int32_t *)nullptr, (const int32_t *)nullptr, n);
-    } else {
-        BXG_LAUNCH((k_set_ranges_multi<false>), grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets,
+    } else if (defer) {
+        BXG_LAUNCH((k_set_ranges_multi<false, true>), grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets,
                    (const int32_t *)dw, (const int32_t *)ds, (const int32_t *)dc, n);
+    } else {
+        BXG_LAUNCH((k_set_ranges_multi<false, false>), grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets,
+                   (const int32_t *)dw, (const int32_t *)ds, (const int32_t *)dc, n);
+    }
+    if (defer) {                                    // bin states of the whole batch in one streaming pass over the bitmaps
+        static MarkDesc h_mark[BATCH_MAX_PAIRS];
+        int64_t nb = 0;
+        int m = 0;
+        for (int k = 0; k < nsets; k++) {
+            bxg_bits *b = sets[k];
+            if (!b || b->flat) continue;
+            h_mark[m++] = MarkDesc{b->words, b->state, b->bin_size, b->size, b->nbins, (int32_t)nb};
+            nb += b->nbins;
+        }
+        if (m > 0) {
+            void *d_mark = (char *)d_desc + sizeof(SetDesc) * (size_t)nsets;
+            BXG_CUDA(cudaMemcpyAsync(d_mark, h_mark, sizeof(MarkDesc) * (size_t)m, cudaMemcpyHostToDevice, c.stream));
+            BXG_LAUNCH(k_mark_touched_bins, grid_for(cdiv(nb * 32, 256), 8), 256, 0, (const MarkDesc *)d_mark, m, nb);
+        }
     }
     for (int k = 0; k < nsets; k++)
         if (sets[k]) invalidate(sets[k]);
@@ -1102,6 +1194,7 @@ int bxg_bits_and(bxg_bits_t *a, const bxg_bits_t *b) {
 int bxg_bits_or(bxg_bits_t *a, const bxg_bits_t *b) {
     BXG_TRY(check_pair(a, b));
     if (a == b) return BXG_OK;
+    a->maybe_one = a->maybe_one || b->maybe_one;          // a takes over b's ALL_ONE sentinels (binBits.c:264-296)
     return binop<OP_OR, false>(a, b, nullptr);
 }
 int bxg_bits_xor(bxg_bits_t *a, const bxg_bits_t *b) {
@@ -1119,6 +1212,7 @@ int bxg_bits_not(bxg_bits_t *a) {
     int64_t nvec = a->nwords_alloc / 2;
     BXG_LAUNCH(k_not, stream_grid(nvec, 1), BINOP_THREADS, 0, (ulonglong2 *)a->words, nvec, a->nwords,
                tail_mask_of(a->size), a->flat ? nullptr : a->state, a->nbins);
+    if (!a->flat) a->maybe_one = true;          // ALL_ZERO bins turn into ALL_ONE sentinels (binBits.c:298-317)
     invalidate(a);
     return BXG_OK;
 }
@@ -1165,6 +1259,7 @@ int bxg_bits_binop_batch(int op, bxg_bits_t *const *a, const bxg_bits_t *const *
         d.flat = a[p]->flat;
         d.chunk0 = nchunks;
         nchunks += cdiv(d.nvec, BATCH_CHUNK_VEC);
+        if (op == OP_OR) a[p]->maybe_one = a[p]->maybe_one || b[p]->maybe_one;
         invalidate(a[p]);
     }
     void *d_desc, *d_cnt;
@@ -1202,27 +1297,55 @@ int bxg_bits_count_all(const bxg_bits_t *b, int64_t *count) {
     return fetch_counter(count);
 }
 
+struct CastU32ToU64 {
+    __device__ __forceinline__ unsigned long long operator()(uint32_t v) const { return (unsigned long long)v; }
+};
+
+// rank lines of every set of the call that needs them, in three launches (see k_line_popc_multi)
+static int build_rank_multi(bxg_bits_t *const *sets, int32_t nsets) {
+    static LineDesc h_line[BATCH_MAX_PAIRS];
+    int m = 0;
+    int64_t total = 0;
+    for (int k = 0; k < nsets; k++) {
+        bxg_bits *b = sets[k];
+        if (!b || b->rank_valid) continue;
+        bool dup = false;
+        for (int q = 0; q < m && !dup; q++) dup = h_line[q].pieces == (const uint32_t *)b->words;   // listed twice: built once
+        if (dup) continue;
+        const int64_t npieces = 2 * b->nwords_alloc, nlines = cdiv(2 * b->nwords, RL_PIECES);
+        if (!b->rank) BXG_CUDA(cudaMalloc(&b->rank, (size_t)(nlines + 1) * 32));
+        b->nlines = nlines;
+        h_line[m++] = LineDesc{(const uint32_t *)b->words, b->rank, npieces, nlines, total};
+        total += nlines + 1;
+    }
+    if (m == 0) return BXG_OK;
+    Context &c = ctx();
+    void *d_line, *d_pc, *d_prefix, *tmp;
+    BXG_TRY(scratch(3, sizeof(LineDesc) * (size_t)m + 64 * (size_t)BATCH_MAX_PAIRS, &d_line));
+    d_line = (char *)d_line + 64 * (size_t)BATCH_MAX_PAIRS;       // (the caller's own descriptor table sits in front)
+    BXG_TRY(scratch(6, (size_t)total * 4, &d_pc));
+    BXG_TRY(scratch(4, (size_t)total * 8, &d_prefix));
+    BXG_CUDA(cudaMemcpyAsync(d_line, h_line, sizeof(LineDesc) * (size_t)m, cudaMemcpyHostToDevice, c.stream));
+    BXG_LAUNCH(k_line_popc_multi, grid_for(cdiv(total, 256), 8), 256, 0, (const LineDesc *)d_line, m, total, (uint32_t *)d_pc);
+    cub::TransformInputIterator<unsigned long long, CastU32ToU64, const uint32_t *> it((const uint32_t *)d_pc, CastU32ToU64());
+    size_t tmp_bytes = 0;
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, (unsigned long long *)d_prefix, total, c.stream));
+    BXG_TRY(scratch(7, tmp_bytes, &tmp));
+    prof_begin("cub::DeviceScan::ExclusiveSum(rank lines)");
+    BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, (unsigned long long *)d_prefix, total, c.stream));
+    prof_end();
+    c.launches += 2;
+    BXG_LAUNCH(k_rank_lines_multi, grid_for(cdiv(total * 2, 256), 8), 256, 0, (const LineDesc *)d_line, m, total,
+               (const unsigned long long *)d_prefix);
+    for (int k = 0; k < nsets; k++)
+        if (sets[k]) sets[k]->rank_valid = true;
+    return BXG_OK;
+}
+
 static int build_rank(bxg_bits *b) {
     if (b->rank_valid) return BXG_OK;
-    Context &c = ctx();
-    const int64_t nlines = cdiv(b->nwords, RL_WORDS), n = nlines + 1;
-    if (!b->rank) BXG_CUDA(cudaMalloc(&b->rank, (size_t)n * 64));
-    b->nlines = nlines;
-    void *d_prefix, *tmp;
-    BXG_TRY(scratch(6, (size_t)n * 4, &d_prefix));
-    cub::CountingInputIterator<int64_t> idx(0);
-    cub::TransformInputIterator<uint32_t, PopcLine, cub::CountingInputIterator<int64_t>> it(idx, PopcLine{b->words, b->nwords, nlines});
-    size_t tmp_bytes = 0;
-    BXG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, (uint32_t *)d_prefix, n, c.stream));
-    BXG_TRY(scratch(7, tmp_bytes, &tmp));
-    prof_begin("cub::DeviceScan::ExclusiveSum(rank)");
-    BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, (uint32_t *)d_prefix, n, c.stream));
-    prof_end();
-    c.launches += 2;   // CUB's single-pass scan: init + scan kernels
-    BXG_LAUNCH(k_rank_lines, grid_for(cdiv(n * 4, 256), 8), 256, 0, b->words, b->nwords, (const uint32_t *)d_prefix, nlines,
-               (ulonglong2 *)b->rank);
-    b->rank_valid = true;
-    return BXG_OK;
+    bxg_bits_t *one[1] = {b};
+    return build_rank_multi(one, 1);
 }
 
 int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *count, int64_t n, int32_t *out,
@@ -1234,7 +1357,7 @@ int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *co
         memcpy(zc_host(0), start, (size_t)n * 4);
         memcpy(zc_host(1), count, (size_t)n * 4);
         const long long seq = zc_next_seq();
-        BXG_LAUNCH(k_count_ranges, 1, 64, 0, b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0,
+        BXG_LAUNCH(k_count_ranges, 1, 64, 0, b->rank, b->state, b->bin_size, (strict && !b->flat && b->maybe_one) ? 1 : 0,
                    (const int32_t *)zc_device(0), (const int32_t *)zc_device(1), n, (int32_t *)zc_device(2), zc_flag_device(), seq);
         BXG_TRY(zc_wait(seq));
         memcpy(out, zc_host(2), (size_t)n * 4);
@@ -1250,7 +1373,7 @@ int bxg_bits_count_ranges(bxg_bits_t *b, const int32_t *start, const int32_t *co
         dout = (int32_t *)t;
     }
     BXG_LAUNCH(k_count_ranges, grid_for(cdiv(n, 256), 8), 256, 0, b->rank, b->state, b->bin_size,
-               (strict && !b->flat) ? 1 : 0, (const int32_t *)ds, (const int32_t *)dc, n, dout, (volatile long long *)nullptr, 0ll);
+               (strict && !b->flat && b->maybe_one) ? 1 : 0, (const int32_t *)ds, (const int32_t *)dc, n, dout, (volatile long long *)nullptr, 0ll);
     if (loc == BXG_HOST) {
         BXG_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx().stream));
         BXG_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -1264,14 +1387,14 @@ int bxg_bits_count_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const in
     if (nsets <= 0 || nsets > BATCH_MAX_PAIRS) return set_error(BXG_ERR_ARG, "nsets must be in [1, %d]", BATCH_MAX_PAIRS);
     if (n <= 0) return BXG_OK;
     static CountDesc h_desc[BATCH_MAX_PAIRS];
+    BXG_TRY(build_rank_multi(sets, nsets));
     for (int k = 0; k < nsets; k++) {
         bxg_bits *b = sets[k];
         if (!b) {                                     // `fields[0] in bitsets` is false (bed_intersect.py:53): count 0
             h_desc[k] = CountDesc{nullptr, nullptr, 1, 0, 0};
             continue;
         }
-        BXG_TRY(build_rank(b));
-        h_desc[k] = CountDesc{b->rank, b->state, b->bin_size, (strict && !b->flat) ? 1 : 0, b->size};
+        h_desc[k] = CountDesc{b->rank, b->state, b->bin_size, (strict && !b->flat && b->maybe_one) ? 1 : 0, b->size};
     }
     Context &c = ctx();
     void *d_desc;
@@ -1301,6 +1424,7 @@ int bxg_bits_clear(bxg_bits_t *b) {
     Context &c = ctx();
     BXG_CUDA(cudaMemsetAsync(b->words, 0, (size_t)b->nwords_alloc * 8, c.stream));
     BXG_CUDA(cudaMemsetAsync(b->state, BZ, (size_t)b->nbins, c.stream));
+    b->maybe_one = false;
     invalidate(b);
     return BXG_OK;
 }
@@ -1312,14 +1436,14 @@ int bxg_bits_count_all_multi(bxg_bits_t *const *sets, int32_t nsets, int64_t *ou
     if (!out || out_stride < 1 || (loc == BXG_HOST && out_stride != 1))
         return set_error(BXG_ERR_ARG, "bad output (host output needs out_stride == 1)");
     static TotalDesc h_desc[BATCH_MAX_PAIRS];
+    BXG_TRY(build_rank_multi(sets, nsets));
     for (int k = 0; k < nsets; k++) {
         bxg_bits *b = sets[k];
         if (!b) {
             h_desc[k] = TotalDesc{nullptr};
             continue;
         }
-        BXG_TRY(build_rank(b));
-        h_desc[k] = TotalDesc{b->rank + 8 * (size_t)b->nlines};
+        h_desc[k] = TotalDesc{b->rank + 8 * (size_t)b->nlines};        // word 0 of the sentinel line
     }
     Context &c = ctx();
     void *d_desc;
@@ -1530,6 +1654,7 @@ int bxg_bits_import_words(bxg_bits_t *b, const uint64_t *in) {
     BXG_CUDA(cudaMemcpyAsync(b->words, in, (size_t)b->nwords * 8, cudaMemcpyHostToDevice, c.stream));
     BXG_LAUNCH(k_mask_tail, 1, 32, 0, b->words, b->nwords, b->nwords_alloc, tail_mask_of(b->size));
     BXG_LAUNCH(k_fill_u8, grid_for(cdiv(b->nbins, 256), 1), 256, 0, b->state, (int64_t)b->nbins, (uint8_t)BA);
+    b->maybe_one = false;
     BXG_CUDA(cudaStreamSynchronize(c.stream));
     invalidate(b);
     return BXG_OK;
