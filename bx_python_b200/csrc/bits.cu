@@ -609,6 +609,8 @@ k_rank_lines_multi(const LineDesc *__restrict__ descs, int nsets, int64_t total,
 __device__ __forceinline__ uint32_t rank_at(const uint32_t *__restrict__ lines, uint32_t p) {
     const uint32_t i = p / RL_BITS, o = p - i * RL_BITS;
     uint32_t d[8];
+    // (r02i/r02j: the load flavour -- .nc, L1::no_allocate, L2 evict_last / evict_first policies, .cg -- and
+    //  cudaLimitMaxL2FetchGranularity 32/64/128 leave time and DRAM traffic unchanged: ~3 DRAM sectors per missed sector)
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
         : "l"(lines + 8 * (size_t)i));

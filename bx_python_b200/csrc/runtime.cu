@@ -142,12 +142,20 @@ int bxg_init(int device) {
     c.l2_bytes = p.l2CacheSize;
     {
         // The query kernels of this library (find, count_range, set_range) read single 32-byte sectors at random from
-        // working sets larger than L2; the default 64-byte L2 fetch granularity doubles their DRAM traffic (ncu,
-        // profiles/r02b).  BXB200_L2_FETCH=64|128 restores a larger granularity for A/B runs.
+        // working sets larger than L2, so the smallest L2 fetch granularity is asked for.  Measured on B200 (r02j): the
+        // limit is accepted (32 / 64 / 128 read back) and changes neither time nor DRAM sectors of those kernels;
+        // kept because it is the documented intent.  BXB200_L2_FETCH=64|128 for A/B runs, BXB200_DEBUG prints the value.
         const char *e = getenv("BXB200_L2_FETCH");
         const size_t g = e ? (size_t)atoi(e) : 32;
         if (g == 32 || g == 64 || g == 128) {
-            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g) != cudaSuccess) cudaGetLastError();
+            cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+            if (le != cudaSuccess) cudaGetLastError();
+            if (getenv("BXB200_DEBUG")) {
+                size_t got = 0;
+                cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+                fprintf(stderr, "[bxb200] cudaLimitMaxL2FetchGranularity: asked %zu -> %s, now %zu\n", g,
+                        cudaGetErrorString(le), got);
+            }
         }
     }
     BXG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
