@@ -244,7 +244,11 @@ def run_reference(args):
 def workload_config(args, world):
     return {"workload": "find: 10M hg38-shaped intervals (24 chromosomes) vs 10M queries per GPU, ordered CSR hit lists",
             "n_intervals": args.n_db, "n_queries": args.nq * world, "queries_per_gpu": args.nq,
-            "sharding": "per-chromosome LPT, no data-path collective; NCCL all-reduce of per-chromosome hit counts",
+            "sharding": "per-chromosome LPT, no data-path collective; NCCL all-reduce of the per-chromosome counters "
+                        "(hit counts here; inside the device-timed step for configs[3]/[4], see roofline.c4_* / c5_*)",
+            "other_configs": "roofline.bitset_and_* = configs[2] (24 x BinnedBitSet(250 Mbp) AND), roofline.c4_* = configs[3] "
+                             "(bed_intersect 50M x 50M), roofline.c5_* = configs[4] (aggregate 100M scores / 5M windows): all "
+                             "ranks, chromosomes sharded, parity against the compiled reference's full-size goldens in the same run",
             "l2_policy": "inputs larger than L2 (index 160 MB + queries 120 MB + results >300 MB per step vs 126 MB L2)"}
 
 
