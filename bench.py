@@ -592,6 +592,10 @@ def run_ours(args):
            # what the box sustains when all ranks copy at once, and how much of it the e2e call uses (per rank)
            "copy_ceiling_gbs_per_rank": probe["bidir_gbs_min"], "copy_ceiling_gbs_aggregate": probe["bidir_gbs_sum"],
            "copy_gbs_achieved_per_rank": e2e_gbs_rank,
+           # the call is device-to-host bound: the slowest rank's D2H rate while every rank copies down, and what the call
+           # needs of it (its result bytes / the step time)
+           "d2h_ceiling_gbs_slowest_rank": probe["d2h_gbs_min"], "d2h_ceiling_gbs_fastest_rank": probe["d2h_gbs_max"],
+           "d2h_gbs_achieved_per_rank": (off_bytes * (nq + 1) + 4 * hits_total) / (nq / (e2e_value / world)) / 1e9,
            "frac_of_copy_ceiling": e2e_gbs_rank / probe["bidir_gbs_min"] if probe["bidir_gbs_min"] else None,
            "count_only_value": e2e_count, "count_only_h2d_bytes_per_step": int(12 * nq),
            "count_only_d2h_bytes_per_step": int(4 * nq)}
