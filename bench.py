@@ -347,6 +347,15 @@ def run_ours(args):
         step_dev()
     timer.stop()
     single_pass_ms = timer.elapsed_ms() / args.steps
+    # ... and the three passes with the count of chunk k+1 overlapping the fill of chunk k on a second stream
+    check(L.bxg_set_find_mode(2))
+    for _ in range(2):
+        step_dev()
+    timer.start()
+    for _ in range(args.steps):
+        step_dev()
+    timer.stop()
+    overlap_ms = timer.elapsed_ms() / args.steps
     check(L.bxg_set_find_mode(-1))
     step_dev()
 
@@ -480,7 +489,8 @@ def run_ours(args):
     extra = {"build_ms": min(build_ms), "hits_per_step": hits_all, "hits_per_query": hits_all / q_all,
              "per_chrom_hits_checksum": int((per_chrom * np.arange(1, 25)).sum()), "parity_spot_check": parity,
              "e2e_serial_copies": e2e_serial, "e2e_int64_offsets": e2e_i64, "e2e_count_only": e2e_count,
-             "single_pass_kernel_ms_per_step": single_pass_ms, "sorted_queries_ms_per_step": sorted_ms,
+             "single_pass_kernel_ms_per_step": single_pass_ms, "three_pass_overlapped_ms_per_step": overlap_ms,
+             "sorted_queries_ms_per_step": sorted_ms,
              "copy_probe": probe, "strong_scaling": strong}
     del h_off, h_hits, h_cnt, h_qt, h_qs, h_qe, d_qt, d_qs, d_qe
     forest = None                                          # free the index before the bitmap / score legs

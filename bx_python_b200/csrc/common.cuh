@@ -14,6 +14,8 @@ struct Context {
     int sm_count = 0;
     int64_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_override = nullptr;   // when set, BXG_LAUNCH issues on this stream (overlapped find pipeline)
+    int cta_cap = 0;                          // when > 0, grid_for() allows at most this many CTAs per SM
     int64_t launches = 0;
     // grow-only device scratch (CUB temp storage, staged host arrays, partials)
     void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -54,12 +56,14 @@ int scratch(int slot, size_t bytes, void **out);
 // optional per-kernel CUDA-event timing (bxg_profile_enable / bxg_profile_report); no-ops when disabled
 void prof_begin(const char *name);
 void prof_end();
+bool prof_enabled();
+static inline cudaStream_t launch_stream() { return ctx().stream_override ? ctx().stream_override : ctx().stream; }
 
 // every kernel launch of the library goes through this so bench.py can report gpu_launches
 #define BXG_LAUNCH(kernel, grid, block, smem, ...)                                   \
     do {                                                                             \
         bxg::prof_begin(#kernel);                                                    \
-        kernel<<<(grid), (block), (smem), bxg::ctx().stream>>>(__VA_ARGS__);         \
+        kernel<<<(grid), (block), (smem), bxg::launch_stream()>>>(__VA_ARGS__);      \
         bxg::prof_end();                                                             \
         bxg::ctx().launches++;                                                       \
         BXG_CUDA(cudaGetLastError());                                                \
@@ -69,6 +73,7 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // grid size for a grid-stride kernel: enough CTAs to cover `work_items / per_cta`, capped at `waves` full waves
 static inline int grid_for(int64_t ctas_needed, int ctas_per_sm) {
+    if (ctx().cta_cap > 0 && ctas_per_sm > ctx().cta_cap) ctas_per_sm = ctx().cta_cap;
     int64_t cap = (int64_t)ctx().sm_count * ctas_per_sm;
     if (ctas_needed < 1) ctas_needed = 1;
     return (int)(ctas_needed < cap ? ctas_needed : cap);

@@ -648,13 +648,16 @@ __device__ __forceinline__ void fill_query(const IndexView &ix, uint32_t lo_raw,
 __global__ void __launch_bounds__(FIND_THREADS, FILL_MIN_CTAS)
 k_fill_staged(const __grid_constant__ IndexView ix, const int32_t *__restrict__ qs_, int64_t nq, const int32_t *__restrict__ lo_,
               const int32_t *__restrict__ hi_, const unsigned long long *__restrict__ mask_, const int64_t *__restrict__ off,
-              int32_t *__restrict__ hits) {
+              int32_t *__restrict__ hits, int64_t hits_cap) {
     __shared__ int32_t stage[FIND_THREADS / 32][FILL_STAGE];
     const int lane = threadIdx.x & 31;
     int32_t *buf = stage[threadIdx.x >> 5];
     const uint32_t buf_a = (uint32_t)__cvta_generic_to_shared(buf);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t off_end = off[nq];
+    // launched speculatively, before the host knows the total: if the hits do not fit the buffer, do nothing -- the host
+    // sees the total a moment later, grows the buffer and launches the fill again
+    if (off_end > hits_cap) return;
     for (int64_t qw = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); qw < nq; qw += stride) {   // warp-uniform
         const int64_t q = qw + lane;
         const bool valid = q < nq;
@@ -902,18 +905,23 @@ static int launch_count(bxg_itree *t, const int32_t *dqt, const int32_t *dqs, co
 }
 
 // pass B over queries [q0, q0+nq): writes hits at the (global) CSR offsets d_off[q0..]
-static int launch_fill(bxg_itree *t, const int32_t *dqs, int64_t nq, int64_t q0 = 0) {
-    int occ = 0;
+static bool fill_is_staged() {
     static const bool staged = [] {
         const char *e = getenv("BXB200_FILL_STAGED");     // 0: direct stores (k_find<true>), for A/B measurements
         return !(e && e[0] == '0');
     }();
+    return staged;
+}
+
+static int launch_fill(bxg_itree *t, const int32_t *dqs, int64_t nq, int64_t q0 = 0) {
+    int occ = 0;
+    const bool staged = fill_is_staged();
     if (staged) {
         BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fill_staged, FIND_THREADS, 0));
         int grid = grid_for(cdiv(nq, FIND_THREADS), occ > 0 ? occ : 1);
         BXG_LAUNCH(k_fill_staged, grid, FIND_THREADS, 0, t->view(), dqs + q0, nq, (const int32_t *)(t->d_lo + q0),
                    (const int32_t *)(t->d_hi + q0), (const unsigned long long *)(t->d_mask + q0),
-                   (const int64_t *)(t->d_off + q0), t->d_hits);
+                   (const int64_t *)(t->d_off + q0), t->d_hits, t->hits_cap);
         return BXG_OK;
     }
     BXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_find<true, 0>, FIND_THREADS, 0));
@@ -1243,12 +1251,113 @@ static int find_three_pass(bxg_itree_t *t, const int32_t *qtree, const int32_t *
     BXG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, t->d_off, nq + 1, c.stream));
     prof_end();
     c.launches += 2;
+    // pass B: fill (reuses lo / masks of pass A).  It is launched BEFORE the host reads the total -- the kernel checks the
+    // total against the buffer it was given and backs off if it does not fit -- so the usual step has no host round trip
+    // between the scan and the fill; only a call that outgrows the hit buffer pays the sync + regrow + second launch.
+    const bool staged = fill_is_staged();
+    const int64_t cap_before = t->hits_cap;
+    if (staged && cap_before > 0) BXG_TRY(launch_fill(t, dqs, nq));
     BXG_CUDA(cudaMemcpyAsync(c.mailbox + 5, t->d_off + nq, 8, cudaMemcpyDeviceToHost, c.stream));
     BXG_CUDA(cudaStreamSynchronize(c.stream));
     t->total = c.mailbox[5];
-    BXG_TRY(grow_hits(t, t->total, false));
-    // pass B: fill (reuses lo/hi of pass A)
-    if (t->total > 0) BXG_TRY(launch_fill(t, dqs, nq));
+    if (!(staged && cap_before > 0) || t->total > cap_before) {
+        BXG_TRY(grow_hits(t, t->total, false));
+        if (t->total > 0) BXG_TRY(launch_fill(t, dqs, nq));
+    }
+    if (total) *total = t->total;
+    return BXG_OK;
+}
+
+// Device-resident find with the count and the fill of different chunks OVERLAPPED.  The two kernels are bound by different
+// things -- the count pass by the latency of dependent random sectors (L1 wavefront pipe ~40 % busy), the staged fill by
+// L1 wavefronts (84 %) -- so run back to back each leaves most of the SM idle half the time.  Here the queries are cut into
+// a few chunks; chunk k is counted and scanned on the library stream (the scan starts from the previous chunk's end
+// offset, read on the device) while chunk k-1 is filled on a second stream, each kernel launched with a share of the SM's
+// CTA slots so that both are resident.  Same CSR, same order; the fill checks the hit buffer's capacity itself (see
+// k_fill_staged), the host learns the total at the end and re-runs the fills only if the buffer was too small.
+static int ensure_pipeline(bxg_itree *t);
+
+static void overlap_shares(int *count_ctas, int *fill_ctas, int *nchunks) {
+    static int cc = 0, fc = 0, nc = 0;
+    if (!cc) {
+        cc = 4; fc = 3; nc = 4;
+        const char *e = getenv("BXB200_OVERLAP");                 // "count_ctas,fill_ctas,chunks"
+        if (e) sscanf(e, "%d,%d,%d", &cc, &fc, &nc);
+        cc = std::max(1, std::min(8, cc));
+        fc = std::max(1, std::min(8, fc));
+        nc = std::max(2, std::min((int)bxg_itree::MAX_CHUNKS, nc));
+    }
+    *count_ctas = cc; *fill_ctas = fc; *nchunks = nc;
+}
+
+static int find_three_pass_overlap(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,
+                                   int loc, int64_t *total) {
+    Context &c = ctx();
+    BXG_TRY(ensure_pipeline(t));
+    BXG_TRY(ensure_query_buffers(t, nq));
+    t->nq = nq;
+    t->total = 0;
+    const int32_t *dqt, *dqs, *dqe;
+    BXG_TRY(stage_queries(t, qtree, qs, qe, nq, loc, &dqt, &dqs, &dqe));
+    int count_ctas, fill_ctas, nchunks;
+    overlap_shares(&count_ctas, &fill_ctas, &nchunks);
+    const int64_t per = cdiv(cdiv(nq, nchunks), FIND_THREADS) * FIND_THREADS;
+    nchunks = (int)cdiv(nq, per);
+    size_t tmp_bytes = 0;
+    {
+        cub::CountingInputIterator<int64_t> idx(0);
+        cub::TransformInputIterator<int64_t, ChunkCount, cub::CountingInputIterator<int64_t>> it(idx, ChunkCount{t->d_cnt, per});
+        BXG_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp_bytes, it, t->d_off, cub::Sum(),
+                                                cub::FutureValue<int64_t>(t->d_off), per + 1, c.stream));
+    }
+    void *tmp;
+    BXG_TRY(scratch(7, tmp_bytes, &tmp));
+    BXG_CUDA(cudaMemsetAsync(t->d_off, 0, 8, c.stream));
+    if (t->hits_cap == 0) BXG_TRY(grow_hits(t, 8 * nq + 1024, false));      // first guess; exact after one overflow
+    auto fills = [&](cudaStream_t st, bool wait_scans) -> int {
+        for (int k = 0; k < nchunks; k++) {
+            const int64_t q0 = k * per, n = std::min(per, nq - q0);
+            if (wait_scans) BXG_CUDA(cudaStreamWaitEvent(st, t->ev_scan[k], 0));
+            c.stream_override = st;
+            c.cta_cap = wait_scans ? fill_ctas : 0;
+            const int r = launch_fill(t, dqs, n, q0);
+            c.stream_override = nullptr;
+            c.cta_cap = 0;
+            BXG_TRY(r);
+        }
+        return BXG_OK;
+    };
+    for (int k = 0; k < nchunks; k++) {
+        const int64_t q0 = k * per, n = std::min(per, nq - q0);
+        c.cta_cap = count_ctas;
+        const int r = launch_count(t, dqt, dqs, dqe, n, nullptr, q0);
+        c.cta_cap = 0;
+        BXG_TRY(r);
+        cub::CountingInputIterator<int64_t> idx(0);
+        cub::TransformInputIterator<int64_t, ChunkCount, cub::CountingInputIterator<int64_t>> it(idx, ChunkCount{t->d_cnt + q0, n});
+        size_t tb = tmp_bytes;
+        BXG_CUDA(cub::DeviceScan::ExclusiveScan(tmp, tb, it, t->d_off + q0, cub::Sum(),
+                                                cub::FutureValue<int64_t>(t->d_off + q0), n + 1, c.stream));
+        c.launches += 2;
+        BXG_CUDA(cudaEventRecord(t->ev_scan[k], c.stream));
+        // fill of this chunk on the second stream, as soon as its offsets exist (it overlaps the next chunk's count)
+        BXG_CUDA(cudaStreamWaitEvent(t->s_out, t->ev_scan[k], 0));
+        c.stream_override = t->s_out;
+        c.cta_cap = fill_ctas;
+        const int rf = launch_fill(t, dqs, n, q0);
+        c.stream_override = nullptr;
+        c.cta_cap = 0;
+        BXG_TRY(rf);
+    }
+    BXG_CUDA(cudaEventRecord(t->ev_fill[0], t->s_out));
+    BXG_CUDA(cudaStreamWaitEvent(c.stream, t->ev_fill[0], 0));            // later work on the library stream sees the hits
+    BXG_CUDA(cudaMemcpyAsync(c.mailbox + 5, t->d_off + nq, 8, cudaMemcpyDeviceToHost, c.stream));
+    BXG_CUDA(cudaStreamSynchronize(c.stream));
+    t->total = c.mailbox[5];
+    if (t->total > t->hits_cap) {                                         // the fills backed off (at least the last one)
+        BXG_TRY(grow_hits(t, t->total, false));
+        BXG_TRY(fills(c.stream, false));
+    }
     if (total) *total = t->total;
     return BXG_OK;
 }
@@ -1592,13 +1701,26 @@ static int g_find_mode = -2;
 static int find_mode() {
     if (g_find_mode == -2) {
         const char *e = getenv("BXB200_FIND_MODE");
-        g_find_mode = !e ? -1 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : -1));
+        g_find_mode = !e ? -1 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : (e[0] == '2' ? 2 : -1)));
     }
     return g_find_mode;
 }
 
+// Measured on B200 (profiles/r02m): the overlapped pipeline LOSES -- 0.77-0.90 ms per 10 M queries against 0.554 ms for the
+// serial passes, for every split of the CTA slots (count,fill = 4,3 / 5,2 / 3,3 / 4,4 / 3,4) and 4-8 chunks: with a share
+// of the SM each kernel slows down by more than the overlap wins, and every chunk adds a scan and three launches.  So auto
+// mode keeps the serial form; BXB200_FIND_OVERLAP=1 (or find mode 2) selects the pipeline for A/B runs.
+static bool overlap_default() {
+    static const bool on = [] {
+        const char *e = getenv("BXB200_FIND_OVERLAP");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 int bxg_set_find_mode(int mode) {
-    if (mode < -1 || mode > 1) return set_error(BXG_ERR_ARG, "find mode must be -1 (auto), 0 (three-pass) or 1 (single-pass)");
+    if (mode < -1 || mode > 2)
+        return set_error(BXG_ERR_ARG, "find mode must be -1 (auto), 0 (three-pass), 1 (single-pass) or 2 (three-pass, count/fill overlapped)");
     g_find_mode = mode;
     return BXG_OK;
 }
@@ -1724,7 +1846,12 @@ int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, cons
                    int64_t *total) {
     if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
     if (nq < 0) return set_error(BXG_ERR_ARG, "nq < 0");
-    return find_mode() == 1 ? find_fused(t, qtree, qs, qe, nq, loc, total) : find_three_pass(t, qtree, qs, qe, nq, loc, total);
+    const int mode = find_mode();
+    if (mode == 1) return find_fused(t, qtree, qs, qe, nq, loc, total);
+    // overlapped count / fill for large batches (mode 2, or auto); the serial three-pass form when per-kernel profiling is
+    // on (each kernel timed alone is what the roofline entries quote) and for the direct-store fill variant
+    const bool overlap = (mode == 2 || (mode == -1 && overlap_default())) && nq >= (1 << 20) && !prof_enabled() && fill_is_staged();
+    return overlap ? find_three_pass_overlap(t, qtree, qs, qe, nq, loc, total) : find_three_pass(t, qtree, qs, qe, nq, loc, total);
 }
 
 int bxg_itree_find_host(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int64_t nq,

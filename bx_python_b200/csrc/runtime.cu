@@ -93,6 +93,8 @@ static cudaEvent_t prof_event() {
     return e;
 }
 
+bool prof_enabled() { return g_prof_on; }
+
 void prof_begin(const char *name) {
     if (!g_prof_on) return;
     ProfRec r{name, prof_event(), prof_event()};

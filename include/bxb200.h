@@ -194,8 +194,10 @@ int bxg_itree_find(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, cons
                    int64_t nq, int loc, int64_t *total);
 int bxg_itree_fetch(bxg_itree_t *t, int64_t *offsets /* nq+1 */, int32_t *hits /* total */);   /* to host */
 /* find implementation: 1 = single-pass kernel (count + decoupled look-back scan + fill in one launch), 0 = count kernel /
- * CUB scan / fill kernel, -1 (default) = auto: three-pass for bxg_itree_find, single-pass for the chunk-pipelined
- * bxg_itree_find_host (the measured winners).  Same results in every mode; env BXB200_FIND_MODE overrides. */
+ * CUB scan / fill kernel back to back, 2 = the same three passes with the count of chunk k+1 and the fill of chunk k
+ * overlapped on two streams (measured slower, kept for A/B), -1 (default) = auto: three-pass for bxg_itree_find,
+ * single-pass for the chunk-pipelined bxg_itree_find_host (the measured winners).  Same results in every mode; env
+ * BXB200_FIND_MODE overrides. */
 int bxg_set_find_mode(int mode);
 /* The same find for HOST query arrays with the PCIe copies overlapped with the kernels (queries are processed in
  * chunks on copy-in / compute / copy-out streams).  *offsets (nq+1 int64) and *hits (*total int32) point into pinned

@@ -70,7 +70,7 @@ def test_find_single_pass_and_three_pass_agree(bx, orc):
     ooff, ohits = orc.OracleIntervalTree(s, e).find(qs, qe)
     L = bx.lib.lib()
     try:
-        for mode in (0, 1):
+        for mode in (0, 1, 2, -1):                      # 2 / auto: count and fill of different chunks overlapped on two streams
             bx.lib.check(L.bxg_set_find_mode(mode))
             t = tree_of(bx, s, e)                       # fresh index: first find must grow its hit buffers
             off, hits = t.find_batch(qs, qe)            # pipelined host path, 2 chunks
@@ -83,6 +83,14 @@ def test_find_single_pass_and_three_pass_agree(bx, orc):
             off2 = np.empty(nq + 1, np.int64); hits2 = np.empty(total.value, np.int32)
             bx.lib.check(L.bxg_itree_fetch(h, bx.lib.ptr(off2), bx.lib.ptr(hits2)))
             assert np.array_equal(off2, ooff) and np.array_equal(hits2, ohits), mode
+            # a second, larger batch on the same index outgrows the hit buffer: the speculative fills back off and re-run
+            big_s, big_e = np.concatenate([qs, qs[:700_000]]), np.concatenate([qe, qe[:700_000] + 5000])
+            bx.lib.check(L.bxg_itree_find(h, None, bx.lib.ptr(big_s), bx.lib.ptr(big_e), len(big_s), bx.lib.HOST, C.byref(total)))
+            off3 = np.empty(len(big_s) + 1, np.int64); hits3 = np.empty(total.value, np.int32)
+            bx.lib.check(L.bxg_itree_fetch(h, bx.lib.ptr(off3), bx.lib.ptr(hits3)))
+            assert np.array_equal(off3[:nq + 1], ooff) and np.array_equal(hits3[:ooff[-1]], ohits), mode
+            boff, bhits = orc.OracleIntervalTree(s, e).find(big_s[nq:], big_e[nq:])
+            assert np.array_equal(off3[nq:] - off3[nq], boff) and np.array_equal(hits3[ooff[-1]:], bhits), mode
     finally:
         bx.lib.check(L.bxg_set_find_mode(-1))
 
