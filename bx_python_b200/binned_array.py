@@ -12,6 +12,10 @@ Scalar ``set`` calls are queued on the host and flushed as one ``bxg_scores_set_
 write wins) before anything reads the track.  Bulk callers use ``set_many`` / ``set_spans`` / ``get_many``.  The
 track plugs straight into ``bx_python_b200.aggregate`` (``ScoreTrack`` protocol: ``_h`` after ``_flush()``).
 
+``FileBinnedArray`` uploads every stored bin when it is opened (the reference reads bins lazily behind an LRU of 32,
+:214-222; its ``cache`` argument is accepted and ignored here): opening a chromosome costs one decompress + H2D of the
+whole track, after which every ``get`` / ``get_range`` / aggregate launch finds it resident.
+
 Only ``typecode="f"`` (float32, what the aggregate path stores) lives on the device; other typecodes raise
 ``NotImplementedError``.  The on-disk format (``to_file`` / ``FileBinnedArray``) is byte-compatible with the
 reference's, version 2, ``zlib`` / ``none`` compression (``lzo`` only if the optional module is importable).
@@ -87,7 +91,15 @@ class _DeviceTrack:
         if self._q_pos:
             pos, val = np.asarray(self._q_pos, np.int64), np.asarray(self._q_val, np.float32)
             self._q_pos, self._q_val = [], []
-            self._apply(pos, None, val)
+            # queued point writes: keep the LAST write of every position and hand the batch over sorted, so the kernel
+            # takes its sorted / disjoint path whatever order `set` was called in (otherwise a few scattered writes would
+            # cost an owner array over their whole bounding range -- ADVICE r1)
+            order = np.argsort(pos, kind="stable")
+            ps = pos[order]
+            last = np.ones(len(ps), bool)
+            last[:-1] = ps[1:] != ps[:-1]
+            sel = order[last]
+            self._apply(pos[sel], None, val[sel])
 
     def _apply(self, start, end, val):
         if len(start) == 0:

@@ -349,14 +349,14 @@ struct SetDesc {
     int32_t bin_size, flat, size;
     int32_t cellbase;      // first locality bucket of this set (bucketed form only)
 };
-struct RangeTriple {
-    int32_t w, s, c;
+struct __align__(16) RangeTriple {      // 16 bytes: one 128-bit load / store per record, in the radix pass too
+    int32_t w, s, c, pad;
 };
 
 // Locality bucket of every range: (set, start >> kshift) flattened over the genome, at most 256 buckets of a few MB of
 // bitmap each.  A file in random order touches the whole genome's bitmaps (386 MB for hg38, three times L2) at random:
 // every edge word's atomicOr pulls its sector from DRAM and every rewritten line goes back to DRAM (ncu r02b: 6.0 GB read +
-// 7.6 GB written for 50 M ranges).  Processed bucket by bucket -- one 8-bit radix pass over 13-byte records -- the same
+// 7.6 GB written for 50 M ranges).  Processed bucket by bucket -- one 8-bit radix pass over 17-byte (key + 16-byte record) pairs -- the same
 // atomics and stores hit lines that are still in L2.
 __global__ void __launch_bounds__(256)
 k_range_buckets(const SetDesc *__restrict__ descs, int nsets, int kshift, int group, const int32_t *__restrict__ which,
@@ -371,7 +371,7 @@ k_range_buckets(const SetDesc *__restrict__ descs, int nsets, int kshift, int gr
             k = k < 0 ? 0 : (k > 255 ? 255 : k);
         }
         keys[i] = (uint8_t)k;
-        vals[i] = RangeTriple{w, s, c};
+        vals[i] = RangeTriple{w, s, c, 0};
     }
 }
 
@@ -391,6 +391,60 @@ constexpr int64_t LANE_WORDS = 64;               // interiors up to 512 bytes ar
 
 // DEFER_STATE: the bin states are not touched here; the caller runs k_mark_touched_bins afterwards.  (The per-range form
 // needs two integer divisions by the run-time bin size; on a whole file those were most of the kernel's instructions.)
+// Bucketed form (records from k_range_buckets + the radix pass; bin states deferred to k_mark_touched_bins).  No barriers,
+// no shared memory: every thread takes SET_ILP consecutive tiles' records at once (their loads and the descriptor lookups
+// are independent, so four ranges per thread are in flight), does the edge words with atomicOr and writes BED-sized
+// interiors itself with full-sector stores; only an interior above 512 bytes is swept by the whole warp.
+constexpr int SET_ILP = 4;
+__global__ void __launch_bounds__(256)
+k_set_ranges_bucketed(const SetDesc *__restrict__ descs, int nsets, const RangeTriple *__restrict__ recs, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockDim.x * SET_ILP;
+    for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {     // warp-uniform trip count
+        RangeTriple r[SET_ILP];
+#pragma unroll
+        for (int j = 0; j < SET_ILP; j++) {
+            const int64_t i = base + (int64_t)j * blockDim.x + threadIdx.x;
+            r[j] = i < n ? recs[i] : RangeTriple{-1, 0, 0, 0};
+        }
+#pragma unroll
+        for (int j = 0; j < SET_ILP; j++) {
+            int64_t mb = 0, me = 0;
+            uint64_t *words = nullptr;
+            const int32_t t = r[j].w, s = r[j].s, c = r[j].c;
+            if (t >= 0 && t < nsets && c > 0 && s >= 0) {
+                const SetDesc d = descs[t];
+                if ((int64_t)s + c <= d.size) {
+                    words = d.words;
+                    const int32_t last = s + c - 1;
+                    const int64_t w0 = s >> 6, w1 = last >> 6;
+                    const unsigned long long m0 = ~0ull << (s & 63), m1 = ~0ull >> (63 - (last & 63));
+                    if (w0 == w1) {
+                        atomicOr((unsigned long long *)words + w0, m0 & m1);
+                    } else {
+                        atomicOr((unsigned long long *)words + w0, m0);
+                        atomicOr((unsigned long long *)words + w1, m1);
+                    }
+                    mb = w0 + 1;
+                    me = w1;
+                    if (me - mb <= LANE_WORDS) {
+                        fill_interior(words, mb, me);
+                        me = mb;
+                    }
+                }
+            }
+            unsigned has = __ballot_sync(0xffffffffu, me > mb);          // long interiors: the warp sweeps them together
+            while (has) {
+                const int src = __ffs(has) - 1;
+                has &= has - 1;
+                const int64_t b = __shfl_sync(0xffffffffu, mb, src), e = __shfl_sync(0xffffffffu, me, src);
+                uint64_t *w = (uint64_t *)__shfl_sync(0xffffffffu, (unsigned long long)words, src);
+                for (int64_t k = b + lane; k < e; k += 32) w[k] = ~0ull;
+            }
+        }
+    }
+}
+
 // AOS (bucketed, L2-resident targets): every lane writes its own interior -- the kernel is instruction-bound there and this
 // form needs no per-range loop over the warp (4.1 -> 3.2 ms per 50 M ranges, r02g).  Unbucketed (DRAM-bound) input keeps
 // the warp-wide coalesced sweep: scattered sector stores cost it more DRAM traffic than they save instructions (5.1 -> 6.3 ms).
@@ -1131,8 +1185,8 @@ int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int3
                                                  (const RangeTriple *)d_v0, (RangeTriple *)d_v1, n, 0, 8, c.stream));
         prof_end();
         c.launches += 3;
-        BXG_LAUNCH((k_set_ranges_multi<true, true>), grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets,
-                   (const int32_t *)d_v1, (const int32_t *)nullptr, (const int32_t *)nullptr, n);
+        BXG_LAUNCH(k_set_ranges_bucketed, grid_for(cdiv(n, 256 * SET_ILP), 8), 256, 0, (const SetDesc *)d_desc, nsets,
+                   (const RangeTriple *)d_v1, n);
     } else if (defer) {
         BXG_LAUNCH((k_set_ranges_multi<false, true>), grid_for(cdiv(n, 256), 8), 256, 0, (const SetDesc *)d_desc, nsets,
                    (const int32_t *)dw, (const int32_t *)ds, (const int32_t *)dc, n);
