@@ -349,14 +349,14 @@ struct SetDesc {
     int32_t bin_size, flat, size;
     int32_t cellbase;      // first locality bucket of this set (bucketed form only)
 };
-struct __align__(16) RangeTriple {      // 16 bytes: one 128-bit load / store per record, in the radix pass too
-    int32_t w, s, c, pad;
+struct RangeTriple {                    // 12 bytes (a 16-byte aligned record made the radix pass slower: 0.67 -> 0.78 ms, r02p)
+    int32_t w, s, c;
 };
 
 // Locality bucket of every range: (set, start >> kshift) flattened over the genome, at most 256 buckets of a few MB of
 // bitmap each.  A file in random order touches the whole genome's bitmaps (386 MB for hg38, three times L2) at random:
 // every edge word's atomicOr pulls its sector from DRAM and every rewritten line goes back to DRAM (ncu r02b: 6.0 GB read +
-// 7.6 GB written for 50 M ranges).  Processed bucket by bucket -- one 8-bit radix pass over 17-byte (key + 16-byte record) pairs -- the same
+// 7.6 GB written for 50 M ranges).  Processed bucket by bucket -- one 8-bit radix pass over 13-byte (key + record) pairs -- the same
 // atomics and stores hit lines that are still in L2.
 __global__ void __launch_bounds__(256)
 k_range_buckets(const SetDesc *__restrict__ descs, int nsets, int kshift, int group, const int32_t *__restrict__ which,
@@ -371,7 +371,7 @@ k_range_buckets(const SetDesc *__restrict__ descs, int nsets, int kshift, int gr
             k = k < 0 ? 0 : (k > 255 ? 255 : k);
         }
         keys[i] = (uint8_t)k;
-        vals[i] = RangeTriple{w, s, c, 0};
+        vals[i] = RangeTriple{w, s, c};
     }
 }
 
@@ -405,7 +405,7 @@ k_set_ranges_bucketed(const SetDesc *__restrict__ descs, int nsets, const RangeT
 #pragma unroll
         for (int j = 0; j < SET_ILP; j++) {
             const int64_t i = base + (int64_t)j * blockDim.x + threadIdx.x;
-            r[j] = i < n ? recs[i] : RangeTriple{-1, 0, 0, 0};
+            r[j] = i < n ? recs[i] : RangeTriple{-1, 0, 0};
         }
 #pragma unroll
         for (int j = 0; j < SET_ILP; j++) {
