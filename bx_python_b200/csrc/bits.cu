@@ -1185,6 +1185,8 @@ int bxg_bits_set_ranges_multi(bxg_bits_t *const *sets, int32_t nsets, const int3
                                                  (const RangeTriple *)d_v0, (RangeTriple *)d_v1, n, 0, 8, c.stream));
         prof_end();
         c.launches += 3;
+        // (8 CTAs per SM although 6 are resident: a grid of exactly the resident CTAs measured slower, 2.06 -> 2.37 ms, r02t --
+        //  ranges differ in length, late CTAs even out the tail)
         BXG_LAUNCH(k_set_ranges_bucketed, grid_for(cdiv(n, 256 * SET_ILP), 8), 256, 0, (const SetDesc *)d_desc, nsets,
                    (const RangeTriple *)d_v1, n);
     } else if (defer) {
