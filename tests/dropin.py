@@ -3,6 +3,7 @@ dropin.py -- harness that runs the reference's OWN unit tests and scripts, unmod
 
     python tests/dropin.py --impl b200|reference unittests              -> JSON {rc, passed, failed, modules}
     python tests/dropin.py --impl b200|reference script NAME WORKDIR ARG...   -> the script's stdout (meta on stderr)
+    python tests/dropin.py --impl b200|reference operations SEED              -> JSON rows of the reference's interval operations
 
   --impl reference : the compiled unmodified reference (oracle/_ref/bx/*.so) + its pure-Python package (oracle/_ref/pylib)
   --impl b200      : the same pure-Python package with bx.bitset / bx.intervals.intersection (and, for the aggregate
@@ -160,6 +161,51 @@ def run_script(name, workdir, argv):
     return 0
 
 
+def run_operations(seed):
+    """The reference's own interval operations (oracle/_ref/pylib/bx/intervals/operations/*.py over its NiceReaderWrapper /
+    GenomicIntervalReader.binned_bitsets, lib/bx/intervals/io.py:190-216) on synth.ops_case(seed) -- exactly what
+    tests/golden/make_golden.py:golden_operations recorded from the compiled reference."""
+    sys.path.insert(0, ROOT)
+    from bx_python_b200 import synth
+    from bx.intervals.io import GenomicInterval, NiceReaderWrapper
+    from bx.intervals.operations.base_coverage import base_coverage
+    from bx.intervals.operations.complement import complement
+    from bx.intervals.operations.coverage import coverage
+    from bx.intervals.operations.intersect import intersect
+    from bx.intervals.operations.merge import merge
+    from bx.intervals.operations.subtract import subtract
+
+    def rd(lines):
+        return NiceReaderWrapper(iter([ln + "\n" for ln in lines]), chrom_col=0, start_col=1, end_col=2, strand_col=5,
+                                 fix_strand=True)
+
+    def rows(gen):
+        out = []
+        for r in gen:
+            if isinstance(r, GenomicInterval):
+                out.append([str(f).rstrip("\n") for f in r.fields])
+            elif isinstance(r, list):
+                out.append([str(f) for f in r])
+        return out
+    p, s2, s3, lens = synth.ops_case(seed)
+    c = {"seed": seed}
+    for pieces in (True, False):
+        for mincols in (1, 40):
+            key = f"pieces{int(pieces)}_min{mincols}"
+            c["intersect_" + key] = rows(intersect([rd(p), rd(s2)], mincols=mincols, pieces=pieces, lens=lens))
+            c["subtract_" + key] = rows(subtract([rd(p), rd(s2)], mincols=mincols, pieces=pieces, lens=lens))
+    c["intersect3"] = rows(intersect([rd(p), rd(s2), rd(s3)], lens=lens))
+    c["subtract3"] = rows(subtract([rd(p), rd(s2), rd(s3)], lens=lens))
+    c["merge"] = rows(merge(rd(p)))
+    c["complement"] = rows(complement(rd(s2), lens))
+    c["coverage"] = rows(coverage([rd(p), rd(s2)]))
+    c["coverage3"] = rows(coverage([rd(p), rd(s2), rd(s3)]))
+    c["base_coverage"] = int(base_coverage(rd(p)))
+    c["modules"] = modules_report()
+    print(json.dumps(c))
+    return 0
+
+
 def main(args):
     assert args[0] == "--impl" and args[1] in ("b200", "reference"), __doc__
     impl, cmd, rest = args[1], args[2], args[3:]
@@ -172,6 +218,8 @@ def main(args):
         return run_unittests()
     if cmd == "script":
         return run_script(rest[0], rest[1], rest[2:])
+    if cmd == "operations":
+        return run_operations(int(rest[0]))
     raise SystemExit(__doc__)
 
 

@@ -43,3 +43,14 @@ def test_shadow_refuses_late_install():
             "try:\n    s.install()\nexcept RuntimeError as e:\n    print('refused')\n") % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert "refused" in r.stdout, r.stderr[-1500:]
+
+
+@needs_ref
+def test_operations_goldens_reproducible():
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "operations.json")))[1]
+    r = subprocess.run([sys.executable, HARNESS, "--impl", "reference", "operations", "1"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    got.pop("modules")
+    assert got == gold

@@ -58,3 +58,19 @@ def test_reference_script_output_identical(workdir, k):
     got = r.stdout.splitlines()
     assert len(got) == len(g["stdout"]), (len(got), len(g["stdout"]))
     assert got == g["stdout"]                                                             # ... and printed the same lines
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_reference_interval_operations_run_on_the_shim(seed):
+    """lib/bx/intervals/operations/{intersect,subtract,merge,complement,coverage,base_coverage}.py and
+    GenomicIntervalReader.binned_bitsets (lib/bx/intervals/io.py:190-216), unmodified, on the shadowed bx.bitset: row for row
+    what they produce on the compiled reference (tests/golden/operations.json)."""
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "operations.json")))[seed]
+    r = subprocess.run([sys.executable, HARNESS, "--impl", "b200", "operations", str(seed)], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    assert got.pop("modules")["bx.bitset"].endswith("bx_python_b200/bitset.py")
+    assert sorted(got) == sorted(gold)
+    for k in gold:
+        assert got[k] == gold[k], k
