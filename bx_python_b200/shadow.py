@@ -55,9 +55,14 @@ def install(scores: bool = False, operations: bool = False) -> dict:
                                "bx_python_b200.shadow.install() before anything imports it")
         sys.modules[name] = mod
         done[name] = mod
-    for name, mod in done.items():
-        parent, _, leaf = name.rpartition(".")
-        setattr(importlib.import_module(parent), leaf, mod)
+    try:
+        for name, mod in done.items():
+            parent, _, leaf = name.rpartition(".")
+            setattr(importlib.import_module(parent), leaf, mod)
+    except ImportError:
+        for name in done:                              # no `bx` package to shadow: leave sys.modules as it was
+            sys.modules.pop(name, None)
+        raise
     return done
 
 
