@@ -46,6 +46,8 @@ SCRIPT_RUNS = [
     ("bed_coverage", ["a.bed", "b.bed"], False),
     ("bed_coverage_by_interval", ["a.bed", "b.bed"], False),
     ("bed_coverage_by_interval", ["a.bed", "b.bed", "mask.bed"], False),
+    ("bed_diff_basewise_summary", ["a.bed", "b.bed"], False),
+    ("bed_count_by_interval", ["a.bed", "b.bed"], False),
 ]
 
 

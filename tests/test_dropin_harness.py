@@ -27,7 +27,7 @@ def test_reference_unit_tests_in_harness():
 
 
 @needs_ref
-@pytest.mark.parametrize("k", [0, 1, 5, 7, 10, 13])
+@pytest.mark.parametrize("k", [0, 1, 5, 7, 10, 13, 14, 15])
 def test_script_goldens_reproducible(tmp_path, k):
     dropin.make_inputs(str(tmp_path), GOLD["inputs_seed"])
     name, argv, _ = dropin.SCRIPT_RUNS[k]
