@@ -112,7 +112,41 @@ int main(void) {
     CHK(bxg_bits_count_all(g[0], &c0));
     CHK(bxg_bits_count_all(g[1], &c1));
     printf("multi %lld %lld\n", (long long)c0, (long long)c1);
+    /* the bed_intersect counting pass in three calls: per-line count_range on the genome, the per-chromosome counters
+     * (lines with >= mincols covered bases, covered bases), whole-bitmap counts; then pieces inside ranges and clear */
+    int32_t qw[4] = {0, 1, 1, 5}, qst[4] = {0, 0, 390, 0}, qct[4] = {100, 500, 100, 10}, per_line[4];
+    CHK(bxg_bits_count_ranges_multi(g, 2, qw, qst, qct, 4, per_line, 0, BXG_HOST));
+    printf("per_line %d %d %d %d\n", per_line[0], per_line[1], per_line[2], per_line[3]);
+    int64_t stats[4] = {0, 0, 0, 0}, all2[2] = {0, 0};
+    CHK(bxg_group_stats_i32(qw, per_line, 4, 2, 50, stats, BXG_HOST));
+    printf("stats %lld %lld %lld %lld\n", (long long)stats[0], (long long)stats[1], (long long)stats[2], (long long)stats[3]);
+    CHK(bxg_bits_count_all_multi(g, 2, all2, 1, BXG_HOST));
+    printf("all_multi %lld %lld\n", (long long)all2[0], (long long)all2[1]);
+    int32_t rrs[2] = {0, 350}, rre[2] = {450, 500};
+    int64_t roff[3], rtotal = 0;
+    CHK(bxg_bits_runs_in_ranges(g[1], rrs, rre, 2, 1, BXG_HOST, roff, &rtotal));
+    int32_t ps2[8], pe2[8];
+    CHK(bxg_bits_runs_in_ranges_fetch(g[1], ps2, pe2, rtotal));
+    printf("pieces %lld |", (long long)rtotal);
+    for (int q = 0; q < 2; q++) {
+        for (int64_t k = roff[q]; k < roff[q + 1]; k++) printf(" %d:%d-%d", q, ps2[k], pe2[k]);
+    }
+    printf("\n");
+    CHK(bxg_bits_clear(g[1]));
+    CHK(bxg_bits_count_all(g[1], &c1));
+    printf("cleared %lld\n", (long long)c1);
     CHK(bxg_bits_free(g[0]));
     CHK(bxg_bits_free(g[1]));
+
+    /* scalar IntervalTree.find through the one-call entry point (hit list in mapped host memory) */
+    bxg_itree_t *t1;
+    CHK(bxg_itree_create(&t1));
+    CHK(bxg_itree_build(t1, NULL, s, e, 5, 1, BXG_HOST));
+    const int32_t *h1;
+    int64_t n1 = bxg_itree_find1(t1, 0, 19, 21, &h1);
+    printf("find1 %lld:", (long long)n1);
+    for (int64_t k = 0; k < n1; k++) printf(" %d", h1[k]);
+    printf("\n");
+    CHK(bxg_itree_free(t1));
     return 0;
 }

@@ -47,4 +47,7 @@ def test_c_client(tmp_path):
     o = orc.summarize([0, 5, 9], [5, 8, 20], [1.5, 2.5, -1.0], 0, 21, 3, 0.0, 0.0)
     exp.append("summary %g %g %g | %g %g %g | %g %g %g" % (*o["valid_count"], *o["sum_data"], *o["sum_squares"]))
     exp.append("multi 300 120")
+    # g[0] = [0,300) of 1000, g[1] = [10,30) + [400,500) of 500; lines: (0: 0+100) (1: 0+500) (1: 390+100) (5: no such set)
+    exp += ["per_line 100 120 90 0", "stats 1 100 2 210", "all_multi 300 120",
+            "pieces 3 | 0:10-30 0:400-450 1:400-500", "cleared 0", "find1 2: 0 4"]
     assert lines == exp
