@@ -87,6 +87,8 @@ SIGNATURES = {
     "bxg_itree_find_host32": [vp, vp, vp, vp, i64, pvp, pvp, pi64],
     "bxg_itree_find_small": [vp, vp, vp, vp, i32, pvp, pvp, pi64],
     "bxg_itree_find1": [vp, i32, i32, i32, pvp],
+    "bxg_set_find_server": [cint],
+    "bxg_find_server_stats": [pi64, pi64, pi32],
     "bxg_itree_result_dev": [vp, pvp, pvp, pi64, pi64],
     "bxg_itree_count": [vp, vp, vp, vp, i64, cint, vp, pi64],
     "bxg_itree_neighbors": [vp, vp, vp, vp, vp, i64, cint, cint, pi64],

@@ -25,6 +25,9 @@ constexpr int MAX_LEVELS = 6;          // 32^7 > 2^31
 constexpr int MAX_SPLIT = 4096;        // splitter entries per array (16 KB each in shared memory)
 constexpr int SMEM_TREES = 256;        // toff entries cached in shared memory
 constexpr int FIND_THREADS = 256;
+#ifndef BXB200_FIND_SERVER_DEFAULT
+#define BXB200_FIND_SERVER_DEFAULT 1   // scalar find through the lingering server kernel (BXB200_FIND_SERVER=0/1 overrides)
+#endif
 #ifndef FIND_MIN_CTAS
 #define FIND_MIN_CTAS 7            // co-resident CTAs per SM the find kernels are compiled for (register budget 36; the
                                    // direct-address search needs 38-40 without a cap and no shared-memory table, so occupancy is
@@ -107,6 +110,8 @@ struct bxg_itree {
     long long *md_off = nullptr;            // their device addresses
     int32_t *md_hits = nullptr;
     long long m_seq = 0;
+    int srv_slot = -1;                      // descriptor slot of the lingering find server (-1: none yet)
+    bool srv_dirty = true;                  // the slot's descriptor does not describe the current arrays
     // the staged query arrays of the last find (device pointers valid until the next call)
     IndexView view() const {
         IndexView v;
@@ -818,7 +823,32 @@ k_find_fused(const __grid_constant__ IndexView ix, const int32_t *__restrict__ q
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
+// the lingering find server (see k_find_server below)
+struct FindDesc {
+    IndexView ix;
+    int32_t *out_hits;
+};
+constexpr int SRV_SLOTS = 256;
+constexpr uint32_t SRV_KILL = 0xffffffffu, SRV_OVERFLOW = 0xffffffffu;
+
+struct FindServer {
+    FindDesc *d_table = nullptr;
+    unsigned long long *m = nullptr, *md = nullptr;   // the six mailbox words (host / device address)
+    cudaStream_t stream = nullptr;
+    uint32_t seq = 0;
+    unsigned long long gen = 0;                        // generation of the last launch (0: never launched)
+    bxg_itree *owner[SRV_SLOTS] = {};
+    int enabled = -1;
+    unsigned idle_us = 100;
+    long long launches = 0, requests = 0;
+};
+static FindServer g_srv;
+
+static void server_stop();
+
 static void free_index(bxg_itree *t) {
+    server_stop();                          // a lingering find server may hold descriptors of these arrays
+    t->srv_dirty = true;
     cudaFree(t->S); cudaFree(t->E); cudaFree(t->I); cudaFree(t->PM); cudaFree(t->toff); cudaFree(t->split);
     cudaFree(t->G); cudaFree(t->G16); cudaFree(t->dir);
     t->G = nullptr; t->G16 = nullptr; t->dir = nullptr; t->dir_bytes = t->dir_grid_off = 0; t->ncells_total = 0;
@@ -966,7 +996,8 @@ int bxg_itree_create(bxg_itree_t **out) {
 int bxg_itree_free(bxg_itree_t *t) {
     if (!t) return BXG_OK;
     cudaStreamSynchronize(ctx().stream);
-    free_index(t);
+    free_index(t);                          // (stops a lingering find server)
+    if (t->srv_slot >= 0) g_srv.owner[t->srv_slot] = nullptr;
     cudaFree(t->d_cnt); cudaFree(t->d_lo); cudaFree(t->d_hi); cudaFree(t->d_off); cudaFree(t->d_hits);
     cudaFree(t->d_mask);
     if (t->s_in) {
@@ -1799,18 +1830,234 @@ static int wait_small(bxg_itree *t, long long seq) {
     return BXG_OK;
 }
 
+static int small_buffers(bxg_itree *t) {
+    if (t->m_off) return BXG_OK;
+    BXG_CUDA(cudaHostAlloc((void **)&t->m_off, (SMALL_Q + 3) * sizeof(long long), cudaHostAllocMapped));
+    BXG_CUDA(cudaHostAlloc((void **)&t->m_hits, (size_t)SMALL_CAP * 4, cudaHostAllocMapped));
+    BXG_CUDA(cudaHostGetDevicePointer((void **)&t->md_off, t->m_off, 0));
+    BXG_CUDA(cudaHostGetDevicePointer((void **)&t->md_hits, t->m_hits, 0));
+    t->m_off[SMALL_Q + 2] = 0;
+    t->m_seq = 0;
+    return BXG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Lingering find server.  The loop `for line in file: tree.find(start, end)` (scripts/bed_count_overlapping.py:27-33,
+// bed_intersect.py without -b ...) pays one kernel launch per call on the path above: ~2.5 us of driver work on the host
+// plus ~3 us until the GPU front end starts the kernel, more than the query itself.  The server is a one-warp kernel that,
+// once launched for a scalar find, stays resident and polls a 32-byte request line in mapped host memory; the next calls
+// are a few plain stores into that line and a spin on the response word -- no launch.  It leaves by itself after
+// `idle_us` without a request (so cudaFree / cudaDeviceSynchronize wait at most that long), when told to (any index
+// rebuild or free), and is relaunched on demand with the request that found it gone.
+//
+//   request  words 0..3 : {slot, start, end, tree} each as (seq << 32 | value) -- every 8-byte word carries the sequence
+//                         number, so a poll that catches the line half-written sees mixed sequence numbers and retries
+//                         (host stores of aligned 8-byte words are atomic; no ordering between them is needed)
+//   response word 4     : (seq << 32 | number of hits) or (seq << 32 | 0xffffffff) when the hits exceed SMALL_CAP;
+//                         written after a system fence behind the hit ids (mapped memory of the index)
+//   exit     word 5     : the generation the host gave this launch, written last; after that the kernel touches nothing
+//
+// The indexes are reached through a device table of descriptors (slot = one index); a descriptor only changes while no
+// server runs (server_stop first), so the server may cache it.  One host thread at a time, like the rest of the library.
+// ------------------------------------------------------------------------------------------------------------------
+extern "C++" {
+static bool server_enabled() {
+    if (g_srv.enabled < 0) {
+        const char *e = getenv("BXB200_FIND_SERVER");
+        g_srv.enabled = e ? (e[0] == '1') : BXB200_FIND_SERVER_DEFAULT;
+        const char *i = getenv("BXB200_FIND_SERVER_IDLE_US");
+        if (i && atoi(i) > 0) g_srv.idle_us = (unsigned)atoi(i);
+    }
+    return g_srv.enabled == 1;
+}
+
+static inline unsigned long long srv_word(const volatile unsigned long long *p) { return *p; }
+static bool server_alive() { return g_srv.gen != 0 && srv_word(g_srv.m + 5) != g_srv.gen; }
+
+static void server_post(uint32_t slot, int32_t a, int32_t b, int32_t c) {
+    const unsigned long long k = (unsigned long long)(++g_srv.seq) << 32;
+    __atomic_store_n(g_srv.m + 0, k | slot, __ATOMIC_RELAXED);
+    __atomic_store_n(g_srv.m + 1, k | (uint32_t)a, __ATOMIC_RELAXED);
+    __atomic_store_n(g_srv.m + 2, k | (uint32_t)b, __ATOMIC_RELAXED);
+    __atomic_store_n(g_srv.m + 3, k | (uint32_t)c, __ATOMIC_RELEASE);
+}
+
+__device__ __forceinline__ unsigned long long srv_timer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(32)
+k_find_server(const FindDesc *__restrict__ table, unsigned long long *mbox, uint32_t last_seq, unsigned long long gen,
+              unsigned long long idle_ns) {
+    const int lane = threadIdx.x;
+    unsigned long long t_last = srv_timer();
+    // the poll count is a second, clock-independent bound on the kernel's life (a poll is a PCIe read, >= ~0.5 us)
+    for (unsigned long long polls = 0; polls < (idle_ns >> 4) + (1u << 16); polls++) {
+        unsigned long long w = 0;
+        if (lane < 4) w = *(volatile unsigned long long *)(mbox + lane);
+        const uint32_t sq = (uint32_t)(w >> 32), val = (uint32_t)w;
+        const uint32_t s0 = __shfl_sync(0xffffffffu, sq, 0);
+        const bool whole = __all_sync(0xffffffffu, lane >= 4 || sq == s0);
+        if (whole && s0 != last_seq) {
+            last_seq = s0;
+            const uint32_t slot = __shfl_sync(0xffffffffu, val, 0);
+            const int32_t qs = (int32_t)__shfl_sync(0xffffffffu, val, 1), qe = (int32_t)__shfl_sync(0xffffffffu, val, 2);
+            const int32_t t = (int32_t)__shfl_sync(0xffffffffu, val, 3);
+            if (slot == SRV_KILL || slot >= SRV_SLOTS) break;
+            if (lane == 0) {
+                const IndexView &ix = table[slot].ix;
+                uint32_t lo = 0, hi = 0;
+                int c = 0;
+                if (t >= 0 && t < ix.ntrees) {
+                    const uint32_t seg_lo = (uint32_t)ix.toff[t], seg_hi = (uint32_t)ix.toff[t + 1];
+                    const bxs::GridDir gd = reinterpret_cast<const bxs::GridDir *>(ix.dir + ix.dir_grid_off)[t];
+                    bxs::search_walk_grid16(ix.G16, gd, ix.S, seg_lo, seg_hi, qe, qs, ix.E, ix.M, ix.nlev,
+                                            [](const bxs::GridRec16 *p) { return *p; }, Ld8(), Ld1(), hi, lo,
+                                            [&](uint32_t, unsigned m) { c += __popc(m); });
+                }
+                if (c > 0 && c <= SMALL_CAP) {
+                    int32_t *dst = table[slot].out_hits;
+                    bxs::walk_hits_halves(ix.E, ix.M, ix.nlev, lo, hi, qs, Ld8(), Ld1(), [&](uint32_t k0, unsigned m) {
+                        bxs::PtrSink out{dst};
+                        bxs::emit_group_halves_to(ix.I, k0, m, out, Ld8());
+                        dst = out.p;
+                    });
+                }
+                __threadfence_system();                       // the hit ids before the response word
+                *(volatile unsigned long long *)(mbox + 4) =
+                    ((unsigned long long)s0 << 32) | (c <= SMALL_CAP ? (uint32_t)c : SRV_OVERFLOW);
+            }
+            __syncwarp();
+            t_last = srv_timer();
+            polls = 0;
+        } else if (__any_sync(0xffffffffu, srv_timer() - t_last > idle_ns)) {   // (one decision for the whole warp)
+            break;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_system();
+        *(volatile unsigned long long *)(mbox + 5) = gen;      // last: the host may relaunch from here on
+    }
+}
+
+static int server_launch() {
+    FindServer &s = g_srv;
+    ++s.gen;
+    ++s.launches;
+    k_find_server<<<1, 32, 0, s.stream>>>(s.d_table, s.md, s.seq - 1, s.gen, (unsigned long long)s.idle_us * 1000ull);
+    BXG_CUDA(cudaGetLastError());
+    return BXG_OK;
+}
+
+// tell a lingering server to leave and wait until it has (a few microseconds; bounded by its idle time-out in any case)
+static void server_stop() {
+    FindServer &s = g_srv;
+    if (!s.m || !server_alive()) return;
+    server_post(SRV_KILL, 0, 0, 0);
+    for (int spin = 0; spin < 2000000; spin++) {
+        if (srv_word(s.m + 5) == s.gen) return;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    cudaStreamSynchronize(s.stream);
+}
+
+static int server_init() {
+    FindServer &s = g_srv;
+    if (s.m) return BXG_OK;
+    BXG_CUDA(cudaMalloc((void **)&s.d_table, sizeof(FindDesc) * SRV_SLOTS));
+    BXG_CUDA(cudaHostAlloc((void **)&s.m, 64, cudaHostAllocMapped));
+    BXG_CUDA(cudaHostGetDevicePointer((void **)&s.md, s.m, 0));
+    for (int i = 0; i < 8; i++) s.m[i] = 0;
+    BXG_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    return BXG_OK;
+}
+
+// -> number of hits (>= 0), a negative status, or FIND1_NO_SERVER when this index cannot use the server
+constexpr int64_t FIND1_NO_SERVER = INT64_MIN;
+static int64_t find1_server(bxg_itree *t, int32_t tree, int32_t start, int32_t end, const int32_t **hits) {
+    FindServer &s = g_srv;
+    if (int rc = server_init()) return rc;
+    if (!t->m_off) server_stop();           // (pinned allocations wait for resident kernels)
+    if (int rc = small_buffers(t)) return rc;
+    if (t->srv_slot < 0) {
+        for (int k = 0; k < SRV_SLOTS && t->srv_slot < 0; k++)
+            if (!s.owner[k]) {
+                s.owner[k] = t;
+                t->srv_slot = k;
+            }
+        if (t->srv_slot < 0) return FIND1_NO_SERVER;
+        t->srv_dirty = true;
+    }
+    if (t->srv_dirty) {
+        server_stop();
+        const FindDesc d{t->view(), t->md_hits};
+        if (cudaMemcpyAsync(s.d_table + t->srv_slot, &d, sizeof d, cudaMemcpyHostToDevice, ctx().stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx().stream) != cudaSuccess)      // also: the build's kernels have finished
+            return set_error(BXG_ERR_CUDA, "find server: descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        t->srv_dirty = false;
+    }
+    ++s.requests;
+    server_post((uint32_t)t->srv_slot, start, end, tree);
+    const uint32_t want = s.seq;
+    if (!server_alive())
+        if (int rc = server_launch()) return rc;
+    for (int relaunch = 0; relaunch < 4; relaunch++) {
+        for (long long spin = 0; spin < 4000000; spin++) {
+            unsigned long long r = srv_word(s.m + 4);
+            if ((uint32_t)(r >> 32) != want && srv_word(s.m + 5) == s.gen) {
+                r = srv_word(s.m + 4);                         // it left: the response, if any, was written before the exit word
+                if ((uint32_t)(r >> 32) != want) break;        // left without serving this request -> start another
+            }
+            if ((uint32_t)(r >> 32) == want) {
+                const uint32_t c = (uint32_t)r;
+                if (c == SRV_OVERFLOW) return FIND1_NO_SERVER;
+                if (hits) *hits = t->m_hits;
+                return (int64_t)c;
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (server_alive()) {                                  // no answer and no exit within the spin budget
+            if (cudaStreamSynchronize(s.stream) != cudaSuccess)
+                return set_error(BXG_ERR_CUDA, "find server: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if ((uint32_t)(srv_word(s.m + 4) >> 32) == want) continue;
+        if (int rc = server_launch()) return rc;
+    }
+    return set_error(BXG_ERR_CUDA, "find server did not answer");
+}
+}  // extern "C++"
+
+int bxg_set_find_server(int on) {
+    if (on < -1 || on > 1) return set_error(BXG_ERR_ARG, "find server: 0 (off), 1 (on) or -1 (the default / environment setting)");
+    if (on < 0) {
+        g_srv.enabled = -1;
+        on = server_enabled();
+    }
+    server_enabled();                       // (reads the idle time-out from the environment once)
+    if (!on) server_stop();
+    g_srv.enabled = on;
+    return BXG_OK;
+}
+
+int bxg_find_server_stats(int64_t *launches, int64_t *requests, int32_t *alive) {
+    if (launches) *launches = g_srv.launches;
+    if (requests) *requests = g_srv.requests;
+    if (alive) *alive = g_srv.m && server_alive();
+    return BXG_OK;
+}
+
 int bxg_itree_find_small(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs, const int32_t *qe, int32_t nq,
                          const int64_t **offsets, const int32_t **hits, int64_t *total) {
     if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
     if (nq < 0 || nq > SMALL_Q) return set_error(BXG_ERR_ARG, "bxg_itree_find_small takes 0..%d queries", SMALL_Q);
-    if (!t->m_off) {
-        BXG_CUDA(cudaHostAlloc((void **)&t->m_off, (SMALL_Q + 3) * sizeof(long long), cudaHostAllocMapped));
-        BXG_CUDA(cudaHostAlloc((void **)&t->m_hits, (size_t)SMALL_CAP * 4, cudaHostAllocMapped));
-        BXG_CUDA(cudaHostGetDevicePointer((void **)&t->md_off, t->m_off, 0));
-        BXG_CUDA(cudaHostGetDevicePointer((void **)&t->md_hits, t->m_hits, 0));
-        t->m_off[SMALL_Q + 2] = 0;
-        t->m_seq = 0;
-    }
+    BXG_TRY(small_buffers(t));
     if (nq == 0 || t->n == 0) {
         for (int q = 0; q <= nq; q++) t->m_off[q] = 0;
     } else {
@@ -1836,6 +2083,11 @@ int bxg_itree_find_small(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs
 // The scalar IntervalTree.find(start, end) (intersection.pyx:400-406) with the thinnest possible call: plain integers in,
 // the number of hits (>= 0) or a negative status out; *hits points into the index's mapped result buffer.
 int64_t bxg_itree_find1(bxg_itree_t *t, int32_t tree, int32_t start, int32_t end, const int32_t **hits) {
+    if (!t || !t->built) return set_error(BXG_ERR_STATE, "index not built");
+    if (t->n > 0 && server_enabled() && !prof_enabled()) {
+        const int64_t r = find1_server(t, tree, start, end, hits);
+        if (r != FIND1_NO_SERVER) return r;
+    }
     const int64_t *off = nullptr;
     int64_t total = 0;
     const int rc = bxg_itree_find_small(t, &tree, &start, &end, 1, &off, hits, &total);

@@ -219,6 +219,12 @@ int bxg_itree_find_small(bxg_itree_t *t, const int32_t *qtree, const int32_t *qs
 /* One query, plain integers in: returns the number of hits (>= 0) or a negative status; *hits points into the index's
  * mapped result buffer (valid until its next find).  The thinnest form of IntervalTree.find (intersection.pyx:400-406). */
 int64_t bxg_itree_find1(bxg_itree_t *t, int32_t tree, int32_t start, int32_t end, const int32_t **hits);
+/* bxg_itree_find1 through the lingering find server: a one-warp kernel that stays resident after a scalar find and takes
+ * the next ones from a request line in mapped host memory (no launch per call); it leaves after ~100 us without a request,
+ * on any index rebuild / free, or when switched off here.  Same results either way; env BXB200_FIND_SERVER=0/1 overrides
+ * the built-in default.  stats: launches of the server kernel, requests it was sent, whether one is resident now. */
+int bxg_set_find_server(int on);       /* 1 on, 0 off, -1 back to the default */
+int bxg_find_server_stats(int64_t *launches, int64_t *requests, int32_t *alive);
 int bxg_itree_result_dev(const bxg_itree_t *t, const int64_t **d_offsets, const int32_t **d_hits, int64_t *nq,
                          int64_t *total);
 /* len(find(...)) only (scripts/bed_count_overlapping.py:27-33): int32 counts[nq] written to `counts` (host or device
