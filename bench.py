@@ -1150,9 +1150,10 @@ def bench_scalar_api(db):
     next_us = (time.perf_counter() - t0) / n * 1e6
     return {"find_us_per_call": find_us, "find1_ctypes_us_per_call": find_raw_us, "count_range_us_per_call": count_us,
             "next_set_us_per_call": next_us,
-            "note": "scalar IntervalTree.find / BinnedBitSet.count_range = one launch + one synchronise each (arguments by value / "
-                    "mapped pinned memory, results written by the kernel into mapped pinned memory: no copies); the reference's "
-                    "Cython calls take ~1-4 us -- bulk callers should still use the batched methods"}
+            "note": "scalar IntervalTree.find goes to the lingering find server (a resident one-warp kernel polling a request "
+                    "line in mapped host memory: no launch per call); BinnedBitSet.count_range / next_set = one launch each, "
+                    "completion word in mapped memory; results are written by the kernels into mapped pinned memory (no "
+                    "copies); the reference's Cython calls take ~1-4 us -- bulk callers should still use the batched methods"}
 
 
 def bench_pcie():
